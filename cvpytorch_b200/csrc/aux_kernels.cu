@@ -1,0 +1,327 @@
+// HBM-bound helper kernels around the conv path: boundary layout adapters, stem space-to-depth,
+// SPPF pooling and the YOLOv5 per-anchor decode.  All are plain coalesced/vectorised CUDA; none is GEMM shaped.
+#include <cuda_fp16.h>
+#include <math_constants.h>
+
+#include "internal.h"
+
+namespace cvb {
+
+__device__ __forceinline__ void split_f32(float x, __half* hi, __half* lo) {
+  x = fminf(fmaxf(x, -65504.0f), 65504.0f);
+  const __half h = __float2half_rn(x);
+  *hi = h;
+  *lo = __float2half_rn(x - __half2float(h));
+}
+
+// ------------------------------------------------------------------ NCHW fp32 -> split16 NHWC
+// grid (ceil(W/32), ceil(C/32), B*H), block (32, 8): smem transpose so both sides are coalesced.
+__global__ void nchw_to_split_kernel(const float* __restrict__ src, int B, int C, int H, int W, __half* __restrict__ dst, int pitch,
+                                     long long plane) {
+  __shared__ float tile[32][33];
+  const int bh = blockIdx.z;
+  const int b = bh / H, h = bh % H;
+  const int w0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, w = w0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && w < W) ? src[(((size_t)b * C + c) * H + h) * W + w] : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int w = w0 + i, c = c0 + threadIdx.x;
+    if (w < W && c < C) {
+      __half hi, lo;
+      split_f32(tile[threadIdx.x][i], &hi, &lo);
+      const size_t o = (((size_t)b * H + h) * W + w) * pitch + c;
+      dst[o] = hi;
+      dst[o + plane] = lo;
+    }
+  }
+}
+
+// split16 NHWC -> NCHW fp32 (x = hi + lo)
+__global__ void split_to_nchw_kernel(const __half* __restrict__ src, int B, int C, int H, int W, int pitch, long long plane,
+                                     float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int bh = blockIdx.z;
+  const int b = bh / H, h = bh % H;
+  const int w0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int w = w0 + i, c = c0 + threadIdx.x;
+    float v = 0.0f;
+    if (w < W && c < C) {
+      const size_t o = (((size_t)b * H + h) * W + w) * pitch + c;
+      v = __half2float(src[o]) + __half2float(src[o + plane]);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, w = w0 + threadIdx.x;
+    if (c < C && w < W) dst[(((size_t)b * C + c) * H + h) * W + w] = tile[threadIdx.x][i];
+  }
+}
+
+__global__ void f32nhwc_to_nchw_kernel(const float* __restrict__ src, int B, int C, int H, int W, int pitch, float* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int bh = blockIdx.z;
+  const int b = bh / H, h = bh % H;
+  const int w0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int w = w0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (w < W && c < C) ? src[(((size_t)b * H + h) * W + w) * pitch + c] : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, w = w0 + threadIdx.x;
+    if (c < C && w < W) dst[(((size_t)b * C + c) * H + h) * W + w] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------ stem space-to-depth
+// One thread per output pixel (b, h2, w2): reads a 2x2x3 patch (float2 per row/channel -> coalesced across
+// the warp) and writes 16 channels (12 used) as two 32-byte hi/lo records (coalesced across the warp).
+__global__ void stem_s2d_kernel(const float* __restrict__ src, int B, int H, int W, __half* __restrict__ dst, int pitch,
+                                long long plane) {
+  const int W2 = W >> 1, H2 = H >> 1;
+  const long long n = (long long)B * H2 * W2;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int w2 = (int)(i % W2);
+    const long long t = i / W2;
+    const int h2 = (int)(t % H2);
+    const int b = (int)(t / H2);
+    float v[16];
+#pragma unroll
+    for (int k = 12; k < 16; ++k) v[k] = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy) {
+        const float2 p = __ldg(reinterpret_cast<const float2*>(src + (((size_t)b * 3 + c) * H + (2 * h2 + dy)) * W + 2 * w2));
+        v[(dy * 2 + 0) * 3 + c] = p.x;
+        v[(dy * 2 + 1) * 3 + c] = p.y;
+      }
+    uint32_t hq[8], lq[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      __half h0, l0, h1, l1;
+      split_f32(v[2 * k], &h0, &l0);
+      split_f32(v[2 * k + 1], &h1, &l1);
+      hq[k] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      lq[k] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    __half* o = dst + (size_t)i * pitch;
+    reinterpret_cast<uint4*>(o)[0] = make_uint4(hq[0], hq[1], hq[2], hq[3]);
+    reinterpret_cast<uint4*>(o)[1] = make_uint4(hq[4], hq[5], hq[6], hq[7]);
+    reinterpret_cast<uint4*>(o + plane)[0] = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+    reinterpret_cast<uint4*>(o + plane)[1] = make_uint4(lq[4], lq[5], lq[6], lq[7]);
+  }
+}
+
+// ------------------------------------------------------------------ SPPF: three chained 5x5/s1/p2 max pools
+// One CTA per (image, 8-channel slice): the whole HxW map of the slice lives in shared memory as fp32;
+// each pool is a separable row-max / column-max pass.  y2 == 9x9 pool, y3 == 13x13 pool of x.
+__global__ void sppf_pool_kernel(const __half* __restrict__ x, int H, int W, int xp, long long xplane, __half* __restrict__ y1, int p1,
+                                 long long plane1, __half* __restrict__ y2, int p2, long long plane2, __half* __restrict__ y3, int p3,
+                                 long long plane3, int cgroups) {
+  extern __shared__ float sm[];
+  float* cur = sm;                 // [H*W][8]
+  float* tmp = sm + (size_t)H * W * 8;
+  const int b = blockIdx.x / cgroups;
+  const int c0 = (blockIdx.x % cgroups) * 8;
+  const int npix = H * W;
+  for (int p = threadIdx.x; p < npix; p += blockDim.x) {
+    const size_t o = ((size_t)b * npix + p) * xp + c0;
+    const uint4 hv = *reinterpret_cast<const uint4*>(x + o);
+    const uint4 lv = *reinterpret_cast<const uint4*>(x + o + xplane);
+    const __half2* h2 = reinterpret_cast<const __half2*>(&hv);
+    const __half2* l2 = reinterpret_cast<const __half2*>(&lv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      cur[p * 8 + 2 * k] = __low2float(h2[k]) + __low2float(l2[k]);
+      cur[p * 8 + 2 * k + 1] = __high2float(h2[k]) + __high2float(l2[k]);
+    }
+  }
+  __syncthreads();
+  __half* outs[3] = {y1, y2, y3};
+  const int pitches[3] = {p1, p2, p3};
+  const long long planes[3] = {plane1, plane2, plane3};
+  for (int r = 0; r < 3; ++r) {
+    // row pass: tmp[h][w] = max_{|d|<=2} cur[h][w+d]
+    for (int i = threadIdx.x; i < npix * 8; i += blockDim.x) {
+      const int c = i & 7, p = i >> 3, w = p % W, h = p / W;
+      float m = -CUDART_INF_F;
+      for (int d = -2; d <= 2; ++d) {
+        const int ww = w + d;
+        if (ww >= 0 && ww < W) m = fmaxf(m, cur[(h * W + ww) * 8 + c]);
+      }
+      tmp[i] = m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npix * 8; i += blockDim.x) {
+      const int c = i & 7, p = i >> 3, w = p % W, h = p / W;
+      float m = -CUDART_INF_F;
+      for (int d = -2; d <= 2; ++d) {
+        const int hh = h + d;
+        if (hh >= 0 && hh < H) m = fmaxf(m, tmp[(hh * W + w) * 8 + c]);
+      }
+      cur[i] = m;
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < npix; p += blockDim.x) {
+      uint32_t hq[4], lq[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        __half h0, l0, h1, l1;
+        split_f32(cur[p * 8 + 2 * k], &h0, &l0);
+        split_f32(cur[p * 8 + 2 * k + 1], &h1, &l1);
+        hq[k] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        lq[k] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      }
+      const size_t o = ((size_t)b * npix + p) * pitches[r] + c0;
+      *reinterpret_cast<uint4*>(outs[r] + o) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
+      *reinterpret_cast<uint4*>(outs[r] + o + planes[r]) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+    }
+    // cur stays as the input of the next chained pool
+  }
+}
+
+// ------------------------------------------------------------------ YOLOv5 decode
+// index space (b, a, pix, c) with c fastest: writes to z / xperm are fully coalesced, reads are 85-float runs.
+__global__ void yolo_decode_kernel(const float* __restrict__ raw, int B, int ny, int nx, int pitch, int na, int no,
+                                   const float* __restrict__ anchors_px, float stride, float* __restrict__ z, long long z_rows,
+                                   long long z_off, float* __restrict__ xperm) {
+  const long long npix = (long long)ny * nx;
+  const long long total = (long long)B * na * npix * no;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % no);
+    long long t = i / no;
+    const long long pix = t % npix;
+    t /= npix;
+    const int a = (int)(t % na);
+    const int b = (int)(t / na);
+    const float v = __ldg(raw + ((size_t)b * npix + pix) * pitch + a * no + c);
+    if (xperm != nullptr) xperm[i] = v;
+    if (z != nullptr) {
+      // reference: y = x.sigmoid(); xy = (y*2 - 0.5 + grid) * stride; wh = (y*2)**2 * anchor_grid   (yolov5_detect.py:50-53)
+      const float y = 1.0f / (1.0f + expf(-v));
+      float o = y;
+      if (c < 2) {
+        const float g = (c == 0) ? (float)(pix % nx) : (float)(pix / nx);
+        o = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(y, 2.0f), 0.5f), g), stride);
+      } else if (c < 4) {
+        const float t2 = __fmul_rn(y, 2.0f);
+        o = __fmul_rn(__fmul_rn(t2, t2), __ldg(anchors_px + a * 2 + (c - 2)));
+      }
+      z[((size_t)b * z_rows + z_off + (long long)a * npix + pix) * no + c] = o;
+    }
+  }
+}
+
+static int check_split_view(const CvbView* v, const char* what) {
+  CVB_REQUIRE(v != nullptr && v->base != nullptr, "%s: null view", what);
+  CVB_REQUIRE(v->c_pitch >= v->C && v->plane_stride % 2 == 0, "%s: bad view", what);
+  return CVB_OK;
+}
+
+}  // namespace cvb
+
+using namespace cvb;
+
+extern "C" int cvb_nchw_to_split(const float* src, int32_t B, int32_t C, int32_t H, int32_t W, const CvbView* dst, void* stream) {
+  int rc = check_split_view(dst, "nchw_to_split");
+  if (rc) return rc;
+  CVB_REQUIRE(src && dst->B == B && dst->C == C && dst->H == H && dst->W == W, "nchw_to_split: shape mismatch");
+  dim3 grid(ceil_div(W, 32), ceil_div(C, 32), B * H), block(32, 8);
+  nchw_to_split_kernel<<<grid, block, 0, as_stream(stream)>>>(src, B, C, H, W, static_cast<__half*>(dst->base), dst->c_pitch,
+                                                              dst->plane_stride / 2);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}
+
+extern "C" int cvb_split_to_nchw(const CvbView* src, float* dst, void* stream) {
+  int rc = check_split_view(src, "split_to_nchw");
+  if (rc) return rc;
+  CVB_REQUIRE(dst != nullptr, "split_to_nchw: null dst");
+  dim3 grid(ceil_div(src->W, 32), ceil_div(src->C, 32), src->B * src->H), block(32, 8);
+  split_to_nchw_kernel<<<grid, block, 0, as_stream(stream)>>>(static_cast<const __half*>(src->base), src->B, src->C, src->H, src->W,
+                                                              src->c_pitch, src->plane_stride / 2, dst);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}
+
+extern "C" int cvb_f32nhwc_to_nchw(const CvbView* src, float* dst, void* stream) {
+  CVB_REQUIRE(src && src->base && dst, "f32nhwc_to_nchw: null argument");
+  dim3 grid(ceil_div(src->W, 32), ceil_div(src->C, 32), src->B * src->H), block(32, 8);
+  f32nhwc_to_nchw_kernel<<<grid, block, 0, as_stream(stream)>>>(static_cast<const float*>(src->base), src->B, src->C, src->H, src->W,
+                                                                src->c_pitch, dst);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}
+
+extern "C" int cvb_stem_s2d(const float* src, int32_t B, int32_t H, int32_t W, const CvbView* dst, void* stream) {
+  int rc = check_split_view(dst, "stem_s2d");
+  if (rc) return rc;
+  CVB_REQUIRE(src && H % 2 == 0 && W % 2 == 0, "stem_s2d: H and W must be even");
+  CVB_REQUIRE(dst->B == B && dst->H == H / 2 && dst->W == W / 2 && dst->C == 16 && dst->c_pitch == 16, "stem_s2d: dst must be [B,H/2,W/2,16]");
+  CVB_REQUIRE((reinterpret_cast<uintptr_t>(src) & 7) == 0 && (reinterpret_cast<uintptr_t>(dst->base) & 15) == 0 && dst->plane_stride % 16 == 0,
+              "stem_s2d: alignment");
+  const long long n = (long long)B * (H / 2) * (W / 2);
+  const int block = 256;
+  long long grid = (n + block - 1) / block;
+  if (grid > 148 * 32) grid = 148 * 32;
+  stem_s2d_kernel<<<(int)grid, block, 0, as_stream(stream)>>>(src, B, H, W, static_cast<__half*>(dst->base), dst->c_pitch,
+                                                             dst->plane_stride / 2);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}
+
+extern "C" int cvb_sppf_pool(const CvbView* x, const CvbView* y1, const CvbView* y2, const CvbView* y3, void* stream) {
+  int rc = check_split_view(x, "sppf x");
+  if (!rc) rc = check_split_view(y1, "sppf y1");
+  if (!rc) rc = check_split_view(y2, "sppf y2");
+  if (!rc) rc = check_split_view(y3, "sppf y3");
+  if (rc) return rc;
+  const CvbView* vs[4] = {x, y1, y2, y3};
+  for (int i = 0; i < 4; ++i) {
+    CVB_REQUIRE(vs[i]->B == x->B && vs[i]->H == x->H && vs[i]->W == x->W && vs[i]->C == x->C, "sppf: view %d shape mismatch", i);
+    CVB_REQUIRE(vs[i]->c_pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(vs[i]->base) & 15) == 0 && vs[i]->plane_stride % 16 == 0,
+                "sppf: view %d alignment", i);
+  }
+  CVB_REQUIRE(x->C % 8 == 0, "sppf: C must be a multiple of 8");
+  const size_t smem = (size_t)x->H * x->W * 8 * sizeof(float) * 2;
+  CVB_REQUIRE(smem <= 200 * 1024, "sppf: map %dx%d too large for the shared-memory pool kernel", x->H, x->W);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CVB_CHECK_CUDA(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const int cgroups = x->C / 8;
+  sppf_pool_kernel<<<x->B * cgroups, 256, smem, as_stream(stream)>>>(
+      static_cast<const __half*>(x->base), x->H, x->W, x->c_pitch, x->plane_stride / 2, static_cast<__half*>(y1->base), y1->c_pitch,
+      y1->plane_stride / 2, static_cast<__half*>(y2->base), y2->c_pitch, y2->plane_stride / 2, static_cast<__half*>(y3->base), y3->c_pitch,
+      y3->plane_stride / 2, cgroups);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}
+
+extern "C" int cvb_yolo_decode(const CvbView* raw, int32_t na, int32_t no, const float* anchors_px, float stride, float* z, int64_t z_rows,
+                               int64_t z_off, float* xperm, void* stream) {
+  CVB_REQUIRE(raw && raw->base && anchors_px, "yolo_decode: null argument");
+  CVB_REQUIRE(raw->c_pitch >= na * no, "yolo_decode: raw pitch %d < na*no %d", raw->c_pitch, na * no);
+  CVB_REQUIRE(z != nullptr || xperm != nullptr, "yolo_decode: nothing to write");
+  const long long total = (long long)raw->B * na * raw->H * raw->W * no;
+  const int block = 256;
+  long long grid = (total + block - 1) / block;
+  if (grid > 148 * 16) grid = 148 * 16;
+  yolo_decode_kernel<<<(int)grid, block, 0, as_stream(stream)>>>(static_cast<const float*>(raw->base), raw->B, raw->H, raw->W, raw->c_pitch,
+                                                                na, no, anchors_px, stride, z, z_rows, z_off, xperm);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}

@@ -1,0 +1,664 @@
+// Fused conv2d + folded-BN bias + SiLU/ReLU (+ residual) (+ 2x-upsampled fp32 partial) for sm_100a.
+//
+// Replaces the reference's per-layer chain  nn.Conv2d -> nn.BatchNorm2d -> nn.SiLU  (3 library kernels,
+// src/models/bricks/conv_module.py:201-214; src/models/modules/yolo11_modules.py:27-39) plus the
+// bottleneck shortcut add (src/models/modules/yolo_modules.py:95-104) and the neck's
+// nearest-upsample + concat (src/models/modules/yolo11_modules.py:388-397) with ONE kernel.
+//
+// Formulation: implicit GEMM, NHWC.  D[128 pixels, BLOCK_N couts] += A[pixels, 64 cin] * W[couts, 64 cin]^T per
+// (filter tap, cin chunk).  A tile = a TMA box {BLOCK_K channels, TW, TH, NB} of the input tensor shifted by
+// the tap offset; TMA's out-of-bounds zero fill IS the convolution padding.  Stride-2 convolutions read
+// through four "parity" tensor maps (even/odd rows x even/odd columns), so the kernel never sees the stride.
+//
+// Precision: activations/weights are fp16 (hi, lo) pairs; three tcgen05.mma per chunk
+// (hi*hi + hi*lo + lo*hi), fp32 accumulation in TMEM -> fp32-equivalent results (rel. err ~1e-6) on the
+// fp16 tensor pipe.  The reference computes fp32 (trainer.py:209 val path is un-autocast).
+//
+// Structure (persistent, warp specialised, 192 threads, 1 CTA/SM):
+//   warp 0      TMA producer   (one lane)   smem ring: full[]/empty[] mbarriers
+//   warp 1      MMA issuer     (one lane)   TMEM accumulators double buffered: tfull[]/tempty[]
+//   warps 2..5  epilogue: tcgen05.ld -> +partial +bias -> act -> +residual -> hi/lo split -> swizzled smem -> TMA store
+#include <cuda_fp16.h>
+
+#include <mutex>
+#include <new>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace cvb {
+
+constexpr int kTileM = 128;
+constexpr int kMaxTaps = 9;
+constexpr int kThreads = 192;
+constexpr int kSmemBudget = 232448;  // 227 KB opt-in limit per CTA on sm_100
+
+struct alignas(64) ConvKArgs {
+  CUtensorMap tmA[4];  // input, one per (row parity, col parity) for stride 2; only [0] for stride 1
+  CUtensorMap tmB;     // weights [2][cout_pad][K]
+  CUtensorMap tmO;     // output (5D; plane dim = 1 for fp32)
+  int tiles_w, tiles_h, tiles_b, tiles_n;
+  int TW, TH, NB;
+  int Ho, Wo, Bn;
+  int cout;
+  int taps, chunks, cin;
+  int stages;
+  int act;
+  int rows_valid;
+  uint32_t a_box_bytes;
+  int8_t tap_map[kMaxTaps];
+  int8_t tap_dh[kMaxTaps];
+  int8_t tap_dw[kMaxTaps];
+  const float* bias;
+  int bias_len;
+  const __half* resid;
+  long long resid_plane;  // elements
+  int resid_pitch;        // elements per pixel
+  const float* up;
+  int up_pitch, up_H, up_W;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == CVB_ACT_SILU) return __fdividef(x, 1.0f + __expf(-x));
+  if (act == CVB_ACT_RELU) return fmaxf(x, 0.0f);
+  return x;
+}
+
+__device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
+  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+template <int BLOCK_N, int BLOCK_K, bool OUT_F32>
+struct ConvCfg {
+  static constexpr int SWZ = BLOCK_K * 2;  // swizzle span == bytes of one K chunk row
+  static constexpr int A_BYTES = kTileM * SWZ;
+  static constexpr int B_BYTES = BLOCK_N * SWZ;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int OUT_GROUP_CH = OUT_F32 ? 32 : (BLOCK_N >= 64 ? 64 : 32);
+  static constexpr int OUT_ROW_BYTES = OUT_F32 ? 128 : OUT_GROUP_CH * 2;
+  static constexpr int OUT_PLANE_BYTES = kTileM * OUT_ROW_BYTES;
+  static constexpr int OUT_STAGE_BYTES = OUT_PLANE_BYTES * (OUT_F32 ? 1 : 2);
+  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
+  static constexpr int TAIL_BYTES = BLOCK_N * 4 + 64 * 8 + 16;  // bias + barriers + tmem slot
+  static constexpr int smem_bytes(int stages) { return 1024 + stages * STAGE_BYTES + OUT_STAGE_BYTES + TAIL_BYTES; }
+};
+
+template <int BLOCK_N, int BLOCK_K, bool OUT_F32>
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvKArgs a) {
+  using Cfg = ConvCfg<BLOCK_N, BLOCK_K, OUT_F32>;
+  constexpr int SWZ = Cfg::SWZ;
+  constexpr int A_BYTES = Cfg::A_BYTES;
+  constexpr int B_BYTES = Cfg::B_BYTES;
+  constexpr int STAGE_BYTES = Cfg::STAGE_BYTES;
+  constexpr int OUT_GROUP_CH = Cfg::OUT_GROUP_CH;
+  constexpr int OUT_ROW_BYTES = Cfg::OUT_ROW_BYTES;
+  constexpr uint32_t IDESC = make_idesc_f16_f32(kTileM, BLOCK_N);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int STAGES = a.stages;
+  uint8_t* stage_base = smem;
+  uint8_t* out_stage = smem + STAGES * STAGE_BYTES;
+  float* bias_s = reinterpret_cast<float*>(out_stage + Cfg::OUT_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + BLOCK_N);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&a.tmA[0]);
+    tma_prefetch_desc(&a.tmB);
+    tma_prefetch_desc(&a.tmO);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full[s], 1);
+        mbar_init(&empty[s], 1);
+      }
+      for (int s = 0; s < 2; ++s) {
+        mbar_init(&tfull[s], 1);
+        mbar_init(&tempty[s], 4);
+      }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = a.tiles_w * a.tiles_h * a.tiles_b;
+  const int total_tiles = m_tiles * a.tiles_n;
+  const int k_iters = a.taps * a.chunks;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t tx_bytes = 2 * a.a_box_bytes + 2 * B_BYTES;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int nt = tile % a.tiles_n;
+        const int mt = tile / a.tiles_n;
+        const int wt = mt % a.tiles_w;
+        const int t2 = mt / a.tiles_w;
+        const int ht = t2 % a.tiles_h;
+        const int bt = t2 / a.tiles_h;
+        const int w0 = wt * a.TW, h0 = ht * a.TH, b0 = bt * a.NB, n0 = nt * BLOCK_N;
+        for (int tap = 0; tap < a.taps; ++tap) {
+          const CUtensorMap* mapA = &a.tmA[a.tap_map[tap]];
+          const int cw = w0 + a.tap_dw[tap];
+          const int ch = h0 + a.tap_dh[tap];
+          for (int ck = 0; ck < a.chunks; ++ck) {
+            mbar_wait(&empty[stage], phase ^ 1, 100 + stage);
+            mbar_expect_tx(&full[stage], tx_bytes);
+            uint8_t* sb = stage_base + stage * STAGE_BYTES;
+            tma_load_5d(mapA, &full[stage], sb, ck * BLOCK_K, cw, ch, b0, 0);
+            tma_load_5d(mapA, &full[stage], sb + A_BYTES, ck * BLOCK_K, cw, ch, b0, 1);
+            const int kc = tap * a.cin + ck * BLOCK_K;
+            tma_load_3d(&a.tmB, &full[stage], sb + 2 * A_BYTES, kc, n0, 0);
+            tma_load_3d(&a.tmB, &full[stage], sb + 2 * A_BYTES + B_BYTES, kc, n0, 1);
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[acc], acc_phase ^ 1, 200 + acc);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int it = 0; it < k_iters; ++it) {
+          mbar_wait(&full[stage], phase, 300 + stage);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + stage * STAGE_BYTES);
+          const uint64_t dah = make_kmajor_desc<SWZ>(sa);
+          const uint64_t dal = make_kmajor_desc<SWZ>(sa + A_BYTES);
+          const uint64_t dbh = make_kmajor_desc<SWZ>(sa + 2 * A_BYTES);
+          const uint64_t dbl = make_kmajor_desc<SWZ>(sa + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / 16; ++k) {
+            const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes per UMMA_K step, in 16-byte units
+            umma_f16(d_tmem, dah + koff, dbh + koff, IDESC, (it | k) != 0 ? 1u : 0u);
+            umma_f16(d_tmem, dah + koff, dbl + koff, IDESC, 1u);
+            umma_f16(d_tmem, dal + koff, dbh + koff, IDESC, 1u);
+          }
+          umma_commit(&empty[stage]);  // frees this smem stage once the MMAs above have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;    // accumulator row == pixel index inside the tile box
+    const int tid_e = threadIdx.x - 64;
+    const int tw = row % a.TW;
+    const int r2 = row / a.TW;
+    const int th = r2 % a.TH;
+    const int nb = r2 / a.TH;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int cur_n0 = -1;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int nt = tile % a.tiles_n;
+      const int mt = tile / a.tiles_n;
+      const int wt = mt % a.tiles_w;
+      const int t2 = mt / a.tiles_w;
+      const int ht = t2 % a.tiles_h;
+      const int bt = t2 / a.tiles_h;
+      const int w0 = wt * a.TW, h0 = ht * a.TH, b0 = bt * a.NB, n0 = nt * BLOCK_N;
+      const int ow = w0 + tw, oh = h0 + th, ob = b0 + nb;
+      const bool valid = (row < a.rows_valid) && (ow < a.Wo) && (oh < a.Ho) && (ob < a.Bn);
+
+      if (n0 != cur_n0) {
+        named_bar_sync(1, 128);
+        for (int i = tid_e; i < BLOCK_N; i += 128) bias_s[i] = (n0 + i < a.bias_len) ? a.bias[n0 + i] : 0.0f;
+        named_bar_sync(1, 128);
+        cur_n0 = n0;
+      }
+      const float* up_row = nullptr;
+      if (a.up != nullptr && valid)
+        up_row = a.up + ((size_t)((size_t)ob * a.up_H + (oh >> 1)) * a.up_W + (ow >> 1)) * a.up_pitch + n0;
+      const __half* res_row = nullptr;
+      if (a.resid != nullptr && valid) res_row = a.resid + ((size_t)((size_t)ob * a.Ho + oh) * a.Wo + ow) * a.resid_pitch + n0;
+
+      mbar_wait(&tfull[acc], acc_phase, 400 + acc);
+      tc_fence_after();
+
+#pragma unroll 1
+      for (int g = 0; g < BLOCK_N / OUT_GROUP_CH; ++g) {
+        if (tid_e == 0) tma_store_wait_read0();  // previous TMA store has finished reading the staging tile
+        named_bar_sync(1, 128);
+#pragma unroll 1
+        for (int hh = 0; hh < OUT_GROUP_CH / 32; ++hh) {
+          const int col = g * OUT_GROUP_CH + hh * 32;
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + col), v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          const bool ch_ok = (n0 + col + 32 <= a.cout);
+          if (up_row != nullptr && ch_ok) {
+            const float4* p = reinterpret_cast<const float4*>(up_row + col);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 u = __ldg(p + j);
+              f[4 * j + 0] += u.x;
+              f[4 * j + 1] += u.y;
+              f[4 * j + 2] += u.z;
+              f[4 * j + 3] += u.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j] + bias_s[col + j], a.act);
+          if (res_row != nullptr && ch_ok) {
+            const uint4* ph = reinterpret_cast<const uint4*>(res_row + col);
+            const uint4* pl = reinterpret_cast<const uint4*>(res_row + a.resid_plane + col);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 hv = __ldg(ph + j);
+              const uint4 lv = __ldg(pl + j);
+              const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+              const uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const __half2 h2 = *reinterpret_cast<const __half2*>(&hw[e]);
+                const __half2 l2 = *reinterpret_cast<const __half2*>(&lw[e]);
+                f[8 * j + 2 * e + 0] += __low2float(h2) + __low2float(l2);
+                f[8 * j + 2 * e + 1] += __high2float(h2) + __high2float(l2);
+              }
+            }
+          }
+          if constexpr (OUT_F32) {
+            // row = 32 fp32 = 128 B, 8 chunks of 16 B, 128B swizzle: chunk ^= row & 7
+            uint8_t* rowp = out_stage + row * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 o = make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                                         __float_as_uint(f[4 * j + 3]));
+              *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
+            }
+          } else {
+            uint8_t* rowh = out_stage + row * OUT_ROW_BYTES;
+            uint8_t* rowl = rowh + Cfg::OUT_PLANE_BYTES;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t hq[4], lq[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float x0 = fminf(fmaxf(f[8 * j + 2 * e], -65504.0f), 65504.0f);
+                const float x1 = fminf(fmaxf(f[8 * j + 2 * e + 1], -65504.0f), 65504.0f);
+                const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+                const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
+                hq[e] = pack_half2(h0, h1);
+                lq[e] = pack_half2(l0, l1);
+              }
+              int chunk;
+              if constexpr (OUT_GROUP_CH == 64) chunk = (hh * 4 + j) ^ (row & 7);   // 128B swizzle
+              else chunk = j ^ ((row >> 1) & 3);                                    // 64B swizzle
+              *reinterpret_cast<uint4*>(rowh + (chunk << 4)) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
+              *reinterpret_cast<uint4*>(rowl + (chunk << 4)) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+            }
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        named_bar_sync(1, 128);
+        if (tid_e == 0) {
+          const int c0 = n0 + g * OUT_GROUP_CH;
+          if (c0 < a.cout) {
+            tma_store_5d(&a.tmO, out_stage, c0, w0, h0, b0, 0);
+            if constexpr (!OUT_F32) tma_store_5d(&a.tmO, out_stage + Cfg::OUT_PLANE_BYTES, c0, w0, h0, b0, 1);
+          }
+          tma_store_commit();
+        }
+      }
+      // all tcgen05.ld of this accumulator are complete -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (tid_e == 0) tma_store_wait_all0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    __syncwarp();
+    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host
+struct KernelEntry {
+  const void* fn;
+  int stage_bytes, out_stage_bytes, tail_bytes;
+};
+
+template <int BN, int BK, bool F32>
+static KernelEntry entry() {
+  using Cfg = ConvCfg<BN, BK, F32>;
+  return KernelEntry{reinterpret_cast<const void*>(&conv_tc_kernel<BN, BK, F32>), Cfg::STAGE_BYTES, Cfg::OUT_STAGE_BYTES,
+                     Cfg::TAIL_BYTES};
+}
+
+static bool lookup_kernel(int bn, int bk, bool f32, KernelEntry* e) {
+#define CVB_CASE(BN, BK)                               \
+  if (bn == BN && bk == BK) {                          \
+    *e = f32 ? entry<BN, BK, true>() : entry<BN, BK, false>(); \
+    return true;                                       \
+  }
+  CVB_CASE(32, 16) CVB_CASE(32, 32) CVB_CASE(32, 64)
+  CVB_CASE(64, 16) CVB_CASE(64, 32) CVB_CASE(64, 64)
+  CVB_CASE(128, 16) CVB_CASE(128, 32) CVB_CASE(128, 64)
+  CVB_CASE(256, 16) CVB_CASE(256, 32) CVB_CASE(256, 64)
+#undef CVB_CASE
+  return false;
+}
+
+}  // namespace cvb
+
+struct CvbConvPlan {
+  cvb::ConvKArgs args;
+  const void* fn;
+  int grid;
+  int smem;
+};
+
+namespace cvb {
+
+static int encode_map(CUtensorMap* m, CUtensorMapDataType dt, int rank, void* base, const cuuint64_t* dims,
+                      const cuuint64_t* strides_bytes /*rank-1*/, const cuuint32_t* box, CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return set_error(CVB_ERR_NO_DEVICE, "cuTensorMapEncodeTiled entry point not found (no CUDA driver?)");
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, dt, (cuuint32_t)rank, base, dims, strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return set_error(CVB_ERR_CUDA,
+                     "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u] base %p", (int)r,
+                     rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                     (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0),
+                     (unsigned long long)(rank > 4 ? dims[4] : 0), box[0], rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0,
+                     rank > 3 ? box[3] : 0, rank > 4 ? box[4] : 0, base);
+  }
+  return CVB_OK;
+}
+
+static CUtensorMapSwizzle swizzle_for_bytes(int bytes) {
+  return bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// Pick the output pixel box (TW x TH x NB <= 128) that wastes the fewest accumulator rows.
+static void choose_box(int B, int H, int W, int* TW, int* TH, int* NB) {
+  double best = -1.0;
+  int bw = 1, bh = 1, bb = 1;
+  for (int tw = 1; tw <= 128; ++tw) {
+    if (tw > W && tw != 1) break;
+    if (!(tw == W || (tw & (tw - 1)) == 0)) continue;  // powers of two, or the full row
+    for (int th = 1; th * tw <= 128; ++th) {
+      if (th > H) break;
+      int nb = 128 / (tw * th);
+      if (nb > B) nb = B;
+      if (nb < 1) nb = 1;
+      // keep all box dims <= 256 (TMA limit) -- implied by <= 128
+      const long long tiles = (long long)ceil_div(W, tw) * ceil_div(H, th) * ceil_div(B, nb);
+      const double util = (double)B * H * W / ((double)tiles * 128.0);
+      const double score = util + 1e-4 * tw / 128.0;  // tie-break: longer contiguous rows
+      if (score > best) {
+        best = score;
+        bw = tw;
+        bh = th;
+        bb = nb;
+      }
+    }
+  }
+  *TW = bw;
+  *TH = bh;
+  *NB = bb;
+}
+
+static int g_num_sms = 0;
+
+}  // namespace cvb
+
+extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan) {
+  using namespace cvb;
+  CVB_REQUIRE(d != nullptr && out_plan != nullptr, "null argument");
+  *out_plan = nullptr;
+  const CvbView& in = d->in;
+  const CvbView& out = d->out;
+  CVB_REQUIRE(in.base && out.base && d->weights && d->bias, "conv: null tensor pointer");
+  CVB_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->kh * d->kw <= kMaxTaps, "conv: kernel %dx%d unsupported (max %d taps)", d->kh, d->kw,
+              kMaxTaps);
+  CVB_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride %d unsupported", d->stride);
+  CVB_REQUIRE(d->dilation >= 1, "conv: bad dilation");
+  const int cin = in.C, cout = out.C;
+  CVB_REQUIRE(cin % 16 == 0, "conv: cin=%d must be a multiple of 16", cin);
+  CVB_REQUIRE(in.c_pitch % 8 == 0 && out.c_pitch % 8 == 0, "conv: channel pitch must be a multiple of 8");
+  CVB_REQUIRE((reinterpret_cast<uintptr_t>(in.base) & 15) == 0 && (reinterpret_cast<uintptr_t>(out.base) & 15) == 0 &&
+                  (reinterpret_cast<uintptr_t>(d->weights) & 15) == 0,
+              "conv: pointers must be 16-byte aligned");
+  const int Ho = (in.H + 2 * d->pad - d->dilation * (d->kh - 1) - 1) / d->stride + 1;
+  const int Wo = (in.W + 2 * d->pad - d->dilation * (d->kw - 1) - 1) / d->stride + 1;
+  CVB_REQUIRE(Ho == out.H && Wo == out.W && in.B == out.B, "conv: output view %dx%dx%d does not match computed %dx%dx%d", out.B, out.H,
+              out.W, in.B, Ho, Wo);
+  CVB_REQUIRE(d->cout_pad >= cout && d->cout_pad % 8 == 0, "conv: bad cout_pad");
+  const bool f32 = d->out_kind == CVB_OUT_F32;
+  if (f32) CVB_REQUIRE(out.c_pitch % 4 == 0, "conv: fp32 output pitch must be a multiple of 4");
+
+  const int bk = (cin % 64 == 0) ? 64 : (cin % 32 == 0 ? 32 : 16);
+  int bn = d->block_n;
+  if (bn == 0) bn = cout <= 32 ? 32 : (cout <= 64 ? 64 : 128);
+  KernelEntry ke;
+  CVB_REQUIRE(lookup_kernel(bn, bk, f32, &ke), "conv: no kernel for block_n=%d block_k=%d", bn, bk);
+
+  CvbConvPlan* p = new (std::nothrow) CvbConvPlan();
+  CVB_REQUIRE(p != nullptr, "out of host memory");
+  ConvKArgs& a = p->args;
+  memset(&a, 0, sizeof(a));
+
+  int TW, TH, NB;
+  choose_box(out.B, Ho, Wo, &TW, &TH, &NB);
+  a.TW = TW;
+  a.TH = TH;
+  a.NB = NB;
+  a.tiles_w = ceil_div(Wo, TW);
+  a.tiles_h = ceil_div(Ho, TH);
+  a.tiles_b = ceil_div(out.B, NB);
+  a.tiles_n = ceil_div(cout, bn);
+  a.Ho = Ho;
+  a.Wo = Wo;
+  a.Bn = out.B;
+  a.cout = cout;
+  a.taps = d->kh * d->kw;
+  a.chunks = cin / bk;
+  a.cin = cin;
+  a.act = d->act;
+  a.rows_valid = TW * TH * NB;
+  a.a_box_bytes = (uint32_t)(TW * TH * NB * bk * 2);
+  a.bias = d->bias;
+  a.bias_len = d->cout_pad;
+
+  const int s = d->stride;
+  for (int ky = 0; ky < d->kh; ++ky)
+    for (int kx = 0; kx < d->kw; ++kx) {
+      const int t = ky * d->kw + kx;
+      const int qy = ky * d->dilation - d->pad, qx = kx * d->dilation - d->pad;
+      if (s == 1) {
+        a.tap_map[t] = 0;
+        a.tap_dh[t] = (int8_t)qy;
+        a.tap_dw[t] = (int8_t)qx;
+      } else {
+        const int py = ((qy % 2) + 2) % 2, px = ((qx % 2) + 2) % 2;
+        a.tap_map[t] = (int8_t)(py * 2 + px);
+        a.tap_dh[t] = (int8_t)((qy - py) / 2);
+        a.tap_dw[t] = (int8_t)((qx - px) / 2);
+      }
+    }
+
+  int rc = CVB_OK;
+  // ---- input maps: 5D (C, W, H, B, plane)
+  {
+    const cuuint32_t box[5] = {(cuuint32_t)bk, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)NB, 1};
+    const long long pix = (long long)in.c_pitch * 2;  // bytes per pixel
+    if (s == 1) {
+      const cuuint64_t dims[5] = {(cuuint64_t)cin, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.B, 2};
+      const cuuint64_t str[4] = {(cuuint64_t)pix, (cuuint64_t)(pix * in.W), (cuuint64_t)(pix * in.W * in.H), (cuuint64_t)in.plane_stride};
+      rc = encode_map(&a.tmA[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, in.base, dims, str, box, swizzle_for_bytes(bk * 2));
+    } else {
+      for (int py = 0; py < 2 && rc == CVB_OK; ++py)
+        for (int px = 0; px < 2 && rc == CVB_OK; ++px) {
+          const int Wp = (in.W - px + 1) / 2, Hp = (in.H - py + 1) / 2;  // number of columns/rows with this parity
+          if (Wp <= 0 || Hp <= 0) {
+            a.tmA[py * 2 + px] = a.tmA[0];
+            continue;
+          }
+          const cuuint64_t dims[5] = {(cuuint64_t)cin, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)in.B, 2};
+          const cuuint64_t str[4] = {(cuuint64_t)(pix * 2), (cuuint64_t)(pix * in.W * 2), (cuuint64_t)(pix * in.W * in.H),
+                                     (cuuint64_t)in.plane_stride};
+          uint8_t* base = static_cast<uint8_t*>(in.base) + ((long long)py * in.W + px) * pix;
+          rc = encode_map(&a.tmA[py * 2 + px], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, base, dims, str, box, swizzle_for_bytes(bk * 2));
+        }
+    }
+  }
+  // ---- weight map: 3D (K, cout_pad, plane)
+  if (rc == CVB_OK) {
+    const long long K = (long long)a.taps * cin;
+    const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)d->cout_pad, 2};
+    const cuuint64_t str[2] = {(cuuint64_t)(K * 2), (cuuint64_t)(K * 2 * d->cout_pad)};
+    const cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)bn, 1};
+    rc = encode_map(&a.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(d->weights), dims, str, box, swizzle_for_bytes(bk * 2));
+  }
+  // ---- output map: 5D (C, W, H, B, plane)
+  if (rc == CVB_OK) {
+    if (f32) {
+      const long long pix = (long long)out.c_pitch * 4;
+      const cuuint64_t dims[5] = {(cuuint64_t)cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)out.B, 1};
+      const cuuint64_t str[4] = {(cuuint64_t)pix, (cuuint64_t)(pix * Wo), (cuuint64_t)(pix * Wo * Ho), (cuuint64_t)(pix * Wo * Ho * out.B)};
+      const cuuint32_t box[5] = {32, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)NB, 1};
+      rc = encode_map(&a.tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, out.base, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    } else {
+      const int gch = bn >= 64 ? 64 : 32;
+      const long long pix = (long long)out.c_pitch * 2;
+      const cuuint64_t dims[5] = {(cuuint64_t)cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)out.B, 2};
+      const cuuint64_t str[4] = {(cuuint64_t)pix, (cuuint64_t)(pix * Wo), (cuuint64_t)(pix * Wo * Ho), (cuuint64_t)out.plane_stride};
+      const cuuint32_t box[5] = {(cuuint32_t)gch, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)NB, 1};
+      rc = encode_map(&a.tmO, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, out.base, dims, str, box, swizzle_for_bytes(gch * 2));
+    }
+  }
+  if (rc != CVB_OK) {
+    delete p;
+    return rc;
+  }
+  // ---- epilogue extras
+  if (d->residual.base) {
+    const CvbView& r = d->residual;
+    if (!(r.B == out.B && r.H == Ho && r.W == Wo && r.C == cout && r.c_pitch % 8 == 0 && cout % 32 == 0 &&
+          (reinterpret_cast<uintptr_t>(r.base) & 15) == 0 && r.plane_stride % 16 == 0)) {
+      delete p;
+      return set_error(CVB_ERR_INVALID, "conv: residual view mismatch");
+    }
+    a.resid = static_cast<const __half*>(r.base);
+    a.resid_plane = r.plane_stride / 2;
+    a.resid_pitch = r.c_pitch;
+  }
+  if (d->up_partial.base) {
+    const CvbView& u = d->up_partial;
+    if (!(u.B == out.B && u.H == (Ho + 1) / 2 && u.W == (Wo + 1) / 2 && u.C == cout && u.c_pitch % 4 == 0 && cout % 32 == 0 &&
+          (reinterpret_cast<uintptr_t>(u.base) & 15) == 0)) {
+      delete p;
+      return set_error(CVB_ERR_INVALID, "conv: up_partial view mismatch");
+    }
+    a.up = static_cast<const float*>(u.base);
+    a.up_pitch = u.c_pitch;
+    a.up_H = u.H;
+    a.up_W = u.W;
+  }
+  // ---- pipeline depth and launch shape
+  const int fixed = 1024 + ke.out_stage_bytes + ke.tail_bytes;
+  int stages = (kSmemBudget - fixed) / ke.stage_bytes;
+  if (stages > 8) stages = 8;
+  const int k_iters = a.taps * a.chunks;
+  if (stages > 2 * k_iters && 2 * k_iters >= 2) stages = 2 * k_iters;  // never need more than two tiles worth
+  if (stages < 2) {
+    delete p;
+    return set_error(CVB_ERR_INVALID, "conv: tile does not fit in shared memory (block_n=%d block_k=%d)", bn, bk);
+  }
+  a.stages = stages;
+  p->smem = fixed + stages * ke.stage_bytes;
+  p->fn = ke.fn;
+
+  static std::mutex mu;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (g_num_sms == 0) {
+      int dev = 0;
+      cudaError_t e = cudaGetDevice(&dev);
+      if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+      if (e != cudaSuccess || g_num_sms <= 0) {
+        g_num_sms = 0;
+        delete p;
+        return set_error(CVB_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(e));
+      }
+    }
+    cudaError_t e = cudaFuncSetAttribute(p->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget);
+    if (e != cudaSuccess) {
+      delete p;
+      return set_error(CVB_ERR_CUDA, "cudaFuncSetAttribute(smem) failed: %s", cudaGetErrorString(e));
+    }
+  }
+  const long long total = (long long)a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
+  int sms = g_num_sms;
+  if (d->sm_limit > 0 && d->sm_limit < sms) sms = d->sm_limit;
+  p->grid = (int)(total < sms ? total : sms);
+  *out_plan = p;
+  return CVB_OK;
+}
+
+extern "C" int cvb_conv_plan_run(const CvbConvPlan* p, void* stream) {
+  using namespace cvb;
+  CVB_REQUIRE(p != nullptr, "null plan");
+  void* kargs[1] = {const_cast<ConvKArgs*>(&p->args)};
+  CVB_CHECK_CUDA(cudaLaunchKernel(p->fn, dim3(p->grid), dim3(kThreads), kargs, (size_t)p->smem, as_stream(stream)));
+  count_launch();
+  return CVB_OK;
+}
+
+extern "C" int cvb_conv_plan_run_many(CvbConvPlan* const* plans, int32_t n, void* stream) {
+  for (int i = 0; i < n; ++i) {
+    int rc = cvb_conv_plan_run(plans[i], stream);
+    if (rc != CVB_OK) return rc;
+  }
+  return CVB_OK;
+}
+
+extern "C" void cvb_conv_plan_destroy(CvbConvPlan* p) { delete p; }

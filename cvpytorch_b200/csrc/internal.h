@@ -1,0 +1,38 @@
+// Internal helpers shared by the translation units of libcvb200.so (not part of the C ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+
+#include "../../include/cvb200.h"
+
+namespace cvb {
+
+// thread-local error text returned by cvb_last_error_string()
+int set_error(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define CVB_CHECK_CUDA(expr)                                                                       \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess)                                                                         \
+      return ::cvb::set_error(CVB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define CVB_REQUIRE(cond, ...)                                       \
+  do {                                                               \
+    if (!(cond)) return ::cvb::set_error(CVB_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+// cuTensorMapEncodeTiled resolved through the runtime (no link-time dependency on libcuda).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_tiled();
+
+inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace cvb

@@ -1,0 +1,447 @@
+// Batched YOLOv5 non-max suppression, all images in flight at once, no host synchronisation.
+//
+// Replaces the reference's Python loop over images (src/models/yolov5.py:87-151: ~15 ATen launches + one
+// torchvision.ops.nms with a device->host sync per image).  Semantics reproduced bit-for-bit:
+//   * candidate = anchor with obj > conf (yolov5.py:71,90); conf = cls*obj in fp32 (:106); multi_label keeps every
+//     (anchor, class) with conf > thres in nonzero() row-major order (:112-114), else best class (:116-117)
+//   * if more than max_nms candidates: keep the max_nms highest scores (:131-132)
+//   * boxes: xywh2xyxy in fp32 (:52-59), class offset cls*max_wh added in fp32 (:135-136)
+//   * torchvision.ops.nms (third-party, v0.7..0.26 identical): stable sort by score descending (ties: lower
+//     candidate index first), greedy, suppress when  inter/(a_i+a_j-inter) > iou_thres  with the comparison done
+//     in DOUBLE (the CPU kernel compares the float IoU against the double threshold), areas without +1
+//   * at most max_det rows returned (:138-139).  Greedy NMS only needs candidates in score order until max_det
+//     boxes are kept, so the scan stops early; the output is identical to truncating the full keep list.
+//
+// Pipeline: histogram of score bits -> per-image threshold bin (top max_nms) -> emit 64-bit keys
+// (score bits << 32 | ~candidate id) -> segmented bitonic sort (descending; shared-memory fused below 4096)
+// -> per-image greedy scan (warp-ballot compaction, 512x512 bit mask in shared memory, single-warp resolve).
+#include <cuda_fp16.h>
+
+#include "internal.h"
+
+namespace cvb {
+
+constexpr int kBins = 16384;   // score_bits >> 17 for positive floats
+constexpr int kCap = 65536;    // candidate key capacity per image
+constexpr int kChunk = 4096;   // keys sorted per CTA in shared memory
+constexpr int kGreedyThreads = 512;
+
+struct NmsWs {
+  uint32_t* hist;   // [B][kBins]
+  uint32_t* cnt;    // [B]
+  uint32_t* tbin;   // [B]
+  uint64_t* keys;   // [B][kCap]
+};
+
+__host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static NmsWs carve_ws(void* ws, int B) {
+  NmsWs w;
+  uint8_t* p = static_cast<uint8_t*>(ws);
+  w.hist = reinterpret_cast<uint32_t*>(p);
+  p += align_up((size_t)B * kBins * 4, 256);
+  w.cnt = reinterpret_cast<uint32_t*>(p);
+  p += align_up((size_t)B * 4, 256);
+  w.tbin = reinterpret_cast<uint32_t*>(p);
+  p += align_up((size_t)B * 4, 256);
+  w.keys = reinterpret_cast<uint64_t*>(p);
+  return w;
+}
+
+// ------------------------------------------------------------------ pass 1/2: scan predictions (warp per anchor row)
+template <bool EMIT>
+__global__ void nms_scan_kernel(const float* __restrict__ pred, int B, int A, int nc, float conf, int multi_label, NmsWs ws,
+                                int* __restrict__ status) {
+  const int no = nc + 5;
+  const int lane = threadIdx.x & 31;
+  const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
+  const long long rows = (long long)B * A;
+  for (long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
+    const float* r = pred + row * no;
+    const float obj = __ldg(r + 4);
+    if (!(obj > conf)) continue;
+    const int b = (int)(row / A);
+    const int anchor = (int)(row % A);
+    uint32_t tb = 0;
+    if (EMIT) tb = ws.tbin[b];
+    if (multi_label) {
+      for (int c = lane; c < nc; c += 32) {
+        const float s = __fmul_rn(__ldg(r + 5 + c), obj);
+        if (s > conf) {
+          const uint32_t bits = __float_as_uint(s);
+          const uint32_t bin = min(bits >> 17, (uint32_t)(kBins - 1));
+          if (EMIT) {
+            if (bin >= tb) {
+              const uint32_t pos = atomicAdd(&ws.cnt[b], 1u);
+              const uint32_t id = (uint32_t)anchor * (uint32_t)nc + (uint32_t)c;
+              if (pos < (uint32_t)kCap) ws.keys[(size_t)b * kCap + pos] = ((uint64_t)bits << 32) | (uint64_t)(0xFFFFFFFFu - id);
+              else if (status) atomicExch(&status[0], 1);
+            }
+          } else {
+            atomicAdd(&ws.hist[(size_t)b * kBins + bin], 1u);
+          }
+        }
+      }
+    } else {
+      // best class only: conf, j = x[:, 5:].max(1)  (first maximum wins ties)
+      float best = -1.0f;
+      int bi = 0x7fffffff;
+      for (int c = lane; c < nc; c += 32) {
+        const float s = __fmul_rn(__ldg(r + 5 + c), obj);
+        if (s > best) {
+          best = s;
+          bi = c;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob > best || (ob == best && oi < bi)) {
+          best = ob;
+          bi = oi;
+        }
+      }
+      if (lane == 0 && best > conf) {
+        const uint32_t bits = __float_as_uint(best);
+        const uint32_t bin = min(bits >> 17, (uint32_t)(kBins - 1));
+        if (EMIT) {
+          if (bin >= tb) {
+            const uint32_t pos = atomicAdd(&ws.cnt[b], 1u);
+            const uint32_t id = (uint32_t)anchor * (uint32_t)nc + (uint32_t)bi;
+            if (pos < (uint32_t)kCap) ws.keys[(size_t)b * kCap + pos] = ((uint64_t)bits << 32) | (uint64_t)(0xFFFFFFFFu - id);
+            else if (status) atomicExch(&status[0], 1);
+          }
+        } else {
+          atomicAdd(&ws.hist[(size_t)b * kBins + bin], 1u);
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ threshold bin: smallest set of top bins holding >= max_nms
+__global__ void nms_threshold_kernel(NmsWs ws, int max_nms) {
+  __shared__ uint32_t part[256];
+  const int b = blockIdx.x;
+  const uint32_t* h = ws.hist + (size_t)b * kBins;
+  constexpr int per = kBins / 256;
+  const int t = threadIdx.x;
+  const int hi_bin = kBins - 1 - t * per;  // this thread walks bins hi_bin, hi_bin-1, ... (top-down)
+  uint32_t s = 0;
+  for (int i = 0; i < per; ++i) s += h[hi_bin - i];
+  part[t] = s;
+  __syncthreads();
+  if (t == 0) {
+    uint32_t run = 0;
+    for (int i = 0; i < 256; ++i) {
+      const uint32_t v = part[i];
+      part[i] = run;  // exclusive prefix (count in all higher bins)
+      run += v;
+    }
+    ws.tbin[b] = 0;  // default: everything
+  }
+  __syncthreads();
+  uint32_t run = part[t];
+  if (run < (uint32_t)max_nms) {
+    for (int i = 0; i < per; ++i) {
+      run += h[hi_bin - i];
+      if (run >= (uint32_t)max_nms) {
+        ws.tbin[b] = (uint32_t)(hi_bin - i);  // exactly one thread crosses the threshold
+        break;
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ segmented bitonic sort (descending)
+__device__ __forceinline__ uint32_t seg_npad(const NmsWs& ws, int b, uint32_t* n_out) {
+  uint32_t n = ws.cnt[b];
+  if (n > (uint32_t)kCap) n = kCap;
+  *n_out = n;
+  return n <= 1 ? 1u : (1u << (32 - __clz(n - 1)));
+}
+
+__device__ __forceinline__ void cmpswap(uint64_t* s, int i, int l, bool desc) {
+  const uint64_t x = s[i], y = s[l];
+  if (desc ? (x < y) : (x > y)) {
+    s[i] = y;
+    s[l] = x;
+  }
+}
+
+// full sort of each 4096-key chunk (stages k = 2..4096)
+__global__ void __launch_bounds__(1024) bitonic_local_sort_kernel(NmsWs ws) {
+  __shared__ uint64_t s[kChunk];
+  const int b = blockIdx.y;
+  uint32_t n;
+  const uint32_t npad = seg_npad(ws, b, &n);
+  const uint32_t start = blockIdx.x * kChunk;
+  if (start >= npad) return;
+  uint64_t* keys = ws.keys + (size_t)b * kCap;
+  for (int i = threadIdx.x; i < kChunk; i += blockDim.x) s[i] = (start + i < n) ? keys[start + i] : 0ull;
+  for (int k = 2; k <= kChunk; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      __syncthreads();
+      for (int t = threadIdx.x; t < kChunk / 2; t += blockDim.x) {
+        const int i = 2 * j * (t / j) + (t % j);
+        cmpswap(s, i, i + j, ((start + i) & k) == 0);
+      }
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kChunk; i += blockDim.x) keys[start + i] = s[i];
+}
+
+// one compare-exchange step with partner distance j >= kChunk
+__global__ void bitonic_global_step_kernel(NmsWs ws, uint32_t k, uint32_t j) {
+  const int b = blockIdx.y;
+  uint32_t n;
+  const uint32_t npad = seg_npad(ws, b, &n);
+  if (k > npad) return;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = 2 * j * (t / j) + (t % j);
+  if (i >= npad) return;
+  uint64_t* keys = ws.keys + (size_t)b * kCap;
+  const uint64_t x = keys[i], y = keys[i + j];
+  const bool desc = (i & k) == 0;
+  if (desc ? (x < y) : (x > y)) {
+    keys[i] = y;
+    keys[i + j] = x;
+  }
+}
+
+// remaining steps j = kChunk/2 .. 1 of stage k, fused in shared memory
+__global__ void __launch_bounds__(1024) bitonic_local_merge_kernel(NmsWs ws, uint32_t k) {
+  __shared__ uint64_t s[kChunk];
+  const int b = blockIdx.y;
+  uint32_t n;
+  const uint32_t npad = seg_npad(ws, b, &n);
+  if (k > npad) return;
+  const uint32_t start = blockIdx.x * kChunk;
+  if (start >= npad) return;
+  uint64_t* keys = ws.keys + (size_t)b * kCap;
+  for (int i = threadIdx.x; i < kChunk; i += blockDim.x) s[i] = keys[start + i];
+  for (int j = kChunk >> 1; j > 0; j >>= 1) {
+    __syncthreads();
+    for (int t = threadIdx.x; t < kChunk / 2; t += blockDim.x) {
+      const int i = 2 * j * (t / j) + (t % j);
+      cmpswap(s, i, i + j, ((start + i) & k) == 0);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kChunk; i += blockDim.x) keys[start + i] = s[i];
+}
+
+// ------------------------------------------------------------------ greedy scan
+__device__ __forceinline__ bool iou_gt(const float4& a, float aa, const float4& b, float ab, double thr) {
+  const float xx1 = fmaxf(a.x, b.x), yy1 = fmaxf(a.y, b.y);
+  const float xx2 = fminf(a.z, b.z), yy2 = fminf(a.w, b.w);
+  const float w = fmaxf(0.0f, __fsub_rn(xx2, xx1));
+  const float h = fmaxf(0.0f, __fsub_rn(yy2, yy1));
+  const float inter = __fmul_rn(w, h);
+  const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
+  return (double)ovr > thr;
+}
+
+struct GreedySmem {
+  float4 cbox[kGreedyThreads];   // class-offset boxes of the alive candidates of this chunk (compacted)
+  float4 cbox0[kGreedyThreads];  // un-offset boxes
+  float carea[kGreedyThreads];
+  float cscore[kGreedyThreads];
+  uint32_t cid[kGreedyThreads];
+  uint32_t mask[kGreedyThreads][kGreedyThreads / 32];
+  uint32_t keeplist[kGreedyThreads];
+  uint32_t warp_cnt[kGreedyThreads / 32];
+  uint32_t m_alive, new_kept;
+};
+
+__global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const float* __restrict__ pred, int A, int nc, NmsWs ws,
+                                                                     double iou_thr, int max_nms, int max_det, float max_wh,
+                                                                     float* __restrict__ det, int* __restrict__ det_idx,
+                                                                     int* __restrict__ det_count) {
+  extern __shared__ uint8_t gs_raw[];
+  GreedySmem& S = *reinterpret_cast<GreedySmem*>(gs_raw);
+  float4* kbox = reinterpret_cast<float4*>(gs_raw + sizeof(GreedySmem));  // [max_det]
+  float* karea = reinterpret_cast<float*>(kbox + max_det);                // [max_det]
+
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int no = nc + 5;
+  uint32_t n = ws.cnt[b];
+  if (n > (uint32_t)kCap) n = kCap;
+  if (n > (uint32_t)max_nms) n = max_nms;
+  const uint64_t* keys = ws.keys + (size_t)b * kCap;
+  int kept_n = 0;
+
+  for (uint32_t base = 0; base < n && kept_n < max_det; base += kGreedyThreads) {
+    const uint32_t i = base + tid;
+    bool alive = i < n;
+    float4 box = make_float4(0, 0, 0, 0), box0 = box;
+    float area = 0.0f, score = 0.0f;
+    uint32_t id = 0;
+    if (alive) {
+      const uint64_t key = keys[i];
+      id = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+      score = __uint_as_float((uint32_t)(key >> 32));
+    }
+    if (alive) {
+      const uint32_t anchor = id / (uint32_t)nc, cls = id % (uint32_t)nc;
+      const float* r = pred + ((size_t)b * A + anchor) * no;
+      const float cx = __ldg(r), cy = __ldg(r + 1), w = __ldg(r + 2), h = __ldg(r + 3);
+      const float hw = __fmul_rn(w, 0.5f), hh = __fmul_rn(h, 0.5f);
+      box0 = make_float4(__fsub_rn(cx, hw), __fsub_rn(cy, hh), __fadd_rn(cx, hw), __fadd_rn(cy, hh));
+      const float off = __fmul_rn((float)cls, max_wh);
+      box = make_float4(__fadd_rn(box0.x, off), __fadd_rn(box0.y, off), __fadd_rn(box0.z, off), __fadd_rn(box0.w, off));
+      area = __fmul_rn(__fsub_rn(box.z, box.x), __fsub_rn(box.w, box.y));
+      // phase 1: suppressed by an already kept (higher score) box?
+      for (int k = 0; k < kept_n; ++k) {
+        if (iou_gt(kbox[k], karea[k], box, area, iou_thr)) {
+          alive = false;
+          break;
+        }
+      }
+    }
+    // order-preserving compaction of the survivors
+    const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+    if (lane == 0) S.warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t v = (lane < kGreedyThreads / 32) ? S.warp_cnt[lane] : 0;
+      uint32_t inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      if (lane < kGreedyThreads / 32) S.warp_cnt[lane] = inc - v;
+      if (lane == 31) S.m_alive = inc;
+    }
+    __syncthreads();
+    const int m = (int)S.m_alive;
+    if (alive) {
+      const int pos = (int)S.warp_cnt[warp] + __popc(bal & ((1u << lane) - 1));
+      S.cbox[pos] = box;
+      S.cbox0[pos] = box0;
+      S.carea[pos] = area;
+      S.cscore[pos] = score;
+      S.cid[pos] = id;
+    }
+    __syncthreads();
+    // phase 2: suppression bit mask among the m survivors (row r suppresses column c > r)
+    const int words = (m + 31) >> 5;
+    if (tid < m) {
+      const float4 me = S.cbox[tid];
+      const float ma = S.carea[tid];
+      for (int wd = 0; wd < words; ++wd) {
+        uint32_t bits = 0;
+        const int c0 = wd << 5;
+        const int c1 = min(m, c0 + 32);
+        for (int c = max(c0, tid + 1); c < c1; ++c)
+          if (iou_gt(me, ma, S.cbox[c], S.carea[c], iou_thr)) bits |= 1u << (c & 31);
+        S.mask[tid][wd] = bits;
+      }
+    }
+    __syncthreads();
+    // phase 3: sequential greedy resolve by one warp; lane l owns word l of the "removed" bitset
+    if (warp == 0) {
+      uint32_t removed = 0;
+      int nk = 0;
+      for (int r = 0; r < m; ++r) {
+        if (kept_n + nk >= max_det) break;
+        const uint32_t rw = __shfl_sync(0xffffffffu, removed, r >> 5);
+        if (!((rw >> (r & 31)) & 1u)) {
+          if (lane == 0) S.keeplist[nk] = (uint32_t)r;
+          ++nk;
+          if (lane < words) removed |= S.mask[r][lane];
+        }
+      }
+      if (lane == 0) S.new_kept = (uint32_t)nk;
+    }
+    __syncthreads();
+    // phase 4: append to the kept list and write the detections
+    const int nk = (int)S.new_kept;
+    for (int t = tid; t < nk; t += kGreedyThreads) {
+      const int r = (int)S.keeplist[t];
+      const int o = kept_n + t;
+      kbox[o] = S.cbox[r];
+      karea[o] = S.carea[r];
+      const float4 b0 = S.cbox0[r];
+      float* d = det + ((size_t)b * max_det + o) * 6;
+      d[0] = b0.x;
+      d[1] = b0.y;
+      d[2] = b0.z;
+      d[3] = b0.w;
+      d[4] = S.cscore[r];
+      d[5] = (float)(S.cid[r] % (uint32_t)nc);
+      det_idx[(size_t)b * max_det + o] = (int)S.cid[r];
+    }
+    kept_n += nk;
+    __syncthreads();
+  }
+  if (tid == 0) det_count[b] = kept_n;
+}
+
+}  // namespace cvb
+
+using namespace cvb;
+
+extern "C" size_t cvb_nms_workspace_bytes(int32_t B, int32_t A, int32_t nc) {
+  (void)A;
+  (void)nc;
+  if (B <= 0) return 0;
+  return align_up((size_t)B * kBins * 4, 256) + 2 * align_up((size_t)B * 4, 256) + (size_t)B * kCap * 8;
+}
+
+extern "C" int cvb_yolo_nms(const float* prediction, const CvbNmsParams* p, float* det, int32_t* det_idx, int32_t* det_count,
+                            void* workspace, size_t workspace_bytes, int32_t* status, void* stream) {
+  CVB_REQUIRE(prediction && p && det && det_idx && det_count && workspace, "nms: null argument");
+  CVB_REQUIRE(p->B > 0 && p->A > 0 && p->nc > 0, "nms: bad shape");
+  CVB_REQUIRE(p->max_det > 0 && p->max_det <= 4096 && p->max_nms > 0, "nms: bad limits");
+  CVB_REQUIRE((long long)p->A * p->nc < 0x7fffffffLL, "nms: candidate id overflow");
+  CVB_REQUIRE(workspace_bytes >= cvb_nms_workspace_bytes(p->B, p->A, p->nc), "nms: workspace too small");
+  CVB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "nms: workspace must be 256-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  NmsWs ws = carve_ws(workspace, p->B);
+  const size_t head_bytes = align_up((size_t)p->B * kBins * 4, 256) + 2 * align_up((size_t)p->B * 4, 256);
+  CVB_CHECK_CUDA(cudaMemsetAsync(workspace, 0, head_bytes, st));
+  if (status) CVB_CHECK_CUDA(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st));
+  CVB_CHECK_CUDA(cudaMemsetAsync(det, 0, (size_t)p->B * p->max_det * 6 * sizeof(float), st));
+  CVB_CHECK_CUDA(cudaMemsetAsync(det_idx, 0xFF, (size_t)p->B * p->max_det * sizeof(int32_t), st));
+
+  const long long rows = (long long)p->B * p->A;
+  const int block = 256;
+  long long grid = (rows + 7) / 8;
+  if (grid > 148 * 8) grid = 148 * 8;
+  nms_scan_kernel<false><<<(int)grid, block, 0, st>>>(prediction, p->B, p->A, p->nc, p->conf_thres, p->multi_label, ws, status);
+  nms_threshold_kernel<<<p->B, 256, 0, st>>>(ws, p->max_nms);
+  nms_scan_kernel<true><<<(int)grid, block, 0, st>>>(prediction, p->B, p->A, p->nc, p->conf_thres, p->multi_label, ws, status);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(3);
+
+  dim3 lgrid(kCap / kChunk, p->B);
+  bitonic_local_sort_kernel<<<lgrid, 1024, 0, st>>>(ws);
+  count_launch();
+  for (uint32_t k = 2 * kChunk; k <= (uint32_t)kCap; k <<= 1) {
+    for (uint32_t j = k >> 1; j >= (uint32_t)kChunk; j >>= 1) {
+      dim3 ggrid(kCap / 2 / 256, p->B);
+      bitonic_global_step_kernel<<<ggrid, 256, 0, st>>>(ws, k, j);
+      count_launch();
+    }
+    bitonic_local_merge_kernel<<<lgrid, 1024, 0, st>>>(ws, k);
+    count_launch();
+  }
+  CVB_CHECK_CUDA(cudaGetLastError());
+
+  const size_t smem = sizeof(GreedySmem) + (size_t)p->max_det * (sizeof(float4) + sizeof(float));
+  static bool attr_set = false;
+  if (!attr_set) {
+    CVB_CHECK_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  CVB_REQUIRE(smem <= 200 * 1024, "nms: max_det too large");
+  nms_greedy_kernel<<<p->B, kGreedyThreads, smem, st>>>(prediction, p->A, p->nc, ws, p->iou_thres, p->max_nms, p->max_det,
+                                                        p->max_wh, det, det_idx, det_count);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}

@@ -1,0 +1,231 @@
+"""Python wrappers over the C ABI: device tensor containers + one function per cvb_* entry point.
+
+PyTorch is used only as plumbing (device memory, streams); all arithmetic on the hot path happens in
+libcvb200.so.  Host-side weight preparation (BN folding, hi/lo split, K-major packing) also lives here.
+"""
+import ctypes
+import math
+from ctypes import byref, c_void_p
+
+import torch
+
+from . import _lib
+from ._lib import CVB_ACT_NONE, CVB_ACT_RELU, CVB_ACT_SILU, CVB_OUT_F32, CVB_OUT_SPLIT16, CvbConvDesc, CvbNmsParams, CvbView
+
+ACTS = {None: CVB_ACT_NONE, 'none': CVB_ACT_NONE, 'silu': CVB_ACT_SILU, 'swish': CVB_ACT_SILU, 'relu': CVB_ACT_RELU}
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise _lib.CvbError(f'{what}: tensor must live on a CUDA device (the B200 path has no CPU fallback)')
+
+
+class SplitTensor:
+    """NHWC activation stored as two fp16 planes [2, B, H, W, C] (hi, lo); x = hi + lo."""
+
+    def __init__(self, B, H, W, C, device='cuda', data=None):
+        self.B, self.H, self.W, self.C = B, H, W, C
+        self.data = data if data is not None else torch.zeros((2, B, H, W, C), dtype=torch.float16, device=device)
+        assert self.data.is_contiguous() and self.data.dtype == torch.float16
+
+    def view(self, c0=0, c=None):
+        c = self.C - c0 if c is None else c
+        assert 0 <= c0 and c0 + c <= self.C and c0 % 8 == 0
+        v = CvbView()
+        v.base = self.data.data_ptr() + 2 * c0
+        v.B, v.H, v.W, v.C = self.B, self.H, self.W, c
+        v.c_pitch = self.C
+        v.plane_stride = 2 * self.B * self.H * self.W * self.C
+        return v
+
+    def to_float_nhwc(self):
+        """Debug helper: fp32 [B,H,W,C] = hi + lo (torch ops; not used on the hot path)."""
+        return self.data[0].float() + self.data[1].float()
+
+
+class F32Tensor:
+    """Plain fp32 NHWC tensor [B, H, W, C] (partials, head logits)."""
+
+    def __init__(self, B, H, W, C, device='cuda'):
+        self.B, self.H, self.W, self.C = B, H, W, C
+        self.data = torch.zeros((B, H, W, C), dtype=torch.float32, device=device)
+
+    def view(self, c0=0, c=None):
+        c = self.C - c0 if c is None else c
+        assert c0 % 4 == 0 and c0 + c <= self.C
+        v = CvbView()
+        v.base = self.data.data_ptr() + 4 * c0
+        v.B, v.H, v.W, v.C = self.B, self.H, self.W, c
+        v.c_pitch = self.C
+        v.plane_stride = 0
+        return v
+
+
+def null_view():
+    v = CvbView()
+    v.base = None
+    return v
+
+
+# --------------------------------------------------------------------------------------- host-side weight prep
+def fold_conv_bn(weight, bias=None, bn=None):
+    """Folds eval-mode BatchNorm into the conv (float64 on the host, rounded once to fp32).
+
+    Algebra of the reference's src/utils/fuse.py:33-54:  W' = W * g/sqrt(var+eps),  b' = (b - mean) * g/sqrt(var+eps) + beta
+    bn = (gamma, beta, running_mean, running_var, eps) or None.
+    """
+    w = weight.detach().double().cpu()
+    b = torch.zeros(w.shape[0], dtype=torch.float64) if bias is None else bias.detach().double().cpu()
+    if bn is not None:
+        gamma, beta, mean, var, eps = bn
+        scale = gamma.detach().double().cpu() / torch.sqrt(var.detach().double().cpu() + eps)
+        w = w * scale.view(-1, 1, 1, 1)
+        b = (b - mean.detach().double().cpu()) * scale + beta.detach().double().cpu()
+    return w, b
+
+
+def pack_conv_weights(w64, b64, cin_pad=None, device='cuda'):
+    """[O,I,kh,kw] float64 -> (fp16 [2, O_pad, kh*kw*I_pad] K-major hi/lo planes, fp32 bias [O_pad])."""
+    O, I, kh, kw = w64.shape
+    cin_pad = I if cin_pad is None else cin_pad
+    o_pad = (O + 7) // 8 * 8
+    w = torch.zeros((o_pad, kh, kw, cin_pad), dtype=torch.float64)
+    w[:O, :, :, :I] = w64.permute(0, 2, 3, 1)
+    w = w.reshape(o_pad, kh * kw * cin_pad)
+    hi = w.to(torch.float16)
+    lo = (w - hi.double()).to(torch.float16)
+    packed = torch.stack([hi, lo], 0).contiguous()
+    bias = torch.zeros(o_pad, dtype=torch.float32)
+    bias[:O] = b64.float()
+    return packed.to(device), bias.to(device)
+
+
+def stem_weights_to_s2d(w64):
+    """6x6/s2/p2 stem kernel [O,3,6,6] -> equivalent 3x3/s1/p1 kernel over the 16-channel space-to-depth input.
+
+    in(2h'+dy, 2w'+dx, c) sits at s2d channel (dy*2+dx)*3+c of pixel (h', w'); kernel row kh = 2a+dy.
+    """
+    O, I, kh, kw = w64.shape
+    assert (I, kh, kw) == (3, 6, 6)
+    out = torch.zeros((O, 16, 3, 3), dtype=torch.float64)
+    for a in range(3):
+        for b in range(3):
+            for dy in range(2):
+                for dx in range(2):
+                    for c in range(3):
+                        out[:, (dy * 2 + dx) * 3 + c, a, b] = w64[:, c, 2 * a + dy, 2 * b + dx]
+    return out
+
+
+# --------------------------------------------------------------------------------------- op wrappers
+class ConvPlan:
+    """Owns a CvbConvPlan handle (host-side TMA descriptors + launch shape) and keeps its tensors alive."""
+
+    def __init__(self, inp, out, weights, bias, k, stride=1, pad=0, dilation=1, act=None, residual=None,
+                 up_partial=None, block_n=0, sm_limit=0, keepalive=()):
+        d = CvbConvDesc()
+        d.inp, d.out = inp, out
+        d.weights = weights.data_ptr()
+        d.cout_pad = weights.shape[1]
+        d.bias = bias.data_ptr()
+        d.kh = d.kw = k
+        d.stride, d.pad, d.dilation = stride, pad, dilation
+        d.act = ACTS[act]
+        d.out_kind = CVB_OUT_F32 if out.plane_stride == 0 else CVB_OUT_SPLIT16
+        d.residual = residual if residual is not None else null_view()
+        d.up_partial = up_partial if up_partial is not None else null_view()
+        d.block_n, d.sm_limit = block_n, sm_limit
+        self._keep = (weights, bias) + tuple(keepalive)
+        self.handle = c_void_p()
+        _lib.check(_lib.lib().cvb_conv_plan_create(byref(d), byref(self.handle)), 'cvb_conv_plan_create')
+
+    def run(self):
+        _lib.check(_lib.lib().cvb_conv_plan_run(self.handle, _stream()), 'cvb_conv_plan_run')
+
+    def __del__(self):
+        try:
+            if getattr(self, 'handle', None) is not None and self.handle.value:
+                _lib.lib().cvb_conv_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+def run_plans(plans):
+    arr = (c_void_p * len(plans))(*[p.handle for p in plans])
+    _lib.check(_lib.lib().cvb_conv_plan_run_many(arr, len(plans), _stream()), 'cvb_conv_plan_run_many')
+
+
+def nchw_to_split(x, dst_view):
+    _require_cuda(x, 'nchw_to_split')
+    x = x.contiguous().float()
+    B, C, H, W = x.shape
+    _lib.check(_lib.lib().cvb_nchw_to_split(x.data_ptr(), B, C, H, W, byref(dst_view), _stream()), 'cvb_nchw_to_split')
+
+
+def split_to_nchw(src_view, out=None):
+    if out is None:
+        out = torch.empty((src_view.B, src_view.C, src_view.H, src_view.W), dtype=torch.float32, device='cuda')
+    _lib.check(_lib.lib().cvb_split_to_nchw(byref(src_view), out.data_ptr(), _stream()), 'cvb_split_to_nchw')
+    return out
+
+
+def f32nhwc_to_nchw(src_view, out=None):
+    if out is None:
+        out = torch.empty((src_view.B, src_view.C, src_view.H, src_view.W), dtype=torch.float32, device='cuda')
+    _lib.check(_lib.lib().cvb_f32nhwc_to_nchw(byref(src_view), out.data_ptr(), _stream()), 'cvb_f32nhwc_to_nchw')
+    return out
+
+
+def stem_s2d(x, dst_view):
+    _require_cuda(x, 'stem_s2d')
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    B, C, H, W = x.shape
+    assert C == 3
+    _lib.check(_lib.lib().cvb_stem_s2d(x.data_ptr(), B, H, W, byref(dst_view), _stream()), 'cvb_stem_s2d')
+
+
+def sppf_pool(x, y1, y2, y3):
+    _lib.check(_lib.lib().cvb_sppf_pool(byref(x), byref(y1), byref(y2), byref(y3), _stream()), 'cvb_sppf_pool')
+
+
+def yolo_decode(raw_view, na, no, anchors_px, stride, z, z_rows, z_off, xperm=None):
+    _lib.check(_lib.lib().cvb_yolo_decode(byref(raw_view), na, no, anchors_px.data_ptr(), float(stride),
+                                          z.data_ptr() if z is not None else None, z_rows, z_off,
+                                          xperm.data_ptr() if xperm is not None else None, _stream()), 'cvb_yolo_decode')
+
+
+class NmsWorkspace:
+    def __init__(self, B, A, nc, max_det=300, device='cuda'):
+        self.B, self.A, self.nc, self.max_det = B, A, nc, max_det
+        nbytes = int(_lib.lib().cvb_nms_workspace_bytes(B, A, nc))
+        self.ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+        off = (-self.ws.data_ptr()) % 256
+        self.ws_ptr = self.ws.data_ptr() + off
+        self.ws_bytes = nbytes
+        self.det = torch.zeros((B, max_det, 6), dtype=torch.float32, device=device)
+        self.det_idx = torch.zeros((B, max_det), dtype=torch.int32, device=device)
+        self.det_count = torch.zeros((B,), dtype=torch.int32, device=device)
+        self.status = torch.zeros((4,), dtype=torch.int32, device=device)
+
+
+def yolo_nms(prediction, ws, conf_thres=0.001, iou_thres=0.6, multi_label=True, max_nms=30000, max_wh=4096.0):
+    """Batched NMS on device.  Returns (det [B,max_det,6], det_idx [B,max_det], det_count [B]) -- device tensors
+    owned by `ws`; no host synchronisation happens here."""
+    _require_cuda(prediction, 'yolo_nms')
+    assert prediction.dtype == torch.float32 and prediction.is_contiguous()
+    B, A, no = prediction.shape
+    assert (B, A, no - 5) == (ws.B, ws.A, ws.nc)
+    p = CvbNmsParams()
+    p.B, p.A, p.nc = B, A, no - 5
+    p.conf_thres, p.iou_thres = conf_thres, iou_thres
+    p.multi_label = 1 if (multi_label and no - 5 > 1) else 0
+    p.max_nms, p.max_det, p.max_wh = max_nms, ws.max_det, max_wh
+    _lib.check(_lib.lib().cvb_yolo_nms(prediction.data_ptr(), byref(p), ws.det.data_ptr(), ws.det_idx.data_ptr(),
+                                       ws.det_count.data_ptr(), ws.ws_ptr, ws.ws_bytes, ws.status.data_ptr(), _stream()),
+               'cvb_yolo_nms')
+    return ws.det, ws.det_idx, ws.det_count

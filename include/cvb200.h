@@ -1,0 +1,151 @@
+/*
+ * cvb200.h -- C ABI of libcvb200.so: the B200 (sm_100a) detector forward hot path.
+ *
+ * The reference (shanglianlm0525/CvPytorch) is pure Python on PyTorch and has no FFI; every entry
+ * point below replaces a run of PyTorch/torchvision library calls on the reference's inference
+ * path.  The "replaces" notes cite the reference file:line (paths relative to /root/reference).
+ *
+ * Conventions
+ *   - plain pointers + sizes only; no torch / C++ types cross this boundary.
+ *   - every device buffer (activations, weights, workspaces, outputs) is OWNED BY THE CALLER; the
+ *     library never allocates or frees device memory and keeps no reference after a call returns,
+ *     except for the raw pointers baked into a CvbConvPlan (valid while the caller keeps them alive).
+ *   - all work is enqueued on the cudaStream_t passed in (as void*); no call synchronises the
+ *     device or reads device memory from the host, so every *_run entry point is CUDA-graph
+ *     capturable.  Plan creation only encodes TMA descriptors on the host.
+ *   - return value: 0 = CVB_OK, negative = error; cvb_last_error_string() gives the thread-local text.
+ *
+ * Activation layout ("split-NHWC"): two fp16 planes [2][B][H][W][C]; plane 0 = hi = fp16(x),
+ * plane 1 = lo = fp16(x - hi).  hi+lo carries ~22 mantissa bits, so three fp16 tensor-core
+ * products (hi*hi + hi*lo + lo*hi, fp32 accumulate in TMEM) reproduce fp32 convolution to ~1e-5.
+ */
+#ifndef CVB200_H_
+#define CVB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CVB_OK 0
+#define CVB_ERR_INVALID (-1)   /* bad argument / unsupported shape            */
+#define CVB_ERR_CUDA (-2)      /* CUDA runtime / driver error                 */
+#define CVB_ERR_NO_DEVICE (-3) /* no sm_100 device / driver entry point found */
+
+#define CVB_ACT_NONE 0
+#define CVB_ACT_SILU 1 /* x*sigmoid(x)   src/models/bricks/swish.py:9-25, nn.SiLU */
+#define CVB_ACT_RELU 2
+
+#define CVB_OUT_SPLIT16 0 /* two fp16 planes (hi, lo)          */
+#define CVB_OUT_F32 1     /* plain fp32 NHWC (partials / heads) */
+
+/* A channel-slice view of an NHWC tensor. */
+typedef struct CvbView {
+  void* base;           /* device pointer to element (b=0,h=0,w=0,c=first channel of the view), plane 0 */
+  int32_t B, H, W, C;   /* logical extent of the view                                                */
+  int32_t c_pitch;      /* channels per pixel of the underlying buffer (>= C)                         */
+  int64_t plane_stride; /* bytes from plane 0 (hi) to plane 1 (lo); ignored for fp32 tensors          */
+} CvbView;
+
+/*
+ * Fused conv2d + folded-BN bias + activation (+ residual) (+ nearest-upsampled fp32 partial).
+ *   out = act( conv(in, W) + up2x(partial) + bias ) + residual
+ * replaces: ConvModule.forward  src/models/bricks/conv_module.py:201-214 (conv -> BN -> act),
+ *           Conv.forward        src/models/modules/yolo11_modules.py:27-39,
+ *           the shortcut add of DarknetBottleneck.forward src/models/modules/yolo_modules.py:95-104,
+ *           nn.UpsamplingNearest2d + torch.cat of UpsamplingModule.forward
+ *           src/models/modules/yolo11_modules.py:388-397 (via conv1x1(up(x)) == up(conv1x1(x))),
+ *           BN folding algebra src/utils/fuse.py:33-54 (done by the caller when packing weights).
+ * Weights: device fp16 [2 planes][cout_pad][kh*kw*cin] with k = (ky*kw + kx)*cin + c  (K-major).
+ */
+typedef struct CvbConvDesc {
+  CvbView in;           /* split16 input view, C = cin (multiple of 16)              */
+  CvbView out;          /* output view, C = cout                                     */
+  const void* weights;  /* packed fp16 hi/lo weights, see above                      */
+  int32_t cout_pad;     /* rows of the packed weight matrix (>= cout, multiple of 8) */
+  const float* bias;    /* fp32 [cout_pad] folded bias (never NULL)                  */
+  int32_t kh, kw, stride, pad, dilation;
+  int32_t act;          /* CVB_ACT_*  */
+  int32_t out_kind;     /* CVB_OUT_*  */
+  CvbView residual;     /* base == NULL -> none; split16, same B/H/W/C as out        */
+  CvbView up_partial;   /* base == NULL -> none; fp32 [B, ceil(H/2), ceil(W/2), C]   */
+  int32_t block_n;      /* 0 = auto, else 32/64/128/256                              */
+  int32_t sm_limit;     /* 0 = all SMs; else cap on the persistent grid              */
+} CvbConvDesc;
+
+typedef struct CvbConvPlan CvbConvPlan;
+
+int cvb_conv_plan_create(const CvbConvDesc* desc, CvbConvPlan** plan);
+int cvb_conv_plan_run(const CvbConvPlan* plan, void* stream);
+void cvb_conv_plan_destroy(CvbConvPlan* plan);
+/* Run n plans back to back on one stream (one C call per forward instead of one per layer). */
+int cvb_conv_plan_run_many(CvbConvPlan* const* plans, int32_t n, void* stream);
+
+/*
+ * Layout / precision conversion at the drop-in boundary (reference tensors are NCHW fp32).
+ * replaces: nothing in the reference (it stays NCHW); this is the module-boundary adapter.
+ */
+int cvb_nchw_to_split(const float* src, int32_t B, int32_t C, int32_t H, int32_t W, const CvbView* dst,
+                      void* stream);
+int cvb_split_to_nchw(const CvbView* src, float* dst, void* stream);
+/* fp32 NHWC view (e.g. head output) -> NCHW fp32 */
+int cvb_f32nhwc_to_nchw(const CvbView* src, float* dst, void* stream);
+/*
+ * Stem input adapter: NCHW fp32 [B,3,H,W] -> space-to-depth split16 [B,H/2,W/2,16] (12 used,
+ * channel = (dy*2+dx)*3 + c, 4 zero pad) so that the 6x6/s2/p2 stem conv
+ * (src/models/backbones/det/yolov5_csp_darknet.py:36-45) becomes a 3x3/s1/p1 tensor-core conv.
+ */
+int cvb_stem_s2d(const float* src, int32_t B, int32_t H, int32_t W, const CvbView* dst, void* stream);
+
+/*
+ * SPPF pooling: y1=maxpool5(x), y2=maxpool5(y1), y3=maxpool5(y2) (stride 1, pad 2), written to
+ * three channel slices.  replaces: SPPF.forward src/models/modules/yolo_modules.py:185-194 /
+ * src/models/modules/yolo11_modules.py:282-288 (3 x nn.MaxPool2d + torch.cat).
+ */
+int cvb_sppf_pool(const CvbView* x, const CvbView* y1, const CvbView* y2, const CvbView* y3, void* stream);
+
+/*
+ * YOLOv5 decode of one level.  raw: fp32 NHWC [B,ny,nx,c_pitch>=na*no] conv output (+bias).
+ *   z[b, z_off + (a*ny+y)*nx + x, :] = decode(sigmoid(raw))   (z row pitch = no floats, z_rows rows/img)
+ *   xperm (optional) = raw permuted to [B,na,ny,nx,no]
+ * replaces: YOLOv5Detect.forward src/models/detects/yolov5_detect.py:42-55, _make_grid :60-65.
+ */
+int cvb_yolo_decode(const CvbView* raw, int32_t na, int32_t no, const float* anchors_px /*[na*2]*/, float stride,
+                    float* z, int64_t z_rows, int64_t z_off, float* xperm, void* stream);
+
+/*
+ * Batched YOLOv5 NMS.  prediction: fp32 [B, A, 5+nc].  Outputs (fixed capacity, device):
+ *   det [B, max_det, 6] = (x1,y1,x2,y2,conf,cls), det_idx [B, max_det] = anchor*nc+cls of each kept
+ *   row (the "NMS-surviving box index"), det_count [B].
+ * replaces: non_max_suppression src/models/yolov5.py:62-153 (multi_label / best-class, class-offset
+ *           4096, max_nms 30000, max_det 300; the 10 s wall-clock break :149-151 is NOT reproduced),
+ *           xywh2xyxy :52-59, torchvision.ops.nms (third party) called at :137.
+ * workspace: cvb_nms_workspace_bytes(B, A, nc) bytes, caller-owned.
+ * status (device int32[4], optional): [0] overflow flag (candidate capacity exceeded), rest reserved.
+ */
+typedef struct CvbNmsParams {
+  int32_t B, A, nc;
+  float conf_thres;    /* compared in fp32: x > float(conf_thres) like the reference's tensor > scalar */
+  double iou_thres;    /* compared in double: torchvision's CPU kernel tests float IoU > double threshold */
+  int32_t multi_label; /* 1: one candidate per (box,class) pair; 0: best class only */
+  int32_t max_nms;     /* 30000 */
+  int32_t max_det;     /* 300   */
+  float max_wh;        /* 4096 class offset; 0 = agnostic */
+} CvbNmsParams;
+
+size_t cvb_nms_workspace_bytes(int32_t B, int32_t A, int32_t nc);
+int cvb_yolo_nms(const float* prediction, const CvbNmsParams* p, float* det, int32_t* det_idx, int32_t* det_count,
+                 void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
+
+/* Library info / errors */
+const char* cvb_last_error_string(void);
+int cvb_version(void);
+/* number of kernels this library has launched in this process (for bench.py's gpu_launches) */
+int64_t cvb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CVB200_H_ */

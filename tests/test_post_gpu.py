@@ -1,0 +1,90 @@
+"""Decode + batched NMS kernels (through the C ABI) against the oracle.
+NMS: kept candidate indices / rows must be BIT-EXACT vs oracle.nms_oracle (pinned to the reference's
+non_max_suppression + torchvision.ops.nms by tests/test_oracle_golden.py)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _nms_case(pred, conf=0.001, iou=0.6, multi_label=True, max_det=300):
+    from cvpytorch_b200 import ops
+    from oracle import nms_oracle as NO
+    B, A, no = pred.shape
+    ws = ops.NmsWorkspace(B, A, no - 5, max_det=max_det)
+    det, idx, cnt = ops.yolo_nms(torch.from_numpy(pred).cuda(), ws, conf, iou, multi_label)
+    torch.cuda.synchronize()
+    assert int(ws.status[0]) == 0, 'candidate capacity overflow'
+    det, idx, cnt = det.cpu().numpy(), idx.cpu().numpy(), cnt.cpu().numpy()
+    ref = NO.non_max_suppression(pred, conf, iou, multi_label=multi_label, max_det=max_det)
+    for b in range(B):
+        rd, ri = ref[b]
+        assert cnt[b] == rd.shape[0], f'image {b}: kept {cnt[b]} vs oracle {rd.shape[0]}'
+        assert np.array_equal(idx[b, :cnt[b]].astype(np.int64), ri), f'image {b}: kept indices differ'
+        assert np.array_equal(det[b, :cnt[b]], rd), f'image {b}: detection rows differ'
+
+
+@pytest.mark.parametrize('regime', ['few', 'sparse', 'typical', 'capped'])
+@pytest.mark.parametrize('multi_label', [True, False])
+def test_nms_stress(cuda, regime, multi_label):
+    from oracle import nms_oracle as NO
+    pred = NO.make_stress_prediction(3, regime=regime, seed=2)
+    _nms_case(pred, multi_label=multi_label)
+
+
+def test_nms_empty_and_single(cuda):
+    pred = np.zeros((2, 1000, 85), np.float32)  # no candidates at all
+    _nms_case(pred)
+    pred[1, 7, :4] = [100, 100, 50, 60]
+    pred[1, 7, 4] = 0.9
+    pred[1, 7, 5 + 3] = 0.8
+    _nms_case(pred)
+
+
+def test_nms_score_ties_and_iou_edge(cuda):
+    """ties: equal scores keep candidate-index order; IoU == float32(0.6) is suppressed (double comparison)."""
+    pred = np.zeros((1, 64, 85), np.float32)
+    # two boxes with inter/union = 3/5 -> float32(0.6): second one must be suppressed at iou_thres=0.6
+    pred[0, 0, :5] = [2.5, 0.5, 5, 1, 0.9]
+    pred[0, 1, :5] = [1.5, 0.5, 3, 1, 0.8]
+    pred[0, :2, 5] = 1.0
+    # exact score ties, far apart
+    for k in range(10):
+        pred[0, 10 + k, :5] = [100 + 30 * k, 300, 20, 20, 0.5]
+        pred[0, 10 + k, 5 + 7] = 0.5
+    _nms_case(pred)
+
+
+def test_nms_other_thresholds(cuda):
+    from oracle import nms_oracle as NO
+    pred = NO.make_stress_prediction(2, regime='typical', seed=4)
+    _nms_case(pred, conf=0.25, iou=0.45, multi_label=False)
+    _nms_case(pred, conf=0.05, iou=0.7, multi_label=True, max_det=100)
+
+
+def test_decode_matches_reference_formula(cuda):
+    from cvpytorch_b200 import ops
+    from oracle import yolov5_oracle as YO
+    torch.manual_seed(3)
+    B, ny, nx, na, no = 2, 12, 20, 3, 85
+    raw = ops.F32Tensor(B, ny, nx, 256)
+    raw.data.normal_(0, 2)
+    anchors_px = (torch.tensor(YO.ANCHORS[1]) * 16.0).float().cuda().contiguous()
+    z = torch.zeros(B, na * ny * nx + 5, no, device='cuda')
+    xperm = torch.zeros(B, na, ny, nx, no, device='cuda')
+    ops.yolo_decode(raw.view(0, 255), na, no, anchors_px, 16.0, z, z.shape[1], 5, xperm)
+    torch.cuda.synchronize()
+    r = raw.data[..., :255].view(B, ny, nx, na, no).permute(0, 3, 1, 2, 4).contiguous().cpu()
+    assert torch.equal(xperm.cpu(), r)
+    yv, xv = torch.meshgrid([torch.arange(ny), torch.arange(nx)], indexing='ij')
+    grid = torch.stack((xv, yv), 2).expand((1, na, ny, nx, 2)).float()
+    ag = (torch.tensor(YO.ANCHORS[1]).float() * 16.0).view(1, na, 1, 1, 2).expand(1, na, ny, nx, 2)
+    y = r.sigmoid()
+    y[..., 0:2] = (y[..., 0:2] * 2 - 0.5 + grid) * 16.0
+    y[..., 2:4] = (y[..., 2:4] * 2) ** 2 * ag
+    ref = y.view(B, -1, no)
+    got = z[:, 5:].cpu()
+    err = float((got - ref).abs().max() / ref.abs().max())
+    assert err < 1e-6, err
+    assert float(z[:, :5].abs().max()) == 0.0
