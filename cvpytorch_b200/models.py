@@ -1,0 +1,372 @@
+"""Drop-in backbone / neck / detect / model modules for the YOLOv5 path (reference surface kept).
+
+Mirrors (paths relative to /root/reference):
+  YOLOv5CSPDarknet   src/models/backbones/det/yolov5_csp_darknet.py:17-120 (+ det/base_yolo_backbone.py:16-113)
+  YOLOv5Neck         src/models/necks/yolov5_neck.py:12-51   (the runnable old-API neck)
+  YOLOv5Detect       src/models/detects/yolov5_detect.py:12-65
+  YOLOv5             src/models/yolov5.py:156-287  (+ non_max_suppression :62-153)
+  build_*            src/models/{backbones,necks,detects}/__init__.py factories
+
+Component modules accept/return the reference's NCHW fp32 tensors (adapter kernels at the boundary); the
+model-level module runs ONE fused graph end to end (split-NHWC internally, decode + batched NMS on device).
+"""
+import math
+from copy import deepcopy
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .engine import GraphBuilder, Val
+from .modules import C3, Conv, ConvModule, CSPLayer, DownsamplingModule, SPPF, UpsamplingModule, folded
+
+
+def _check_infer_input(module, x):
+    if module.training:
+        raise RuntimeError(f'{type(module).__name__}: the B200 path implements inference only; call .eval() first '
+                           '(training stays on the reference implementation)')
+    if not (isinstance(x, torch.Tensor) and x.is_cuda):
+        raise _lib.CvbError(f'{type(module).__name__}: input must be a CUDA tensor; there is no CPU fallback')
+
+
+class _GraphCache(nn.Module):
+    """Caches one built graph per input shape; invalidated when weights change."""
+
+    def __init__(self):
+        super().__init__()
+        self._graphs = {}
+        self.register_load_state_dict_post_hook(lambda m, k: m.invalidate())
+
+    def invalidate(self):
+        self._graphs = {}
+        for m in self.children():
+            if isinstance(m, _GraphCache):
+                m.invalidate()
+
+    def train(self, mode=True):
+        self.invalidate()
+        return super().train(mode)
+
+
+# =============================================================================================== backbone
+class YOLOv5CSPDarknet(_GraphCache):
+    cfg = {"n": [0.33, 0.25], "t": [0.33, 0.375], "s": [0.33, 0.5], "m": [0.67, 0.75], "l": [1.0, 1.0], "x": [1.33, 1.25]}
+
+    def __init__(self, subtype='cspdark_s', in_channels=3, out_channels=[64, 128, 256, 512, 1024], num_blocks=[3, 6, 9, 3],
+                 spp_ksizes=5, depthwise=False, conv_cfg=None, norm_cfg=dict(type='BN', momentum=0.03, eps=0.001),
+                 act_cfg=dict(type='SiLU', inplace=True), out_stages=[2, 3, 4], output_stride=32, backbone_path=None,
+                 pretrained=False, frozen_stages=-1, norm_eval=False, **unused):
+        super().__init__()
+        if depthwise:
+            raise NotImplementedError('depthwise YOLOv5 backbone is not on the B200 hot path')
+        self.subtype = subtype
+        self.out_stages = out_stages
+        depth_mul, width_mul = self.cfg[subtype.split("_")[1]]
+        self.out_channels = list(map(lambda x: int(x * width_mul), out_channels))
+        self.num_blocks = list(map(lambda x: max(round(x * depth_mul), 1), num_blocks))
+        self.in_channels = in_channels
+        if in_channels != 3:
+            raise NotImplementedError('stem expects 3 input channels')
+        kw = dict(norm_cfg=norm_cfg, act_cfg=act_cfg)
+        self.stem = ConvModule(in_channels, self.out_channels[0], kernel_size=6, stride=2, padding=2, **kw)
+        for idx, (cin, cout, n) in enumerate(zip(self.out_channels[:-1], self.out_channels[1:], self.num_blocks)):
+            stage = [ConvModule(cin, cout, kernel_size=3, stride=2, padding=1, **kw),
+                     CSPLayer(cout, cout, n=n, shortcut=False if idx == 3 else True, **kw)]
+            if idx == 3:
+                stage.append(SPPF(cout, cout, kernel_sizes=spp_ksizes, **kw))
+            self.add_module(f'stage{idx + 1}', nn.Sequential(*stage))
+        self.init_weights()
+
+    def init_weights(self):
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_uniform_(m.weight, a=math.sqrt(5))
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.BatchNorm2d):
+                m.eps = 1e-3
+                m.momentum = 0.03
+
+    def emit(self, g, img_nchw_getter, H, W, name='backbone'):
+        """img_nchw_getter() -> contiguous fp32 CUDA tensor [B,3,H,W] at run time.  Returns list of Val."""
+        x0 = g.new_act(H // 2, W // 2, 16)
+        g.fn(lambda: ops.stem_s2d(img_nchw_getter(), x0.view()))
+        w, b = folded(self.stem.conv, self.stem.bn)
+        x = g.conv(x0, ops.stem_weights_to_s2d(w), b, 3, 1, 1, 'silu', name=name + '.stem')
+        outs = []
+        for i in range(1, 5):
+            stage = getattr(self, f'stage{i}')
+            x = stage[0].emit(g, x, f'{name}.stage{i}.0')
+            x = stage[1].emit(g, x, f'{name}.stage{i}.1')
+            if len(stage) > 2:
+                x = stage[2].emit(g, x, f'{name}.stage{i}.2')
+            if i in self.out_stages:
+                outs.append(x)
+        return outs
+
+    def forward(self, x):
+        _check_infer_input(self, x)
+        B, _, H, W = x.shape
+        key = (B, H, W, x.device.index)
+        if key not in self._graphs:
+            g = GraphBuilder(B, x.device)
+            holder = {}
+            outs = self.emit(g, lambda: holder['x'], H, W)
+            self._graphs[key] = (g, holder, outs)
+        g, holder, outs = self._graphs[key]
+        holder['x'] = x.contiguous().float()
+        g.run()
+        res = [ops.split_to_nchw(o.view()) for o in outs]
+        return res if len(self.out_stages) > 1 else res[0]
+
+
+# =============================================================================================== neck
+class YOLOv5Neck(_GraphCache):
+    def __init__(self, in_channels, out_channels, depth_mul=1.0, width_mul=1.0, **unused):
+        super().__init__()
+        assert isinstance(in_channels, list)
+        self.in_channels = list(map(lambda x: max(round(x * width_mul), 1), in_channels))
+        self.out_channels = list(map(lambda x: max(round(x * width_mul), 1), out_channels))
+        layers = [3, 3, 3, 3]
+        self.layers = list(map(lambda x: max(round(x * depth_mul), 1), layers))
+        self.up_1 = UpsamplingModule(self.in_channels[2], self.in_channels[1], self.layers[0])
+        self.up_2 = UpsamplingModule(self.in_channels[1], self.out_channels[0], self.layers[1])
+        self.down_1 = DownsamplingModule(self.in_channels[0], self.in_channels[1], self.layers[2])
+        self.down_2 = DownsamplingModule(self.in_channels[1], self.in_channels[2], self.layers[3])
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.eps = 1e-3
+                m.momentum = 0.03
+
+    def emit(self, g, feats, name='neck'):
+        x3, x4, x5 = feats
+        c1 = self.down_1.down.conv.out_channels  # lateral channels of level 4 -> concat at 1/16
+        c2 = self.down_2.down.conv.out_channels
+        cat1 = g.new_act(x4.H, x4.W, 2 * c1)   # [down_1(x3_up) | x3_t]
+        cat2 = g.new_act(x5.H, x5.W, 2 * c2)   # [down_2(x4_down) | x4_t]
+        x4_up, _ = self.up_1.emit(g, x5, x4, name + '.up_1', lateral_out=cat2.slice(c2, c2))
+        x3_up, _ = self.up_2.emit(g, x4_up, x3, name + '.up_2', lateral_out=cat1.slice(c1, c1))
+        x4_down = self.down_1.emit(g, x3_up, cat1, name + '.down_1')
+        x5_down = self.down_2.emit(g, x4_down, cat2, name + '.down_2')
+        return [x3_up, x4_down, x5_down]
+
+    def forward(self, x):
+        assert len(x) == len(self.in_channels)
+        _check_infer_input(self, x[0])
+        key = tuple(tuple(t.shape) for t in x)
+        if key not in self._graphs:
+            B = x[0].shape[0]
+            g = GraphBuilder(B, x[0].device)
+            ins = [g.new_act(t.shape[2], t.shape[3], t.shape[1]) for t in x]
+            outs = self.emit(g, ins)
+            self._graphs[key] = (g, ins, outs)
+        g, ins, outs = self._graphs[key]
+        for t, v in zip(x, ins):
+            ops.nchw_to_split(t, v.view())
+        g.run()
+        return [ops.split_to_nchw(o.view()) for o in outs]
+
+
+# =============================================================================================== detect
+class YOLOv5Detect(_GraphCache):
+    def __init__(self, num_classes=80, in_channels=[256, 512, 1024], stride=[8., 16., 32.], anchors=(), depth_mul=1.0, width_mul=1.0):
+        super().__init__()
+        in_channels = list(map(lambda x: int(x * width_mul), in_channels))
+        self.num_classes = num_classes
+        self.num_outputs = num_classes + 5
+        self.num_layers = len(anchors)
+        self.num_anchors = len(anchors[0])
+        self.stride = stride
+        self.register_buffer('anchors', torch.tensor(anchors).float())
+        self.m = nn.ModuleList(nn.Conv2d(x, self.num_outputs * self.num_anchors, 1) for x in in_channels)
+        self.init_weight()
+
+    def init_weight(self, cf=None):
+        for mi, s in zip(self.m, self.stride):
+            b = mi.bias.view(self.num_anchors, -1)
+            b.data[:, 4] += math.log(8 / (640 / s) ** 2)
+            b.data[:, 5:] += math.log(0.6 / (self.num_classes - 0.999999)) if cf is None else torch.log(cf / cf.sum())
+            mi.bias = torch.nn.Parameter(b.view(-1), requires_grad=True)
+
+    def emit(self, g, feats, name='detect', want_raw=True):
+        """Returns (z tensor [B, A, no] fp32 on device, [raw_i [B,na,ny,nx,no]] or None)."""
+        na, no = self.num_anchors, self.num_outputs
+        A = sum(na * f.H * f.W for f in feats)
+        dev = g.device
+        z = torch.zeros((g.B, A, no), dtype=torch.float32, device=dev)
+        raws = []
+        off = 0
+        for i, f in enumerate(feats):
+            cpitch = (na * no + 31) // 32 * 32
+            raw = g.new_f32(f.H, f.W, cpitch)
+            w, b = folded(self.m[i])
+            g.conv(f, w, b, 1, 1, 0, None, f32_out=raw, name=f'{name}.m.{i}')
+            anchors_px = (self.anchors[i].detach().float().cpu() * float(self.stride[i])).to(dev).contiguous()
+            xp = torch.zeros((g.B, na, f.H, f.W, no), dtype=torch.float32, device=dev) if want_raw else None
+            raws.append(xp)
+            g.fn(lambda raw=raw, anchors_px=anchors_px, s=float(self.stride[i]), off=off, xp=xp:
+                 ops.yolo_decode(raw.view(0, na * no), na, no, anchors_px, s, z, A, off, xp))
+            off += na * f.H * f.W
+        g.buffers.append(z)
+        return z, (raws if want_raw else None)
+
+    def forward(self, x):
+        _check_infer_input(self, x[0])
+        key = tuple(tuple(t.shape) for t in x)
+        if key not in self._graphs:
+            B = x[0].shape[0]
+            g = GraphBuilder(B, x[0].device)
+            ins = [g.new_act(t.shape[2], t.shape[3], t.shape[1]) for t in x]
+            z, raws = self.emit(g, ins)
+            self._graphs[key] = (g, ins, z, raws)
+        g, ins, z, raws = self._graphs[key]
+        for t, v in zip(x, ins):
+            ops.nchw_to_split(t, v.view())
+        g.run()
+        for i in range(len(x)):  # the reference replaces the list entries in place (yolov5_detect.py:42-44)
+            x[i] = raws[i]
+        return z, x
+
+
+# =============================================================================================== factories
+_BACKBONES = {'YOLOv5CSPDarknet': YOLOv5CSPDarknet, 'YOLOv5Backbone': YOLOv5CSPDarknet}
+_NECKS = {'YOLOv5Neck': YOLOv5Neck}
+_DETECTS = {'YOLOv5Detect': YOLOv5Detect}
+
+
+def _build(table, cfg):
+    c = deepcopy(dict(cfg))
+    name = c.pop('name')
+    if name not in table:
+        raise NotImplementedError(name)
+    return table[name](**c)
+
+
+def build_backbone(cfg):
+    """src/models/backbones/__init__.py:61-134 contract: deepcopy, pop 'name', Class(**cfg); unknown -> NotImplementedError.
+    'YOLOv5Backbone' (the name conf/coco_yolov5_s.yml:68 uses but the reference factory lacks) maps to YOLOv5CSPDarknet."""
+    c = deepcopy(dict(cfg))
+    if c.get('name') == 'YOLOv5Backbone':
+        c.setdefault('subtype', 'yolov5_s')
+        c.pop('depth_mul', None)
+        c.pop('width_mul', None)
+    elif c.get('name') == 'YOLOv5CSPDarknet':
+        c.pop('depth_mul', None)   # injected by YOLOv5.setup_extra_params (yolov5.py:207-208), not a ctor arg
+        c.pop('width_mul', None)
+    return _build(_BACKBONES, c)
+
+
+def build_neck(cfg):
+    return _build(_NECKS, cfg)
+
+
+def build_detect(cfg):
+    return _build(_DETECTS, cfg)
+
+
+# =============================================================================================== model
+def non_max_suppression(prediction, conf_thres=0.25, iou_thres=0.45, classes=None, agnostic=False, multi_label=False,
+                        labels=(), max_det=300, workspace=None, return_indices=False):
+    """Device-side replacement of src/models/yolov5.py:62-153 with the same signature / return type
+    (list of [n,6] tensors xyxy, conf, cls).  `classes`/`labels` (unused by the reference's callers) are not supported."""
+    if classes is not None or labels:
+        raise NotImplementedError('classes= / labels= filters are not on the B200 hot path')
+    B, A, no = prediction.shape
+    ws = workspace if workspace is not None else ops.NmsWorkspace(B, A, no - 5, max_det=max_det, device=prediction.device)
+    det, idx, cnt = ops.yolo_nms(prediction.contiguous(), ws, conf_thres, iou_thres, multi_label, max_wh=0.0 if agnostic else 4096.0)
+    cnt_h = cnt.cpu().tolist()  # the only host sync: the API returns variable-length tensors
+    if int(ws.status[0]) != 0:
+        raise _lib.CvbError('NMS candidate capacity overflow')
+    out = [det[b, :cnt_h[b]] for b in range(B)]
+    if return_indices:
+        return out, [idx[b, :cnt_h[b]] for b in range(B)]
+    return out
+
+
+class YOLOv5(_GraphCache):
+    """Model-level drop-in for src.models.yolov5.YOLOv5 (inference path).  forward(imgs, targets, mode) keeps the
+    reference contract: mode 'val' -> (losses_dict, outputs list of {'boxes','labels','scores'})."""
+    anchors = [[[1.25000, 1.62500], [2.00000, 3.75000], [4.12500, 2.87500]],
+               [[1.87500, 3.81250], [3.87500, 2.81250], [3.68750, 7.43750]],
+               [[3.62500, 2.81250], [4.87500, 6.18750], [11.65625, 10.18750]]]
+    cfg = {"nano": [0.33, 0.25], "tiny": [0.33, 0.375], "s": [0.33, 0.5], "m": [0.67, 0.75], "l": [1.0, 1.0], "x": [1.33, 1.25]}
+
+    def __init__(self, dictionary=None, model_cfg=None):
+        super().__init__()
+        self.dictionary = dictionary
+        self.model_cfg = model_cfg
+        self.dummy_input = torch.zeros(1, 3, 640, 640)
+        self.num_classes = len(self.dictionary)
+        self.category = [v for d in self.dictionary for v in d.keys()]
+        self.weight = [d[v] for d in self.dictionary for v in d.keys() if v in self.category]
+        get = (lambda k: model_cfg[k]) if isinstance(model_cfg, dict) else (lambda k: getattr(model_cfg, k))
+        self.depth_mul, self.width_mul = self.cfg[get('TYPE').split("_")[1]]
+        bcfg, ncfg, dcfg = dict(get('BACKBONE')), dict(get('NECK')), dict(get('DETECT'))
+        bcfg.setdefault('subtype', get('TYPE'))
+        ncfg.update(depth_mul=self.depth_mul, width_mul=self.width_mul)
+        dcfg.update(depth_mul=self.depth_mul, width_mul=self.width_mul, anchors=self.anchors, num_classes=self.num_classes)
+        self.backbone = build_backbone(bcfg)
+        self.neck = build_neck(ncfg)
+        self.detect = build_detect(dcfg)
+        self.conf_thres = 0.001   # yolov5.py:189
+        self.iou_thres = 0.6      # yolov5.py:190
+        self.max_det = 300
+        self.loss = None          # training loss stays with the reference (out of scope)
+        for m in self.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.eps = 1e-3
+                m.momentum = 0.03
+
+    # ------------------------------------------------------------------ fused graph
+    def build_graph(self, B, H, W, device, want_raw=False):
+        g = GraphBuilder(B, device)
+        holder = {}
+        feats = self.backbone.emit(g, lambda: holder['x'], H, W)
+        feats = self.neck.emit(g, feats)
+        z, raws = self.detect.emit(g, feats, want_raw=want_raw)
+        ws = ops.NmsWorkspace(B, z.shape[1], self.num_classes, max_det=self.max_det, device=device)
+        conf, iou = self.conf_thres, self.iou_thres
+        g.fn(lambda: ops.yolo_nms(z, ws, conf, iou, True))
+        return dict(g=g, holder=holder, z=z, raws=raws, ws=ws)
+
+    def _graph_for(self, imgs, want_raw=False):
+        B, _, H, W = imgs.shape
+        key = (B, H, W, imgs.device.index, want_raw)
+        if key not in self._graphs:
+            self._graphs[key] = self.build_graph(B, H, W, imgs.device, want_raw)
+        return self._graphs[key]
+
+    def predict(self, imgs):
+        """Device-only inference: returns (det [B,300,6], det_idx [B,300], det_count [B]) device tensors, no host sync."""
+        _check_infer_input(self, imgs)
+        G = self._graph_for(imgs)
+        G['holder']['x'] = imgs.contiguous().float()
+        G['g'].run()
+        return G['ws'].det, G['ws'].det_idx, G['ws'].det_count
+
+    def forward(self, imgs, targets=None, mode='infer', **kwargs):
+        if mode == 'infer':
+            return  # the reference returns None here (yolov5.py:247-249)
+        if mode != 'val':
+            raise RuntimeError("YOLOv5 (B200): only mode='val' (inference) is implemented; training stays on the reference")
+        det, _, cnt = self.predict(imgs)
+        losses = {}  # val-mode loss (yolov5.py:258) is a training diagnostic; not computed on the B200 path
+        det_h = det.cpu()
+        cnt_h = cnt.cpu().tolist()
+        outputs = []
+        for i, pred in enumerate(det_h[b, :cnt_h[b]] for b in range(det_h.shape[0])):
+            t = targets[i] if targets is not None else {}
+            scale = np.asarray(t['scales'].cpu() if 'scales' in t else [1.0, 1.0], dtype=np.float32)
+            pad = np.asarray(t['pads'].cpu() if 'pads' in t else [0.0, 0.0], dtype=np.float32)
+            width = float(t['width']) if 'width' in t else float(imgs.shape[3])
+            height = float(t['height']) if 'height' in t else float(imgs.shape[2])
+            b = pred[:, :4].numpy().copy()          # yolov5.py:267-282
+            b[:, [0, 2]] -= pad[1]
+            b[:, [1, 3]] -= pad[0]
+            b[:, [0, 2]] /= scale[1]
+            b[:, [1, 3]] /= scale[0]
+            b[:, [0, 2]] = b[:, [0, 2]].clip(0, width)
+            b[:, [1, 3]] = b[:, [1, 3]].clip(0, height)
+            outputs.append({"boxes": torch.tensor(b), "labels": pred[:, 5], "scores": pred[:, 4]})
+        return losses, outputs

@@ -1,0 +1,123 @@
+"""Deterministic synthetic YOLOv5-s weights in the reference's ``state_dict`` format (workload generator).
+
+There is no network, so there are no trained checkpoints: tests and bench.py use random-init weights of the
+named architecture.  Naive random BatchNorm statistics collapse the features (logits become
+bias-dominated and a low-precision kernel *appears* to pass), so the BN running statistics come from a
+calibration pass of the REFERENCE model (tools/make_golden.py, run once in the build container) stored in
+tests/golden/yolov5s_calib.npz (~40 KB):  conv weights ~ N(0, 1/fan_in) from a per-key seeded generator,
+BN gamma ~ U(0.5,1.5), beta ~ N(0,0.2), running_mean/var := batch statistics of randn(4,3,640,640) (seed 7)
+through the reference in train mode with momentum 1.0, Detect conv weights scaled so std(logit-bias)=1.5 and
+biases set to the reference's prior (src/models/detects/yolov5_detect.py:29-36).
+The same state_dict loads into the reference modules and into the drop-in modules.
+"""
+import hashlib
+import math
+import os
+
+import numpy as np
+import torch
+
+CALIB_PATH = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'tests', 'golden', 'yolov5s_calib.npz')
+
+
+def _gen(key):
+    seed = int.from_bytes(hashlib.sha256(key.encode()).digest()[:4], 'little')
+    return torch.Generator().manual_seed(seed)
+
+
+def base_state_dict(template):
+    """template: {key: tensor} with the reference's key names/shapes.  Returns un-calibrated synthetic values."""
+    out = {}
+    for k, v in template.items():
+        g = _gen(k)
+        if k.endswith('num_batches_tracked'):
+            out[k] = torch.zeros((), dtype=torch.long)
+        elif k.endswith('anchors'):
+            out[k] = v.clone().float()
+        elif k.endswith('.bn.weight'):
+            out[k] = torch.rand(v.shape, generator=g) + 0.5
+        elif k.endswith('.bn.bias'):
+            out[k] = torch.randn(v.shape, generator=g) * 0.2
+        elif k.endswith('running_mean'):
+            out[k] = torch.zeros(v.shape)
+        elif k.endswith('running_var'):
+            out[k] = torch.ones(v.shape)
+        elif k.endswith('.weight') and v.dim() == 4:
+            fan_in = v.shape[1] * v.shape[2] * v.shape[3]
+            out[k] = torch.randn(v.shape, generator=g) / math.sqrt(fan_in)
+        elif k.endswith('.bias'):
+            out[k] = torch.zeros(v.shape)
+        else:
+            raise KeyError(f'unexpected key {k}')
+    return out
+
+
+def detect_prior_bias(num_classes=80, na=3, strides=(8.0, 16.0, 32.0)):
+    """Bias prior of YOLOv5Detect.init_weight (src/models/detects/yolov5_detect.py:29-36) on a zero base."""
+    outs = []
+    for s in strides:
+        b = torch.zeros(na, num_classes + 5)
+        b[:, 4] += math.log(8 / (640 / s) ** 2)
+        b[:, 5:] += math.log(0.6 / (num_classes - 0.999999))
+        outs.append(b.view(-1))
+    return outs
+
+
+def apply_calibration(sd, calib):
+    """calib: mapping with '<bn prefix>.running_mean/var' arrays and 'detect_scale' [3]."""
+    for k in list(sd.keys()):
+        if k.endswith('running_mean') or k.endswith('running_var'):
+            sd[k] = torch.from_numpy(np.asarray(calib[k])).float().clone()
+    scale = np.asarray(calib['detect_scale'])
+    pri = detect_prior_bias()
+    for i in range(3):
+        sd[f'detect.m.{i}.weight'] = sd[f'detect.m.{i}.weight'] * float(scale[i])
+        sd[f'detect.m.{i}.bias'] = pri[i].clone()
+    return sd
+
+
+def template_state_dict():
+    """Key/shape template from the drop-in modules (identical to the reference's, tests/test_host_logic.py)."""
+    from . import models as M
+    bb = M.build_backbone({'name': 'YOLOv5CSPDarknet', 'subtype': 'yolov5_s', 'out_stages': [2, 3, 4]})
+    nk = M.build_neck({'name': 'YOLOv5Neck', 'in_channels': [256, 512, 1024], 'out_channels': [256, 512, 1024],
+                       'depth_mul': 0.33, 'width_mul': 0.5})
+    dt = M.build_detect({'name': 'YOLOv5Detect', 'in_channels': [256, 512, 1024], 'depth_mul': 0.33, 'width_mul': 0.5,
+                         'anchors': M.YOLOv5.anchors, 'num_classes': 80})
+    t = {}
+    for p, m in (('backbone.', bb), ('neck.', nk), ('detect.', dt)):
+        for k, v in m.state_dict().items():
+            t[p + k] = v
+    return t
+
+
+def yolov5s_state_dict(calibrated=True):
+    sd = base_state_dict(template_state_dict())
+    if calibrated:
+        if not os.path.exists(CALIB_PATH):
+            raise FileNotFoundError(f'{CALIB_PATH} missing: run tools/make_golden.py in the build container')
+        sd = apply_calibration(sd, np.load(CALIB_PATH))
+    return sd
+
+
+def split_prefix(sd, prefix):
+    return {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+YOLOV5S_CFG = {'TYPE': 'yolov5_s',
+               'BACKBONE': {'name': 'YOLOv5Backbone', 'out_stages': [2, 3, 4], 'output_stride': 32, 'pretrained': False},
+               'NECK': {'name': 'YOLOv5Neck', 'in_channels': [256, 512, 1024], 'out_channels': [256, 512, 1024]},
+               'DETECT': {'name': 'YOLOv5Detect', 'in_channels': [256, 512, 1024]},
+               'LOSS': {'name': 'YOLOv5Loss', 'hyp_box': 0.05, 'hyp_obj': 1.0, 'hyp_cls': 0.5}}  # conf/coco_yolov5_s.yml:65-71
+
+
+def build_yolov5s(calibrated=True, device=None):
+    """Drop-in YOLOv5 model (the conf/coco_yolov5_s.yml configuration) with the synthetic weights loaded."""
+    from . import models as M
+    dictionary = [{f'c{i}': 1.0} for i in range(80)]
+    model = M.YOLOv5(dictionary=dictionary, model_cfg=dict(YOLOV5S_CFG))
+    model.load_state_dict(yolov5s_state_dict(calibrated), strict=True)
+    model.eval()
+    if device is not None:
+        model.to(device)
+    return model
