@@ -1,0 +1,45 @@
+"""Multi-GPU plumbing: one process per GPU, batch sharded by rank, ONE all-gather of the final detections.
+
+The reference has no collective on its inference path (multi-GPU val runs independent DistributedSampler shards
+and "reduces" with a no-op, trainer.py:227-231 / src/utils/distributed.py:122-125); its only gather precedent is
+the pickle all_gather of the COCO evaluator (src/evaluator/eval_coco.py:464-506).  Images are independent through
+conv, decode and NMS, so the shards need no data-path collective; the fixed-capacity result buffer
+[B_local, max_det*6 + max_det + 1] (rows, candidate ids, count) is gathered with a single all_gather_into_tensor
+(NCCL over NVLink on the box; gloo in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_range(global_batch, rank, world):
+    """Contiguous shard [lo, hi) of rank; sizes differ by at most one."""
+    base, rem = divmod(global_batch, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def pack_detections(det, det_idx, det_count):
+    """det [B,M,6] f32, det_idx [B,M] i32, det_count [B] i32 -> one f32 tensor [B, M*7+1] (ints bit-cast)."""
+    B, M, _ = det.shape
+    return torch.cat([det.reshape(B, M * 6), det_idx.view(torch.float32).reshape(B, M),
+                      det_count.view(torch.float32).reshape(B, 1)], 1).contiguous()
+
+
+def unpack_detections(packed, max_det):
+    B = packed.shape[0]
+    M = max_det
+    det = packed[:, :M * 6].reshape(B, M, 6)
+    idx = packed[:, M * 6:M * 7].contiguous().view(torch.int32)
+    cnt = packed[:, M * 7:].contiguous().view(torch.int32).reshape(B)
+    return det, idx, cnt
+
+
+def all_gather_detections(det, det_idx, det_count, group=None, out=None):
+    """Single collective: every rank ends up with the detections of the whole global batch (rank-major order).
+    All ranks must hold the same local batch size (pad the last shard)."""
+    packed = pack_detections(det, det_idx, det_count)
+    world = dist.get_world_size(group)
+    if out is None:
+        out = torch.empty((world * packed.shape[0], packed.shape[1]), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(out, packed, group=group)
+    return unpack_detections(out, det.shape[1])

@@ -1,0 +1,86 @@
+"""Host-side inference runtime: pinned-host -> device -> fused graph -> (all-gather) -> pinned-host, double buffered.
+
+The reference's loop is synchronous (trainer.py:156-157 ``imgs.cuda()`` then ``model(imgs, targets, 'val')`` then
+``.cpu().numpy()`` per image, yolov5.py:267-284).  Here the H2D copy of batch i+1, the fused graph of batch i and
+the D2H read of batch i-1 run on three streams; nothing on the path synchronises the host except ``result()``.
+"""
+import torch
+
+from . import dist as cdist
+
+
+class InferencePipeline:
+    def __init__(self, model, batch, height, width, device, depth=2, gather_group=None, use_cuda_graph=True):
+        self.model = model
+        self.device = device
+        self.depth = depth
+        self.group = gather_group
+        self.G = model.build_graph(batch, height, width, device)
+        self.g = self.G['g']
+        self.ws = self.G['ws']
+        self.x_dev = [torch.empty((batch, 3, height, width), dtype=torch.float32, device=device) for _ in range(depth)]
+        self.copy_stream = torch.cuda.Stream(device)
+        self.out_stream = torch.cuda.Stream(device)
+        self.compute_stream = torch.cuda.Stream(device)
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]        # input slot filled
+        self.ev_free = [torch.cuda.Event() for _ in range(depth)]      # input slot consumed by the stem
+        self.ev_done = [torch.cuda.Event() for _ in range(depth)]      # results of slot ready on device
+        self.ev_host = [torch.cuda.Event() for _ in range(depth)]      # results landed in pinned host memory
+        M = self.ws.max_det
+        world = torch.distributed.get_world_size(gather_group) if (gather_group is not None or (
+            torch.distributed.is_available() and torch.distributed.is_initialized())) else 1
+        self.world = world
+        self.res_dev = [torch.empty((world * batch, M * 7 + 1), dtype=torch.float32, device=device) for _ in range(depth)]
+        self.res_host = [torch.empty((world * batch, M * 7 + 1), dtype=torch.float32).pin_memory() for _ in range(depth)]
+        self.graphs = [None] * depth
+        self.n_submitted = 0
+        self.h2d_bytes = self.x_dev[0].numel() * 4
+        self.d2h_bytes = self.res_host[0].numel() * 4
+        if use_cuda_graph:
+            with torch.cuda.stream(self.compute_stream):
+                # one CUDA graph per input slot; activation buffers are shared (the compute stream serialises them)
+                for s in range(depth):
+                    self.G['holder']['x'] = self.x_dev[s]
+                    self.g._graph = None
+                    self.graphs[s] = self.g.capture(warmup=1 if s else 2)
+            torch.cuda.synchronize(device)
+
+    def submit(self, x_host_pinned):
+        """Enqueue one batch (pinned host fp32 [B,3,H,W]).  Returns the slot index."""
+        s = self.n_submitted % self.depth
+        if self.n_submitted >= self.depth:
+            self.copy_stream.wait_event(self.ev_free[s])      # stem of the previous user of this slot has read it
+        with torch.cuda.stream(self.copy_stream):
+            self.x_dev[s].copy_(x_host_pinned, non_blocking=True)
+            self.ev_in[s].record(self.copy_stream)
+        with torch.cuda.stream(self.compute_stream):
+            self.compute_stream.wait_event(self.ev_in[s])
+            if self.n_submitted >= self.depth:
+                self.compute_stream.wait_event(self.ev_host[s])  # result slot s has been drained to the host
+            if self.graphs[s] is not None:
+                self.graphs[s].replay()
+            else:
+                self.G['holder']['x'] = self.x_dev[s]
+                self.g.run()
+            self.ev_free[s].record(self.compute_stream)
+            packed = cdist.pack_detections(self.ws.det, self.ws.det_idx, self.ws.det_count)
+            if self.world > 1:
+                torch.distributed.all_gather_into_tensor(self.res_dev[s], packed, group=self.group)
+            else:
+                self.res_dev[s].copy_(packed)
+            self.ev_done[s].record(self.compute_stream)
+        with torch.cuda.stream(self.out_stream):
+            self.out_stream.wait_event(self.ev_done[s])
+            self.res_host[s].copy_(self.res_dev[s], non_blocking=True)
+            self.ev_host[s].record(self.out_stream)
+        self.n_submitted += 1
+        return s
+
+    def result(self, slot):
+        """Blocks until the slot's detections are in host memory; returns (det, idx, count) CPU tensors (views)."""
+        self.ev_host[slot].synchronize()
+        return cdist.unpack_detections(self.res_host[slot], self.ws.max_det)
+
+    def drain(self):
+        for s in range(min(self.depth, self.n_submitted)):
+            self.ev_host[s].synchronize()

@@ -1,0 +1,145 @@
+"""CPU suite, part 2: host-side logic (state_dict surface, BN folding, weight packing, stem re-formulation, factories,
+C-ABI export list, loud failure without CUDA) and the world_size-2 gloo test of the detection all-gather."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+
+
+def test_state_dict_keys_equal_reference():
+    from cvpytorch_b200 import synth
+    g = np.load(os.path.join(GOLD, 'yolov5s_keys.npz'))
+    t = synth.template_state_dict()
+    assert list(t.keys()) == list(g['keys'])
+    assert [str(tuple(v.shape)) for v in t.values()] == list(g['shapes'])
+    assert sum(v.numel() for k, v in t.items() if not k.endswith('num_batches_tracked') and not k.endswith('running_mean')
+               and not k.endswith('running_var') and not k.endswith('anchors')) == 7235389
+
+
+def test_fold_conv_bn_matches_batchnorm():
+    """Algebra of src/utils/fuse.py:33-54 (the reference's only numeric self-check, :67-80, prints this error)."""
+    from cvpytorch_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 8, 9, 9, generator=g)
+    w = torch.randn(16, 8, 3, 3, generator=g)
+    gamma, beta = torch.rand(16, generator=g) + 0.5, torch.randn(16, generator=g)
+    mean, var = torch.randn(16, generator=g), torch.rand(16, generator=g) + 0.1
+    ref = F.batch_norm(F.conv2d(x, w, None, 1, 1), mean, var, gamma, beta, False, 0.0, 1e-3)
+    w64, b64 = ops.fold_conv_bn(w, None, (gamma, beta, mean, var, 1e-3))
+    got = F.conv2d(x.double(), w64, b64, 1, 1)
+    assert float((got - ref.double()).abs().max() / ref.abs().max()) < 2e-6  # fp32 rounding of the reference itself
+
+
+def test_pack_weights_layout_and_split_precision():
+    from cvpytorch_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    w = torch.randn(10, 16, 3, 3, generator=g, dtype=torch.float64)
+    b = torch.randn(10, generator=g, dtype=torch.float64)
+    packed, bias = ops.pack_conv_weights(w, b, device='cpu')
+    assert packed.shape == (2, 16, 3 * 3 * 16) and packed.dtype == torch.float16 and bias.shape == (16,)
+    rec = (packed[0].double() + packed[1].double()).reshape(16, 3, 3, 16)[:10].permute(0, 3, 1, 2)
+    assert float((rec - w).abs().max() / w.abs().max()) < 2 ** -20  # hi+lo carries ~22 mantissa bits
+    assert float(packed[:, 10:].abs().max()) == 0.0 and torch.equal(bias[:10], b.float())
+
+
+def test_stem_space_to_depth_equivalence():
+    """6x6/s2/p2 conv == 3x3/s1/p1 conv over the 2x2 space-to-depth input (channel = (dy*2+dx)*3+c)."""
+    from cvpytorch_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(1, 3, 16, 20, generator=g, dtype=torch.float64)
+    w = torch.randn(4, 3, 6, 6, generator=g, dtype=torch.float64)
+    ref = F.conv2d(x, w, None, 2, 2)
+    s2d = torch.zeros(1, 16, 8, 10, dtype=torch.float64)
+    for dy in range(2):
+        for dx in range(2):
+            for c in range(3):
+                s2d[:, (dy * 2 + dx) * 3 + c] = x[:, c, dy::2, dx::2]
+    got = F.conv2d(s2d, ops.stem_weights_to_s2d(w), None, 1, 1)
+    assert float((got - ref).abs().max()) < 1e-12
+
+
+def test_factories_follow_reference_contract():
+    from cvpytorch_b200 import models as M
+    with pytest.raises(NotImplementedError):
+        M.build_backbone({'name': 'NoSuchBackbone'})
+    with pytest.raises(NotImplementedError):
+        M.build_neck({'name': 'BiFPN'})
+    cfg = {'name': 'YOLOv5Detect', 'in_channels': [256, 512, 1024], 'width_mul': 0.5, 'anchors': M.YOLOv5.anchors, 'num_classes': 80}
+    d = M.build_detect(cfg)
+    assert 'name' in cfg and d.m[0].weight.shape == (255, 128, 1, 1)  # cfg is deep-copied, not consumed
+    bias = d.m[0].bias.view(3, 85)
+    assert abs(float(bias[0, 4]) - np.log(8 / (640 / 8) ** 2)) < 1.0  # prior added on top of the default init
+
+
+def test_model_surface_and_loud_failure_without_cuda():
+    from cvpytorch_b200 import _lib, synth
+    m = synth.build_yolov5s(calibrated=True)
+    assert tuple(m.dummy_input.shape) == (1, 3, 640, 640) and m.conf_thres == 0.001 and m.iou_thres == 0.6
+    assert m(torch.zeros(1, 3, 64, 64), None, 'infer') is None  # reference returns None in 'infer' mode
+    with pytest.raises(_lib.CvbError):
+        m(torch.zeros(1, 3, 64, 64), None, 'val')  # CPU tensor: no fallback
+    m.train()
+    with pytest.raises(RuntimeError):
+        m.backbone(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(RuntimeError):
+        m.backbone.stage1[1](torch.zeros(1, 64, 8, 8))  # fused-path block is not executable stand-alone
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    from cvpytorch_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'cvb200.h')).read()
+    declared = set(re.findall(r'\b(cvb_[a-z0-9_]+)\s*\(', header))
+    assert declared == set(_lib.SYMBOLS.keys()), declared ^ set(_lib.SYMBOLS.keys())
+    assert os.path.exists(_lib.LIB_PATH), 'libcvb200.so not built (python -c "import __graft_entry__ as g; g.build()")'
+    h = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(h, name), name
+    assert _lib.lib().cvb_version() == 100
+    assert _lib.lib().cvb_nms_workspace_bytes(2, 25200, 80) > 2 * 65536 * 8
+
+
+def test_shard_range_covers_batch():
+    from cvpytorch_b200.dist import shard_range
+    for gb, w in ((64, 8), (64, 3), (5, 8)):
+        spans = [shard_range(gb, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == gb and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from cvpytorch_b200.dist import all_gather_detections
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    B, M = 3, 7
+    det = torch.full((B, M, 6), float(rank)) + torch.arange(B).view(B, 1, 1)
+    idx = (torch.arange(B * M, dtype=torch.int32).view(B, M) + 1000 * rank)
+    cnt = torch.tensor([rank + 1, 0, M], dtype=torch.int32)
+    d, i, c = all_gather_detections(det, idx, cnt)
+    q.put((rank, d.clone(), i.clone(), c.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_all_gather_detections_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, d, i, c in res:
+        assert d.shape == (6, 7, 6) and i.shape == (6, 7) and c.tolist() == [1, 0, 7, 2, 0, 7]
+        assert float(d[0, 0, 0]) == 0.0 and float(d[3, 0, 0]) == 1.0 and float(d[5, 0, 0]) == 3.0
+        assert int(i[3, 0]) == 1000 and int(i[0, 6]) == 6
