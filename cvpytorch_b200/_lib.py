@@ -30,7 +30,7 @@ class CvbConvDesc(ctypes.Structure):
 class CvbNmsParams(ctypes.Structure):
     _fields_ = [('B', c_int32), ('A', c_int32), ('nc', c_int32), ('conf_thres', c_float),
                 ('iou_thres', c_double), ('multi_label', c_int32), ('max_nms', c_int32), ('max_det', c_int32),
-                ('max_wh', c_float)]
+                ('max_wh', c_float), ('hist_ready', c_int32)]
 
 
 # name -> (restype, argtypes); must list every symbol include/cvb200.h declares
@@ -45,7 +45,8 @@ SYMBOLS = {
     'cvb_stem_s2d': (c_int32, [c_void_p, c_int32, c_int32, c_int32, POINTER(CvbView), c_void_p]),
     'cvb_sppf_pool': (c_int32, [POINTER(CvbView), POINTER(CvbView), POINTER(CvbView), POINTER(CvbView), c_void_p]),
     'cvb_yolo_decode': (c_int32, [POINTER(CvbView), c_int32, c_int32, c_void_p, c_float, c_void_p, c_int64,
-                                  c_int64, c_void_p, c_void_p]),
+                                  c_int64, c_void_p, c_void_p, c_float, c_int32, c_void_p]),
+    'cvb_nms_workspace_reset': (c_int32, [c_void_p, c_size_t, c_int32, c_void_p]),
     'cvb_nms_workspace_bytes': (c_size_t, [c_int32, c_int32, c_int32]),
     'cvb_yolo_nms': (c_int32, [c_void_p, POINTER(CvbNmsParams), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                c_void_p, c_void_p]),

@@ -187,33 +187,60 @@ __global__ void sppf_pool_kernel(const __half* __restrict__ x, int H, int W, int
 }
 
 // ------------------------------------------------------------------ YOLOv5 decode
-// index space (b, a, pix, c) with c fastest: writes to z / xperm are fully coalesced, reads are 85-float runs.
-__global__ void yolo_decode_kernel(const float* __restrict__ raw, int B, int ny, int nx, int pitch, int na, int no,
-                                   const float* __restrict__ anchors_px, float stride, float* __restrict__ z, long long z_rows,
-                                   long long z_off, float* __restrict__ xperm) {
+// One warp per output row (b, a, pix): 85 contiguous floats are read and written coalesced, index arithmetic is
+// per row (not per element).  While the scores are in registers the warp also feeds the NMS score histogram
+// (replaces the separate counting pass over the 548 MB prediction tensor).
+__global__ void __launch_bounds__(256) yolo_decode_kernel(const float* __restrict__ raw, int B, int ny, int nx, int pitch, int na, int no,
+                                                          const float* __restrict__ anchors_px, float stride, float* __restrict__ z,
+                                                          long long z_rows, long long z_off, float* __restrict__ xperm,
+                                                          uint32_t* __restrict__ hist, float conf, int multi_label) {
+  const int lane = threadIdx.x & 31;
   const long long npix = (long long)ny * nx;
-  const long long total = (long long)B * na * npix * no;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i % no);
-    long long t = i / no;
-    const long long pix = t % npix;
-    t /= npix;
+  const long long rows = (long long)B * na * npix;
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
+    const long long pix = row % npix;
+    const long long t = row / npix;
     const int a = (int)(t % na);
     const int b = (int)(t / na);
-    const float v = __ldg(raw + ((size_t)b * npix + pix) * pitch + a * no + c);
-    if (xperm != nullptr) xperm[i] = v;
-    if (z != nullptr) {
-      // reference: y = x.sigmoid(); xy = (y*2 - 0.5 + grid) * stride; wh = (y*2)**2 * anchor_grid   (yolov5_detect.py:50-53)
-      const float y = 1.0f / (1.0f + expf(-v));
-      float o = y;
-      if (c < 2) {
-        const float g = (c == 0) ? (float)(pix % nx) : (float)(pix / nx);
-        o = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(y, 2.0f), 0.5f), g), stride);
-      } else if (c < 4) {
-        const float t2 = __fmul_rn(y, 2.0f);
-        o = __fmul_rn(__fmul_rn(t2, t2), __ldg(anchors_px + a * 2 + (c - 2)));
+    const float* src = raw + ((size_t)b * npix + pix) * pitch + a * no;
+    float* zdst = z ? z + ((size_t)b * z_rows + z_off + (long long)a * npix + pix) * no : nullptr;
+    float* xdst = xperm ? xperm + (size_t)row * no : nullptr;
+    const float gx = (float)(pix % nx), gy = (float)(pix / nx);
+    float obj = 0.0f, best = -1.0f;
+    for (int c0 = 0; c0 < no; c0 += 32) {
+      const int c = c0 + lane;
+      float o = 0.0f;
+      if (c < no) {
+        const float v = __ldg(src + c);
+        if (xdst) xdst[c] = v;
+        // reference: y = x.sigmoid(); xy = (y*2 - 0.5 + grid) * stride; wh = (y*2)**2 * anchor_grid   (yolov5_detect.py:50-53)
+        const float y = 1.0f / (1.0f + expf(-v));
+        o = y;
+        if (c < 2) {
+          o = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(y, 2.0f), 0.5f), c == 0 ? gx : gy), stride);
+        } else if (c < 4) {
+          const float t2 = __fmul_rn(y, 2.0f);
+          o = __fmul_rn(__fmul_rn(t2, t2), __ldg(anchors_px + a * 2 + (c - 2)));
+        }
+        if (zdst) zdst[c] = o;
       }
-      z[((size_t)b * z_rows + z_off + (long long)a * npix + pix) * no + c] = o;
+      if (hist != nullptr) {
+        if (c0 == 0) obj = __shfl_sync(0xffffffffu, o, 4);
+        if (obj > conf && c >= 5 && c < no) {
+          const float s = __fmul_rn(o, obj);  // same fp32 product the NMS kernels recompute from z (yolov5.py:106)
+          if (multi_label) {
+            if (s > conf) atomicAdd(&hist[(size_t)b * kNmsBins + min(__float_as_uint(s) >> 17, (uint32_t)(kNmsBins - 1))], 1u);
+          } else {
+            best = fmaxf(best, s);
+          }
+        }
+      }
+    }
+    if (hist != nullptr && !multi_label && obj > conf) {
+#pragma unroll
+      for (int o2 = 16; o2 > 0; o2 >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o2));
+      if (lane == 0 && best > conf) atomicAdd(&hist[(size_t)b * kNmsBins + min(__float_as_uint(best) >> 17, (uint32_t)(kNmsBins - 1))], 1u);
     }
   }
 }
@@ -311,16 +338,18 @@ extern "C" int cvb_sppf_pool(const CvbView* x, const CvbView* y1, const CvbView*
 }
 
 extern "C" int cvb_yolo_decode(const CvbView* raw, int32_t na, int32_t no, const float* anchors_px, float stride, float* z, int64_t z_rows,
-                               int64_t z_off, float* xperm, void* stream) {
+                               int64_t z_off, float* xperm, void* nms_workspace, float conf_thres, int32_t multi_label, void* stream) {
   CVB_REQUIRE(raw && raw->base && anchors_px, "yolo_decode: null argument");
   CVB_REQUIRE(raw->c_pitch >= na * no, "yolo_decode: raw pitch %d < na*no %d", raw->c_pitch, na * no);
   CVB_REQUIRE(z != nullptr || xperm != nullptr, "yolo_decode: nothing to write");
-  const long long total = (long long)raw->B * na * raw->H * raw->W * no;
+  CVB_REQUIRE(nms_workspace == nullptr || z != nullptr, "yolo_decode: histogram needs the decoded output");
+  const long long rows = (long long)raw->B * na * raw->H * raw->W;
   const int block = 256;
-  long long grid = (total + block - 1) / block;
+  long long grid = (rows + 7) / 8;
   if (grid > 148 * 16) grid = 148 * 16;
   yolo_decode_kernel<<<(int)grid, block, 0, as_stream(stream)>>>(static_cast<const float*>(raw->base), raw->B, raw->H, raw->W, raw->c_pitch,
-                                                                na, no, anchors_px, stride, z, z_rows, z_off, xperm);
+                                                                na, no, anchors_px, stride, z, z_rows, z_off, xperm,
+                                                                static_cast<uint32_t*>(nms_workspace), conf_thres, multi_label);
   CVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return CVB_OK;

@@ -14,10 +14,10 @@
 // (hi*hi + hi*lo + lo*hi), fp32 accumulation in TMEM -> fp32-equivalent results (rel. err ~1e-6) on the
 // fp16 tensor pipe.  The reference computes fp32 (trainer.py:209 val path is un-autocast).
 //
-// Structure (persistent, warp specialised, 192 threads, 1 CTA/SM):
+// Structure (persistent, warp specialised, 320 threads, 1 CTA/SM):
 //   warp 0      TMA producer   (one lane)   smem ring: full[]/empty[] mbarriers
 //   warp 1      MMA issuer     (one lane)   TMEM accumulators double buffered: tfull[]/tempty[]
-//   warps 2..5  epilogue: tcgen05.ld -> +partial +bias -> act -> +residual -> hi/lo split -> swizzled smem -> TMA store
+//   warps 2..9  epilogue (two warps per TMEM lane quarter): tcgen05.ld -> +partial +bias -> act -> +residual -> hi/lo split -> swizzled smem -> TMA store
 #include <cuda_fp16.h>
 
 #include <mutex>
@@ -30,7 +30,8 @@ namespace cvb {
 
 constexpr int kTileM = 128;
 constexpr int kMaxTaps = 9;
-constexpr int kThreads = 192;
+constexpr int kEpiThreads = 256;          // 8 epilogue warps
+constexpr int kThreads = 64 + kEpiThreads;  // + TMA producer warp + MMA issuer warp
 constexpr int kSmemBudget = 232448;  // 227 KB opt-in limit per CTA on sm_100
 
 struct alignas(64) ConvKArgs {
@@ -43,6 +44,8 @@ struct alignas(64) ConvKArgs {
   int cout;
   int taps, chunks, cin;
   int stages;
+  int n_main;   // number of round-robin accumulators for the hi*hi products (1..3); the cross terms have their own
+  int nbuf;     // accumulator sets in TMEM (2 = epilogue of tile i overlaps the MMAs of tile i+1)
   int act;
   int rows_valid;
   uint32_t a_box_bytes;
@@ -64,8 +67,25 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-__device__ __forceinline__ uint32_t pack_half2(__half a, __half b) {
-  return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+// x * sigmoid(x) with two MUFU ops (ex2, rcp); |rel err| ~ 2^-22.  x -> -inf gives -0, x -> +inf gives x.
+__device__ __forceinline__ float silu_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;
+}
+
+// (x0, x1) -> packed fp16 hi pair and lo = x - hi pair; saturating converts (one F2FP per pair) keep |x| > 65504 finite
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - hf.y), "f"(x0 - hf.x));
+}
+
+template <int CW>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[CW]) {
+  if constexpr (CW == 32) tmem_ld_32x32(taddr, v);
+  else tmem_ld_32x16(taddr, v);
 }
 
 template <int BLOCK_N, int BLOCK_K, bool OUT_F32>
@@ -78,7 +98,7 @@ struct ConvCfg {
   static constexpr int OUT_ROW_BYTES = OUT_F32 ? 128 : OUT_GROUP_CH * 2;
   static constexpr int OUT_PLANE_BYTES = kTileM * OUT_ROW_BYTES;
   static constexpr int OUT_STAGE_BYTES = OUT_PLANE_BYTES * (OUT_F32 ? 1 : 2);
-  static constexpr int TMEM_COLS = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
+  static constexpr int TMEM_COLS = 512;  // whole TMEM: nbuf x (n_main + 1) accumulators of BLOCK_N columns (1 CTA/SM)
   static constexpr int TAIL_BYTES = BLOCK_N * 4 + 64 * 8 + 16;  // bias + barriers + tmem slot
   static constexpr int smem_bytes(int stages) { return 1024 + stages * STAGE_BYTES + OUT_STAGE_BYTES + TAIL_BYTES; }
 };
@@ -123,7 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tfull[s], 1);
-        mbar_init(&tempty[s], 4);
+        mbar_init(&tempty[s], kEpiThreads / 32);
       }
       fence_barrier_init();
     }
@@ -182,10 +202,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      const int n_main = a.n_main;
+      const uint32_t set_cols = (uint32_t)((n_main + 1) * BLOCK_N);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(&tempty[acc], acc_phase ^ 1, 200 + acc);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        // The tensor core's fp32 adder rounds toward zero, so a long accumulation chain shrinks |sum| by ~1.6e-8 per
+        // MMA (measured, tools/precision_probe.py).  Chains are kept short: the hi*hi products rotate over n_main
+        // accumulators, the (2^-11 smaller) hi*lo + lo*hi cross terms go to their own; the epilogue adds them in RN fp32.
+        const uint32_t d_base = tmem_base + (uint32_t)acc * set_cols;
+        const uint32_t d_cross = d_base + (uint32_t)(n_main * BLOCK_N);
+        int r = 0;
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&full[stage], phase, 300 + stage);
           tc_fence_after();
@@ -194,36 +221,46 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           const uint64_t dal = make_kmajor_desc<SWZ>(sa + A_BYTES);
           const uint64_t dbh = make_kmajor_desc<SWZ>(sa + 2 * A_BYTES);
           const uint64_t dbl = make_kmajor_desc<SWZ>(sa + 2 * A_BYTES + B_BYTES);
+          const uint32_t d_main = d_base + (uint32_t)(r * BLOCK_N);
+          const bool first_main = it < n_main;
 #pragma unroll
           for (int k = 0; k < BLOCK_K / 16; ++k) {
             const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes per UMMA_K step, in 16-byte units
-            umma_f16(d_tmem, dah + koff, dbh + koff, IDESC, (it | k) != 0 ? 1u : 0u);
-            umma_f16(d_tmem, dah + koff, dbl + koff, IDESC, 1u);
-            umma_f16(d_tmem, dal + koff, dbh + koff, IDESC, 1u);
+            umma_f16(d_main, dah + koff, dbh + koff, IDESC, (first_main && k == 0) ? 0u : 1u);
+            umma_f16(d_cross, dah + koff, dbl + koff, IDESC, (it | k) != 0 ? 1u : 0u);
+            umma_f16(d_cross, dal + koff, dbh + koff, IDESC, 1u);
           }
           umma_commit(&empty[stage]);  // frees this smem stage once the MMAs above have read it
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
+          if (++r == n_main) r = 0;
         }
-        umma_commit(&tfull[acc]);  // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        umma_commit(&tfull[acc]);  // accumulators complete -> epilogue
+        if (++acc == a.nbuf) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    // Two warps per TMEM lane quarter (a warp may only touch lanes 32*(warp%4)..+31): each handles half of the columns
+    // of every staged group, so every SM sub-partition has two warps to hide MUFU / tcgen05.ld latency.
     const int q = warp & 3;           // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2; // which half of each column group this warp converts
     const int row = q * 32 + lane;    // accumulator row == pixel index inside the tile box
     const int tid_e = threadIdx.x - 64;
     const int tw = row % a.TW;
     const int r2 = row / a.TW;
     const int th = r2 % a.TH;
     const int nb = r2 / a.TH;
+    constexpr int CW = OUT_GROUP_CH / 2;  // columns per warp per group (32, or 16 for 32-wide groups)
     int acc = 0;
     uint32_t acc_phase = 0;
     int cur_n0 = -1;
+    const int n_main = a.n_main;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % a.tiles_n;
       const int mt = tile / a.tiles_n;
@@ -236,9 +273,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const bool valid = (row < a.rows_valid) && (ow < a.Wo) && (oh < a.Ho) && (ob < a.Bn);
 
       if (n0 != cur_n0) {
-        named_bar_sync(1, 128);
-        for (int i = tid_e; i < BLOCK_N; i += 128) bias_s[i] = (n0 + i < a.bias_len) ? a.bias[n0 + i] : 0.0f;
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kEpiThreads);
+        for (int i = tid_e; i < BLOCK_N; i += kEpiThreads) bias_s[i] = (n0 + i < a.bias_len) ? a.bias[n0 + i] : 0.0f;
+        named_bar_sync(1, kEpiThreads);
         cur_n0 = n0;
       }
       const float* up_row = nullptr;
@@ -249,86 +286,94 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
       mbar_wait(&tfull[acc], acc_phase, 400 + acc);
       tc_fence_after();
+      const uint32_t t_set = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (n_main + 1) * BLOCK_N);
 
 #pragma unroll 1
       for (int g = 0; g < BLOCK_N / OUT_GROUP_CH; ++g) {
         if (tid_e == 0) tma_store_wait_read0();  // previous TMA store has finished reading the staging tile
-        named_bar_sync(1, 128);
-#pragma unroll 1
-        for (int hh = 0; hh < OUT_GROUP_CH / 32; ++hh) {
-          const int col = g * OUT_GROUP_CH + hh * 32;
-          uint32_t v[32];
-          tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N + col), v);
+        named_bar_sync(1, kEpiThreads);
+        const int col = g * OUT_GROUP_CH + half * CW;
+        float f[CW];
+        {
+          uint32_t v[CW];
+          tmem_ld_cols<CW>(t_set + (uint32_t)(n_main * BLOCK_N + col), v);  // cross terms first (smallest magnitude)
           tmem_ld_wait();
-          float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          const bool ch_ok = (n0 + col + 32 <= a.cout);
-          if (up_row != nullptr && ch_ok) {
-            const float4* p = reinterpret_cast<const float4*>(up_row + col);
+          for (int j = 0; j < CW; ++j) f[j] = __uint_as_float(v[j]);
+          for (int r = 0; r < n_main; ++r) {
+            tmem_ld_cols<CW>(t_set + (uint32_t)(r * BLOCK_N + col), v);
+            tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 u = __ldg(p + j);
-              f[4 * j + 0] += u.x;
-              f[4 * j + 1] += u.y;
-              f[4 * j + 2] += u.z;
-              f[4 * j + 3] += u.w;
-            }
+            for (int j = 0; j < CW; ++j) f[j] = __fadd_rn(f[j], __uint_as_float(v[j]));
           }
+        }
+        const bool ch_ok = (n0 + col + CW <= a.cout);
+        if (up_row != nullptr && ch_ok) {
+          const float4* p = reinterpret_cast<const float4*>(up_row + col);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j] + bias_s[col + j], a.act);
-          if (res_row != nullptr && ch_ok) {
-            const uint4* ph = reinterpret_cast<const uint4*>(res_row + col);
-            const uint4* pl = reinterpret_cast<const uint4*>(res_row + a.resid_plane + col);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 hv = __ldg(ph + j);
-              const uint4 lv = __ldg(pl + j);
-              const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-              const uint32_t lw[4] = {lv.x, lv.y, lv.z, lv.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const __half2 h2 = *reinterpret_cast<const __half2*>(&hw[e]);
-                const __half2 l2 = *reinterpret_cast<const __half2*>(&lw[e]);
-                f[8 * j + 2 * e + 0] += __low2float(h2) + __low2float(l2);
-                f[8 * j + 2 * e + 1] += __high2float(h2) + __high2float(l2);
-              }
-            }
+          for (int j = 0; j < CW / 4; ++j) {
+            const float4 u = __ldg(p + j);
+            f[4 * j + 0] += u.x;
+            f[4 * j + 1] += u.y;
+            f[4 * j + 2] += u.z;
+            f[4 * j + 3] += u.w;
           }
-          if constexpr (OUT_F32) {
-            // row = 32 fp32 = 128 B, 8 chunks of 16 B, 128B swizzle: chunk ^= row & 7
-            uint8_t* rowp = out_stage + row * 128;
+        }
+        if (a.act == CVB_ACT_SILU) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const uint4 o = make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
-                                         __float_as_uint(f[4 * j + 3]));
-              *reinterpret_cast<uint4*>(rowp + ((j ^ (row & 7)) << 4)) = o;
-            }
-          } else {
-            uint8_t* rowh = out_stage + row * OUT_ROW_BYTES;
-            uint8_t* rowl = rowh + Cfg::OUT_PLANE_BYTES;
+          for (int j = 0; j < CW; ++j) f[j] = silu_fast(f[j] + bias_s[col + j]);
+        } else if (a.act == CVB_ACT_RELU) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint32_t hq[4], lq[4];
+          for (int j = 0; j < CW; ++j) f[j] = fmaxf(f[j] + bias_s[col + j], 0.0f);
+        } else {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float x0 = fminf(fmaxf(f[8 * j + 2 * e], -65504.0f), 65504.0f);
-                const float x1 = fminf(fmaxf(f[8 * j + 2 * e + 1], -65504.0f), 65504.0f);
-                const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
-                const __half l0 = __float2half_rn(x0 - __half2float(h0)), l1 = __float2half_rn(x1 - __half2float(h1));
-                hq[e] = pack_half2(h0, h1);
-                lq[e] = pack_half2(l0, l1);
-              }
-              int chunk;
-              if constexpr (OUT_GROUP_CH == 64) chunk = (hh * 4 + j) ^ (row & 7);   // 128B swizzle
-              else chunk = j ^ ((row >> 1) & 3);                                    // 64B swizzle
-              *reinterpret_cast<uint4*>(rowh + (chunk << 4)) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
-              *reinterpret_cast<uint4*>(rowl + (chunk << 4)) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+          for (int j = 0; j < CW; ++j) f[j] = f[j] + bias_s[col + j];
+        }
+        if (res_row != nullptr && ch_ok) {
+          const uint4* ph = reinterpret_cast<const uint4*>(res_row + col);
+          const uint4* pl = reinterpret_cast<const uint4*>(res_row + a.resid_plane + col);
+#pragma unroll
+          for (int j = 0; j < CW / 8; ++j) {
+            const uint4 hv = __ldg(ph + j);
+            const uint4 lv = __ldg(pl + j);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&hv);
+            const __half2* l2 = reinterpret_cast<const __half2*>(&lv);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 hf = __half22float2(h2[e]);
+              const float2 lf = __half22float2(l2[e]);
+              f[8 * j + 2 * e + 0] += hf.x + lf.x;
+              f[8 * j + 2 * e + 1] += hf.y + lf.y;
             }
           }
         }
+        if constexpr (OUT_F32) {
+          // row = 32 fp32 = 128 B = 8 chunks of 16 B, 128B swizzle: chunk ^= row & 7; this warp owns chunks half*4 .. +3
+          uint8_t* rowp = out_stage + row * 128;
+#pragma unroll
+          for (int j = 0; j < CW / 4; ++j) {
+            const uint4 o = make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                                       __float_as_uint(f[4 * j + 3]));
+            *reinterpret_cast<uint4*>(rowp + (((half * (CW / 4) + j) ^ (row & 7)) << 4)) = o;
+          }
+        } else {
+          uint8_t* rowh = out_stage + row * OUT_ROW_BYTES;
+          uint8_t* rowl = rowh + Cfg::OUT_PLANE_BYTES;
+#pragma unroll
+          for (int j = 0; j < CW / 8; ++j) {
+            uint32_t hq[4], lq[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) split_pair(f[8 * j + 2 * e], f[8 * j + 2 * e + 1], hq[e], lq[e]);
+            const int cj = half * (CW / 8) + j;  // 16-byte chunk (8 channels) inside the staged row
+            int chunk;
+            if constexpr (OUT_GROUP_CH == 64) chunk = cj ^ (row & 7);   // 128B swizzle
+            else chunk = cj ^ ((row >> 1) & 3);                         // 64B swizzle
+            *reinterpret_cast<uint4*>(rowh + (chunk << 4)) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
+            *reinterpret_cast<uint4*>(rowl + (chunk << 4)) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+          }
+        }
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-        named_bar_sync(1, 128);
+        named_bar_sync(1, kEpiThreads);
         if (tid_e == 0) {
           const int c0 = n0 + g * OUT_GROUP_CH;
           if (c0 < a.cout) {
@@ -338,12 +383,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           tma_store_commit();
         }
       }
-      // all tcgen05.ld of this accumulator are complete -> hand it back to the MMA warp
+      // all tcgen05.ld of this accumulator set are complete -> hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (++acc == a.nbuf) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
     }
     if (tid_e == 0) tma_store_wait_all0();
   }
@@ -614,6 +661,19 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
     return set_error(CVB_ERR_INVALID, "conv: tile does not fit in shared memory (block_n=%d block_k=%d)", bn, bk);
   }
   a.stages = stages;
+  {
+    // accumulation chains of at most ~48 MMAs (see the MMA issuer); all accumulator sets must fit the 512 TMEM columns
+    const int chain = a.taps * cin / 16;
+    int n_main = (chain + 47) / 48;
+    if (n_main > 3) n_main = 3;
+    while ((n_main + 1) * bn > 512) --n_main;
+    if (n_main < 1) {
+      delete p;
+      return set_error(CVB_ERR_INVALID, "conv: block_n=%d leaves no room for the split accumulators", bn);
+    }
+    a.n_main = n_main;
+    a.nbuf = (2 * (n_main + 1) * bn <= 512) ? 2 : 1;
+  }
   p->smem = fixed + stages * ke.stage_bytes;
   p->fn = ke.fn;
 

@@ -35,4 +35,7 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// NMS score histogram (shared by nms.cu and the decode kernel): bin = float_bits(score) >> 17, per image
+constexpr int kNmsBins = 16384;
+
 }  // namespace cvb

@@ -21,7 +21,7 @@
 
 namespace cvb {
 
-constexpr int kBins = 16384;   // score_bits >> 17 for positive floats
+constexpr int kBins = kNmsBins;  // score_bits >> 17 for positive floats
 constexpr int kCap = 65536;    // candidate key capacity per image
 constexpr int kChunk = 4096;   // keys sorted per CTA in shared memory
 constexpr int kGreedyThreads = 512;
@@ -48,37 +48,59 @@ static NmsWs carve_ws(void* ws, int B) {
   return w;
 }
 
-// ------------------------------------------------------------------ pass 1/2: scan predictions (warp per anchor row)
+// ------------------------------------------------------------------ pass 1/2: scan predictions
+// Grid (ceil(A / kRowsPerCta), B); each warp walks rows of ONE image.  COUNT pass: histogram of score bits (spread
+// global atomics).  EMIT pass: candidates are staged in shared memory (warp-aggregated smem atomics), then the CTA
+// reserves one contiguous range of the image's key array with a single global atomic and copies the keys out
+// coalesced -- the per-image counter sees ~A/64 atomics instead of one per candidate.
+constexpr int kRowsPerCta = 64;
+constexpr int kScanThreads = 256;
+
+__device__ __forceinline__ uint32_t score_bin(uint32_t bits) { return min(bits >> 17, (uint32_t)(kBins - 1)); }
+
 template <bool EMIT>
-__global__ void nms_scan_kernel(const float* __restrict__ pred, int B, int A, int nc, float conf, int multi_label, NmsWs ws,
-                                int* __restrict__ status) {
+__global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const float* __restrict__ pred, int B, int A, int nc, float conf,
+                                                                int multi_label, NmsWs ws, int* __restrict__ status) {
+  extern __shared__ uint64_t stage[];  // EMIT: [kRowsPerCta * nc] worst case
+  __shared__ uint32_t s_cnt, s_base;
   const int no = nc + 5;
-  const int lane = threadIdx.x & 31;
-  const long long warps_total = (long long)gridDim.x * (blockDim.x >> 5);
-  const long long rows = (long long)B * A;
-  for (long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += warps_total) {
-    const float* r = pred + row * no;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int row0 = blockIdx.x * kRowsPerCta;
+  const int row1 = min(A, row0 + kRowsPerCta);
+  if (EMIT) {
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+  }
+  const uint32_t tb = EMIT ? ws.tbin[b] : 0u;
+  for (int anchor = row0 + warp; anchor < row1; anchor += kScanThreads / 32) {
+    const float* r = pred + ((size_t)b * A + anchor) * no;
     const float obj = __ldg(r + 4);
     if (!(obj > conf)) continue;
-    const int b = (int)(row / A);
-    const int anchor = (int)(row % A);
-    uint32_t tb = 0;
-    if (EMIT) tb = ws.tbin[b];
     if (multi_label) {
-      for (int c = lane; c < nc; c += 32) {
-        const float s = __fmul_rn(__ldg(r + 5 + c), obj);
-        if (s > conf) {
-          const uint32_t bits = __float_as_uint(s);
-          const uint32_t bin = min(bits >> 17, (uint32_t)(kBins - 1));
-          if (EMIT) {
-            if (bin >= tb) {
-              const uint32_t pos = atomicAdd(&ws.cnt[b], 1u);
+      for (int c0 = 0; c0 < nc; c0 += 32) {
+        const int c = c0 + lane;
+        bool pass = false;
+        uint32_t bits = 0;
+        if (c < nc) {
+          const float s = __fmul_rn(__ldg(r + 5 + c), obj);
+          if (s > conf) {
+            bits = __float_as_uint(s);
+            const uint32_t bin = score_bin(bits);
+            if (EMIT) pass = bin >= tb;
+            else atomicAdd(&ws.hist[(size_t)b * kBins + bin], 1u);
+          }
+        }
+        if (EMIT) {
+          const uint32_t m = __ballot_sync(0xffffffffu, pass);
+          if (m) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&s_cnt, (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) {
               const uint32_t id = (uint32_t)anchor * (uint32_t)nc + (uint32_t)c;
-              if (pos < (uint32_t)kCap) ws.keys[(size_t)b * kCap + pos] = ((uint64_t)bits << 32) | (uint64_t)(0xFFFFFFFFu - id);
-              else if (status) atomicExch(&status[0], 1);
+              stage[base + __popc(m & ((1u << lane) - 1))] = ((uint64_t)bits << 32) | (uint64_t)(0xFFFFFFFFu - id);
             }
-          } else {
-            atomicAdd(&ws.hist[(size_t)b * kBins + bin], 1u);
           }
         }
       }
@@ -104,19 +126,29 @@ __global__ void nms_scan_kernel(const float* __restrict__ pred, int B, int A, in
       }
       if (lane == 0 && best > conf) {
         const uint32_t bits = __float_as_uint(best);
-        const uint32_t bin = min(bits >> 17, (uint32_t)(kBins - 1));
+        const uint32_t bin = score_bin(bits);
         if (EMIT) {
           if (bin >= tb) {
-            const uint32_t pos = atomicAdd(&ws.cnt[b], 1u);
             const uint32_t id = (uint32_t)anchor * (uint32_t)nc + (uint32_t)bi;
-            if (pos < (uint32_t)kCap) ws.keys[(size_t)b * kCap + pos] = ((uint64_t)bits << 32) | (uint64_t)(0xFFFFFFFFu - id);
-            else if (status) atomicExch(&status[0], 1);
+            stage[atomicAdd(&s_cnt, 1u)] = ((uint64_t)bits << 32) | (uint64_t)(0xFFFFFFFFu - id);
           }
         } else {
           atomicAdd(&ws.hist[(size_t)b * kBins + bin], 1u);
         }
       }
     }
+  }
+  if (EMIT) {
+    __syncthreads();
+    const uint32_t n = s_cnt;
+    if (n == 0) return;
+    if (threadIdx.x == 0) s_base = atomicAdd(&ws.cnt[b], n);
+    __syncthreads();
+    const uint32_t base = s_base;
+    if (base + n > (uint32_t)kCap && status && threadIdx.x == 0) atomicExch(&status[0], 1);
+    uint64_t* keys = ws.keys + (size_t)b * kCap;
+    for (uint32_t i = threadIdx.x; i < n; i += kScanThreads)
+      if (base + i < (uint32_t)kCap) keys[base + i] = stage[i];
   }
 }
 
@@ -392,6 +424,13 @@ extern "C" size_t cvb_nms_workspace_bytes(int32_t B, int32_t A, int32_t nc) {
   return align_up((size_t)B * kBins * 4, 256) + 2 * align_up((size_t)B * 4, 256) + (size_t)B * kCap * 8;
 }
 
+extern "C" int cvb_nms_workspace_reset(void* workspace, size_t workspace_bytes, int32_t B, void* stream) {
+  CVB_REQUIRE(workspace && B > 0 && workspace_bytes >= cvb_nms_workspace_bytes(B, 1, 1), "nms reset: bad workspace");
+  const size_t head_bytes = align_up((size_t)B * kBins * 4, 256) + 2 * align_up((size_t)B * 4, 256);
+  CVB_CHECK_CUDA(cudaMemsetAsync(workspace, 0, head_bytes, as_stream(stream)));
+  return CVB_OK;
+}
+
 extern "C" int cvb_yolo_nms(const float* prediction, const CvbNmsParams* p, float* det, int32_t* det_idx, int32_t* det_count,
                             void* workspace, size_t workspace_bytes, int32_t* status, void* stream) {
   CVB_REQUIRE(prediction && p && det && det_idx && det_count && workspace, "nms: null argument");
@@ -403,20 +442,27 @@ extern "C" int cvb_yolo_nms(const float* prediction, const CvbNmsParams* p, floa
   cudaStream_t st = as_stream(stream);
   NmsWs ws = carve_ws(workspace, p->B);
   const size_t head_bytes = align_up((size_t)p->B * kBins * 4, 256) + 2 * align_up((size_t)p->B * 4, 256);
-  CVB_CHECK_CUDA(cudaMemsetAsync(workspace, 0, head_bytes, st));
+  if (!p->hist_ready) CVB_CHECK_CUDA(cudaMemsetAsync(workspace, 0, head_bytes, st));
   if (status) CVB_CHECK_CUDA(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st));
   CVB_CHECK_CUDA(cudaMemsetAsync(det, 0, (size_t)p->B * p->max_det * 6 * sizeof(float), st));
   CVB_CHECK_CUDA(cudaMemsetAsync(det_idx, 0xFF, (size_t)p->B * p->max_det * sizeof(int32_t), st));
 
-  const long long rows = (long long)p->B * p->A;
-  const int block = 256;
-  long long grid = (rows + 7) / 8;
-  if (grid > 148 * 8) grid = 148 * 8;
-  nms_scan_kernel<false><<<(int)grid, block, 0, st>>>(prediction, p->B, p->A, p->nc, p->conf_thres, p->multi_label, ws, status);
+  dim3 sgrid(ceil_div(p->A, kRowsPerCta), p->B);
+  const size_t stage_bytes = (size_t)kRowsPerCta * p->nc * sizeof(uint64_t);
+  CVB_REQUIRE(stage_bytes <= 160 * 1024, "nms: too many classes (%d) for the shared-memory candidate stage", p->nc);
+  static bool scan_attr_set = false;
+  if (!scan_attr_set) {
+    CVB_CHECK_CUDA(cudaFuncSetAttribute(nms_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    scan_attr_set = true;
+  }
+  if (!p->hist_ready) {
+    nms_scan_kernel<false><<<sgrid, kScanThreads, 0, st>>>(prediction, p->B, p->A, p->nc, p->conf_thres, p->multi_label, ws, status);
+    count_launch();
+  }
   nms_threshold_kernel<<<p->B, 256, 0, st>>>(ws, p->max_nms);
-  nms_scan_kernel<true><<<(int)grid, block, 0, st>>>(prediction, p->B, p->A, p->nc, p->conf_thres, p->multi_label, ws, status);
+  nms_scan_kernel<true><<<sgrid, kScanThreads, stage_bytes, st>>>(prediction, p->B, p->A, p->nc, p->conf_thres, p->multi_label, ws, status);
   CVB_CHECK_CUDA(cudaGetLastError());
-  count_launch(3);
+  count_launch(2);
 
   dim3 lgrid(kCap / kChunk, p->B);
   bitonic_local_sort_kernel<<<lgrid, 1024, 0, st>>>(ws);

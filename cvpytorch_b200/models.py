@@ -189,14 +189,20 @@ class YOLOv5Detect(_GraphCache):
             b.data[:, 5:] += math.log(0.6 / (self.num_classes - 0.999999)) if cf is None else torch.log(cf / cf.sum())
             mi.bias = torch.nn.Parameter(b.view(-1), requires_grad=True)
 
-    def emit(self, g, feats, name='detect', want_raw=True):
-        """Returns (z tensor [B, A, no] fp32 on device, [raw_i [B,na,ny,nx,no]] or None)."""
+    def num_candidates(self, feats):
+        return sum(self.num_anchors * f.H * f.W for f in feats)
+
+    def emit(self, g, feats, name='detect', want_raw=True, nms_ws=None, conf_thres=0.001, multi_label=True):
+        """Returns (z tensor [B, A, no] fp32 on device, [raw_i [B,na,ny,nx,no]] or None).
+        nms_ws: the decode kernels also accumulate the NMS score histogram into this workspace (fused count pass)."""
         na, no = self.num_anchors, self.num_outputs
-        A = sum(na * f.H * f.W for f in feats)
+        A = self.num_candidates(feats)
         dev = g.device
         z = torch.zeros((g.B, A, no), dtype=torch.float32, device=dev)
         raws = []
         off = 0
+        if nms_ws is not None:
+            g.fn(lambda: ops.nms_reset(nms_ws))
         for i, f in enumerate(feats):
             cpitch = (na * no + 31) // 32 * 32
             raw = g.new_f32(f.H, f.W, cpitch)
@@ -206,7 +212,7 @@ class YOLOv5Detect(_GraphCache):
             xp = torch.zeros((g.B, na, f.H, f.W, no), dtype=torch.float32, device=dev) if want_raw else None
             raws.append(xp)
             g.fn(lambda raw=raw, anchors_px=anchors_px, s=float(self.stride[i]), off=off, xp=xp:
-                 ops.yolo_decode(raw.view(0, na * no), na, no, anchors_px, s, z, A, off, xp))
+                 ops.yolo_decode(raw.view(0, na * no), na, no, anchors_px, s, z, A, off, xp, nms_ws, conf_thres, multi_label))
             off += na * f.H * f.W
         g.buffers.append(z)
         return z, (raws if want_raw else None)
@@ -324,10 +330,10 @@ class YOLOv5(_GraphCache):
         holder = {}
         feats = self.backbone.emit(g, lambda: holder['x'], H, W)
         feats = self.neck.emit(g, feats)
-        z, raws = self.detect.emit(g, feats, want_raw=want_raw)
-        ws = ops.NmsWorkspace(B, z.shape[1], self.num_classes, max_det=self.max_det, device=device)
         conf, iou = self.conf_thres, self.iou_thres
-        g.fn(lambda: ops.yolo_nms(z, ws, conf, iou, True))
+        ws = ops.NmsWorkspace(B, self.detect.num_candidates(feats), self.num_classes, max_det=self.max_det, device=device)
+        z, raws = self.detect.emit(g, feats, want_raw=want_raw, nms_ws=ws, conf_thres=conf, multi_label=True)
+        g.fn(lambda: ops.yolo_nms(z, ws, conf, iou, True, hist_ready=True))
         return dict(g=g, holder=holder, z=z, raws=raws, ws=ws)
 
     def _graph_for(self, imgs, want_raw=False):

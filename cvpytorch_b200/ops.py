@@ -193,10 +193,17 @@ def sppf_pool(x, y1, y2, y3):
     _lib.check(_lib.lib().cvb_sppf_pool(byref(x), byref(y1), byref(y2), byref(y3), _stream()), 'cvb_sppf_pool')
 
 
-def yolo_decode(raw_view, na, no, anchors_px, stride, z, z_rows, z_off, xperm=None):
+def yolo_decode(raw_view, na, no, anchors_px, stride, z, z_rows, z_off, xperm=None, nms_ws=None, conf_thres=0.001, multi_label=True):
+    """nms_ws: NmsWorkspace previously reset with nms_reset(); the decode then also fills the NMS score histogram."""
     _lib.check(_lib.lib().cvb_yolo_decode(byref(raw_view), na, no, anchors_px.data_ptr(), float(stride),
                                           z.data_ptr() if z is not None else None, z_rows, z_off,
-                                          xperm.data_ptr() if xperm is not None else None, _stream()), 'cvb_yolo_decode')
+                                          xperm.data_ptr() if xperm is not None else None,
+                                          nms_ws.ws_ptr if nms_ws is not None else None, float(conf_thres),
+                                          1 if (multi_label and no - 5 > 1) else 0, _stream()), 'cvb_yolo_decode')
+
+
+def nms_reset(ws):
+    _lib.check(_lib.lib().cvb_nms_workspace_reset(ws.ws_ptr, ws.ws_bytes, ws.B, _stream()), 'cvb_nms_workspace_reset')
 
 
 class NmsWorkspace:
@@ -213,7 +220,7 @@ class NmsWorkspace:
         self.status = torch.zeros((4,), dtype=torch.int32, device=device)
 
 
-def yolo_nms(prediction, ws, conf_thres=0.001, iou_thres=0.6, multi_label=True, max_nms=30000, max_wh=4096.0):
+def yolo_nms(prediction, ws, conf_thres=0.001, iou_thres=0.6, multi_label=True, max_nms=30000, max_wh=4096.0, hist_ready=False):
     """Batched NMS on device.  Returns (det [B,max_det,6], det_idx [B,max_det], det_count [B]) -- device tensors
     owned by `ws`; no host synchronisation happens here."""
     _require_cuda(prediction, 'yolo_nms')
@@ -225,6 +232,7 @@ def yolo_nms(prediction, ws, conf_thres=0.001, iou_thres=0.6, multi_label=True, 
     p.conf_thres, p.iou_thres = conf_thres, iou_thres
     p.multi_label = 1 if (multi_label and no - 5 > 1) else 0
     p.max_nms, p.max_det, p.max_wh = max_nms, ws.max_det, max_wh
+    p.hist_ready = 1 if hist_ready else 0
     _lib.check(_lib.lib().cvb_yolo_nms(prediction.data_ptr(), byref(p), ws.det.data_ptr(), ws.det_idx.data_ptr(),
                                        ws.det_count.data_ptr(), ws.ws_ptr, ws.ws_bytes, ws.status.data_ptr(), _stream()),
                'cvb_yolo_nms')

@@ -110,10 +110,14 @@ int cvb_sppf_pool(const CvbView* x, const CvbView* y1, const CvbView* y2, const 
  * YOLOv5 decode of one level.  raw: fp32 NHWC [B,ny,nx,c_pitch>=na*no] conv output (+bias).
  *   z[b, z_off + (a*ny+y)*nx + x, :] = decode(sigmoid(raw))   (z row pitch = no floats, z_rows rows/img)
  *   xperm (optional) = raw permuted to [B,na,ny,nx,no]
+ *   nms_workspace (optional): a workspace prepared with cvb_nms_workspace_reset(); the decode then also accumulates the
+ *   NMS score histogram (conf_thres / multi_label as later passed to cvb_yolo_nms with hist_ready = 1), which saves
+ *   one full pass over the prediction tensor.
  * replaces: YOLOv5Detect.forward src/models/detects/yolov5_detect.py:42-55, _make_grid :60-65.
  */
 int cvb_yolo_decode(const CvbView* raw, int32_t na, int32_t no, const float* anchors_px /*[na*2]*/, float stride,
-                    float* z, int64_t z_rows, int64_t z_off, float* xperm, void* stream);
+                    float* z, int64_t z_rows, int64_t z_off, float* xperm, void* nms_workspace, float conf_thres,
+                    int32_t multi_label, void* stream);
 
 /*
  * Batched YOLOv5 NMS.  prediction: fp32 [B, A, 5+nc].  Outputs (fixed capacity, device):
@@ -133,9 +137,12 @@ typedef struct CvbNmsParams {
   int32_t max_nms;     /* 30000 */
   int32_t max_det;     /* 300   */
   float max_wh;        /* 4096 class offset; 0 = agnostic */
+  int32_t hist_ready;  /* 1: the score histogram was already accumulated by cvb_yolo_decode (all levels) */
 } CvbNmsParams;
 
 size_t cvb_nms_workspace_bytes(int32_t B, int32_t A, int32_t nc);
+/* zero the per-image histogram / counters (only needed before cvb_yolo_decode(..., nms_workspace, ...)) */
+int cvb_nms_workspace_reset(void* workspace, size_t workspace_bytes, int32_t B, void* stream);
 int cvb_yolo_nms(const float* prediction, const CvbNmsParams* p, float* det, int32_t* det_idx, int32_t* det_count,
                  void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
 
