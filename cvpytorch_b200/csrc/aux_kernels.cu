@@ -82,7 +82,7 @@ __global__ void f32nhwc_to_nchw_kernel(const float* __restrict__ src, int B, int
 // One thread per output pixel (b, h2, w2): reads a 2x2x3 patch (float2 per row/channel -> coalesced across
 // the warp) and writes 16 channels (12 used) as two 32-byte hi/lo records (coalesced across the warp).
 __global__ void stem_s2d_kernel(const float* __restrict__ src, int B, int H, int W, __half* __restrict__ dst, int pitch,
-                                long long plane) {
+                                long long plane, int Wd, int col_off) {
   const int W2 = W >> 1, H2 = H >> 1;
   const long long n = (long long)B * H2 * W2;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -110,7 +110,7 @@ __global__ void stem_s2d_kernel(const float* __restrict__ src, int B, int H, int
       hq[k] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
       lq[k] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
     }
-    __half* o = dst + (size_t)i * pitch;
+    __half* o = dst + (((size_t)b * H2 + h2) * Wd + (w2 + col_off)) * pitch;  // Wd > W2: zero-padded row-window layout
     reinterpret_cast<uint4*>(o)[0] = make_uint4(hq[0], hq[1], hq[2], hq[3]);
     reinterpret_cast<uint4*>(o)[1] = make_uint4(hq[4], hq[5], hq[6], hq[7]);
     reinterpret_cast<uint4*>(o + plane)[0] = make_uint4(lq[0], lq[1], lq[2], lq[3]);
@@ -187,26 +187,35 @@ __global__ void sppf_pool_kernel(const __half* __restrict__ x, int H, int W, int
 }
 
 // ------------------------------------------------------------------ YOLOv5 decode
-// One warp per output row (b, a, pix): 85 contiguous floats are read and written coalesced, index arithmetic is
-// per row (not per element).  While the scores are in registers the warp also feeds the NMS score histogram
-// (replaces the separate counting pass over the 548 MB prediction tensor).
-__global__ void __launch_bounds__(256) yolo_decode_kernel(const float* __restrict__ raw, int B, int ny, int nx, int pitch, int na, int no,
+// Grid (pixel chunks, B); one warp per output row (a, pix): 85 contiguous floats are read and written coalesced, all
+// index arithmetic is 32-bit and per row.  While the scores are in registers the CTA also builds the NMS score
+// histogram of its image in shared memory (64 KB) and flushes the non-empty bins once -- this replaces the separate
+// counting pass over the 548 MB prediction tensor and keeps the hot bins out of global atomics.
+constexpr int kDecodePix = 256;  // pixels per CTA (x na anchors rows)
+
+__global__ void __launch_bounds__(256) yolo_decode_kernel(const float* __restrict__ raw, int ny, int nx, int pitch, int na, int no,
                                                           const float* __restrict__ anchors_px, float stride, float* __restrict__ z,
                                                           long long z_rows, long long z_off, float* __restrict__ xperm,
                                                           uint32_t* __restrict__ hist, float conf, int multi_label) {
-  const int lane = threadIdx.x & 31;
-  const long long npix = (long long)ny * nx;
-  const long long rows = (long long)B * na * npix;
-  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
-    const long long pix = row % npix;
-    const long long t = row / npix;
-    const int a = (int)(t % na);
-    const int b = (int)(t / na);
+  extern __shared__ uint32_t s_hist[];  // [kNmsBins] when hist != nullptr
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const int npix = ny * nx;
+  const int pix0 = blockIdx.x * kDecodePix;
+  const int pix1 = min(npix, pix0 + kDecodePix);
+  if (hist != nullptr) {
+    for (int i = threadIdx.x; i < kNmsBins; i += blockDim.x) s_hist[i] = 0;
+    __syncthreads();
+  }
+  const int nrows = (pix1 - pix0) * na;
+  for (int rr = warp; rr < nrows; rr += 8) {
+    const int a = rr / (pix1 - pix0);
+    const int pix = pix0 + rr - a * (pix1 - pix0);
+    const int py = pix / nx, px = pix - py * nx;
     const float* src = raw + ((size_t)b * npix + pix) * pitch + a * no;
-    float* zdst = z ? z + ((size_t)b * z_rows + z_off + (long long)a * npix + pix) * no : nullptr;
-    float* xdst = xperm ? xperm + (size_t)row * no : nullptr;
-    const float gx = (float)(pix % nx), gy = (float)(pix / nx);
+    const size_t orow = (size_t)a * npix + pix;
+    float* zdst = z ? z + ((size_t)b * z_rows + z_off + orow) * no : nullptr;
+    float* xdst = xperm ? xperm + ((size_t)b * na * npix + orow) * no : nullptr;
     float obj = 0.0f, best = -1.0f;
     for (int c0 = 0; c0 < no; c0 += 32) {
       const int c = c0 + lane;
@@ -218,7 +227,7 @@ __global__ void __launch_bounds__(256) yolo_decode_kernel(const float* __restric
         const float y = 1.0f / (1.0f + expf(-v));
         o = y;
         if (c < 2) {
-          o = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(y, 2.0f), 0.5f), c == 0 ? gx : gy), stride);
+          o = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(y, 2.0f), 0.5f), c == 0 ? (float)px : (float)py), stride);
         } else if (c < 4) {
           const float t2 = __fmul_rn(y, 2.0f);
           o = __fmul_rn(__fmul_rn(t2, t2), __ldg(anchors_px + a * 2 + (c - 2)));
@@ -228,11 +237,11 @@ __global__ void __launch_bounds__(256) yolo_decode_kernel(const float* __restric
       if (hist != nullptr) {
         if (c0 == 0) obj = __shfl_sync(0xffffffffu, o, 4);
         if (obj > conf && c >= 5 && c < no) {
-          const float s = __fmul_rn(o, obj);  // same fp32 product the NMS kernels recompute from z (yolov5.py:106)
+          const float sc = __fmul_rn(o, obj);  // same fp32 product the NMS kernels recompute from z (yolov5.py:106)
           if (multi_label) {
-            if (s > conf) atomicAdd(&hist[(size_t)b * kNmsBins + min(__float_as_uint(s) >> 17, (uint32_t)(kNmsBins - 1))], 1u);
+            if (sc > conf) atomicAdd(&s_hist[min(__float_as_uint(sc) >> 17, (uint32_t)(kNmsBins - 1))], 1u);
           } else {
-            best = fmaxf(best, s);
+            best = fmaxf(best, sc);
           }
         }
       }
@@ -240,7 +249,15 @@ __global__ void __launch_bounds__(256) yolo_decode_kernel(const float* __restric
     if (hist != nullptr && !multi_label && obj > conf) {
 #pragma unroll
       for (int o2 = 16; o2 > 0; o2 >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o2));
-      if (lane == 0 && best > conf) atomicAdd(&hist[(size_t)b * kNmsBins + min(__float_as_uint(best) >> 17, (uint32_t)(kNmsBins - 1))], 1u);
+      if (lane == 0 && best > conf) atomicAdd(&s_hist[min(__float_as_uint(best) >> 17, (uint32_t)(kNmsBins - 1))], 1u);
+    }
+  }
+  if (hist != nullptr) {
+    __syncthreads();
+    uint32_t* gh = hist + (size_t)b * kNmsBins;
+    for (int i = threadIdx.x; i < kNmsBins; i += blockDim.x) {
+      const uint32_t v = s_hist[i];
+      if (v) atomicAdd(&gh[i], v);
     }
   }
 }
@@ -293,7 +310,8 @@ extern "C" int cvb_stem_s2d(const float* src, int32_t B, int32_t H, int32_t W, c
   int rc = check_split_view(dst, "stem_s2d");
   if (rc) return rc;
   CVB_REQUIRE(src && H % 2 == 0 && W % 2 == 0, "stem_s2d: H and W must be even");
-  CVB_REQUIRE(dst->B == B && dst->H == H / 2 && dst->W == W / 2 && dst->C == 16 && dst->c_pitch == 16, "stem_s2d: dst must be [B,H/2,W/2,16]");
+  CVB_REQUIRE(dst->B == B && dst->H == H / 2 && (dst->W == W / 2 || dst->W == W / 2 + 3) && dst->C == 16 && dst->c_pitch == 16,
+              "stem_s2d: dst must be [B,H/2,W/2,16] or the zero-padded row-window layout [B,H/2,W/2+3,16]");
   CVB_REQUIRE((reinterpret_cast<uintptr_t>(src) & 7) == 0 && (reinterpret_cast<uintptr_t>(dst->base) & 15) == 0 && dst->plane_stride % 16 == 0,
               "stem_s2d: alignment");
   const long long n = (long long)B * (H / 2) * (W / 2);
@@ -301,7 +319,7 @@ extern "C" int cvb_stem_s2d(const float* src, int32_t B, int32_t H, int32_t W, c
   long long grid = (n + block - 1) / block;
   if (grid > 148 * 32) grid = 148 * 32;
   stem_s2d_kernel<<<(int)grid, block, 0, as_stream(stream)>>>(src, B, H, W, static_cast<__half*>(dst->base), dst->c_pitch,
-                                                             dst->plane_stride / 2);
+                                                             dst->plane_stride / 2, dst->W, dst->W == W / 2 ? 0 : 1);
   CVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return CVB_OK;
@@ -343,13 +361,17 @@ extern "C" int cvb_yolo_decode(const CvbView* raw, int32_t na, int32_t no, const
   CVB_REQUIRE(raw->c_pitch >= na * no, "yolo_decode: raw pitch %d < na*no %d", raw->c_pitch, na * no);
   CVB_REQUIRE(z != nullptr || xperm != nullptr, "yolo_decode: nothing to write");
   CVB_REQUIRE(nms_workspace == nullptr || z != nullptr, "yolo_decode: histogram needs the decoded output");
-  const long long rows = (long long)raw->B * na * raw->H * raw->W;
-  const int block = 256;
-  long long grid = (rows + 7) / 8;
-  if (grid > 148 * 16) grid = 148 * 16;
-  yolo_decode_kernel<<<(int)grid, block, 0, as_stream(stream)>>>(static_cast<const float*>(raw->base), raw->B, raw->H, raw->W, raw->c_pitch,
-                                                                na, no, anchors_px, stride, z, z_rows, z_off, xperm,
-                                                                static_cast<uint32_t*>(nms_workspace), conf_thres, multi_label);
+  CVB_REQUIRE((long long)raw->H * raw->W * na < 0x7fffffffLL, "yolo_decode: level too large");
+  const size_t smem = nms_workspace ? (size_t)kNmsBins * sizeof(uint32_t) : 0;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CVB_CHECK_CUDA(cudaFuncSetAttribute(yolo_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsBins * (int)sizeof(uint32_t)));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(raw->H * raw->W, kDecodePix), raw->B);
+  yolo_decode_kernel<<<grid, 256, smem, as_stream(stream)>>>(static_cast<const float*>(raw->base), raw->H, raw->W, raw->c_pitch, na, no,
+                                                            anchors_px, stride, z, z_rows, z_off, xperm,
+                                                            static_cast<uint32_t*>(nms_workspace), conf_thres, multi_label);
   CVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return CVB_OK;

@@ -49,6 +49,8 @@ struct alignas(64) ConvKArgs {
   int act;
   int rows_valid;
   uint32_t a_box_bytes;
+  uint32_t a_lo_off;   // smem offset of the lo plane of A inside a stage (== a_box_bytes when hi+lo arrive in ONE TMA box)
+  int a_fused;         // 1: one 5D box {K, TW, TH, NB, 2 planes} per stage instead of two
   int8_t tap_map[kMaxTaps];
   int8_t tap_dh[kMaxTaps];
   int8_t tap_dw[kMaxTaps];
@@ -182,11 +184,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             mbar_wait(&empty[stage], phase ^ 1, 100 + stage);
             mbar_expect_tx(&full[stage], tx_bytes);
             uint8_t* sb = stage_base + stage * STAGE_BYTES;
-            tma_load_5d(mapA, &full[stage], sb, ck * BLOCK_K, cw, ch, b0, 0);
-            tma_load_5d(mapA, &full[stage], sb + A_BYTES, ck * BLOCK_K, cw, ch, b0, 1);
+            tma_load_5d(mapA, &full[stage], sb, ck * BLOCK_K, cw, ch, b0, 0);  // fused: both planes in one box
+            if (!a.a_fused) tma_load_5d(mapA, &full[stage], sb + A_BYTES, ck * BLOCK_K, cw, ch, b0, 1);
             const int kc = tap * a.cin + ck * BLOCK_K;
-            tma_load_3d(&a.tmB, &full[stage], sb + 2 * A_BYTES, kc, n0, 0);
-            tma_load_3d(&a.tmB, &full[stage], sb + 2 * A_BYTES + B_BYTES, kc, n0, 1);
+            tma_load_3d(&a.tmB, &full[stage], sb + 2 * A_BYTES, kc, n0, 0);    // box {K, N, 2 planes}: hi then lo
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -218,7 +219,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * STAGE_BYTES);
           const uint64_t dah = make_kmajor_desc<SWZ>(sa);
-          const uint64_t dal = make_kmajor_desc<SWZ>(sa + A_BYTES);
+          const uint64_t dal = make_kmajor_desc<SWZ>(sa + a.a_lo_off);
           const uint64_t dbh = make_kmajor_desc<SWZ>(sa + 2 * A_BYTES);
           const uint64_t dbl = make_kmajor_desc<SWZ>(sa + 2 * A_BYTES + B_BYTES);
           const uint32_t d_main = d_base + (uint32_t)(r * BLOCK_N);
@@ -508,14 +509,22 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
               kMaxTaps);
   CVB_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride %d unsupported", d->stride);
   CVB_REQUIRE(d->dilation >= 1, "conv: bad dilation");
-  const int cin = in.C, cout = out.C;
+  const int win = d->w_window;  // >0: K chunk of a filter row = `win` horizontally adjacent input pixels (see cvb200.h)
+  if (win > 0) {
+    CVB_REQUIRE(d->stride == 1 && d->dilation == 1 && d->kw <= win && d->pad == (d->kw - 1) / 2 && d->pad == (d->kh - 1) / 2,
+                "conv: w_window needs a stride-1 'same' convolution with kw <= w_window");
+    CVB_REQUIRE(in.c_pitch == in.C && (win * in.C == 64 || win * in.C == 32), "conv: w_window needs contiguous pixels and window*C in {32,64}");
+    CVB_REQUIRE(in.W > win - 1, "conv: padded input too narrow");
+  }
+  const int cin = win > 0 ? win * in.C : in.C;  // K per tap as seen by the GEMM
+  const int cout = out.C;
   CVB_REQUIRE(cin % 16 == 0, "conv: cin=%d must be a multiple of 16", cin);
   CVB_REQUIRE(in.c_pitch % 8 == 0 && out.c_pitch % 8 == 0, "conv: channel pitch must be a multiple of 8");
   CVB_REQUIRE((reinterpret_cast<uintptr_t>(in.base) & 15) == 0 && (reinterpret_cast<uintptr_t>(out.base) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(d->weights) & 15) == 0,
               "conv: pointers must be 16-byte aligned");
   const int Ho = (in.H + 2 * d->pad - d->dilation * (d->kh - 1) - 1) / d->stride + 1;
-  const int Wo = (in.W + 2 * d->pad - d->dilation * (d->kw - 1) - 1) / d->stride + 1;
+  const int Wo = win > 0 ? in.W - (win - 1) : (in.W + 2 * d->pad - d->dilation * (d->kw - 1) - 1) / d->stride + 1;
   CVB_REQUIRE(Ho == out.H && Wo == out.W && in.B == out.B, "conv: output view %dx%dx%d does not match computed %dx%dx%d", out.B, out.H,
               out.W, in.B, Ho, Wo);
   CVB_REQUIRE(d->cout_pad >= cout && d->cout_pad % 8 == 0, "conv: bad cout_pad");
@@ -546,16 +555,25 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   a.Wo = Wo;
   a.Bn = out.B;
   a.cout = cout;
-  a.taps = d->kh * d->kw;
+  a.taps = win > 0 ? d->kh : d->kh * d->kw;
   a.chunks = cin / bk;
   a.cin = cin;
   a.act = d->act;
   a.rows_valid = TW * TH * NB;
   a.a_box_bytes = (uint32_t)(TW * TH * NB * bk * 2);
+  a.a_fused = (a.rows_valid % 8 == 0) ? 1 : 0;  // the lo plane must start on a swizzle-atom boundary (8 rows)
+  a.a_lo_off = a.a_fused ? a.a_box_bytes : (uint32_t)(kTileM * bk * 2);
   a.bias = d->bias;
   a.bias_len = d->cout_pad;
 
   const int s = d->stride;
+  if (win > 0) {
+    for (int ky = 0; ky < d->kh; ++ky) {
+      a.tap_map[ky] = 0;
+      a.tap_dh[ky] = (int8_t)(ky - d->pad);
+      a.tap_dw[ky] = 0;  // the physical tensor carries the left zero column: window of output w starts at padded column w
+    }
+  } else
   for (int ky = 0; ky < d->kh; ++ky)
     for (int kx = 0; kx < d->kw; ++kx) {
       const int t = ky * d->kw + kx;
@@ -575,9 +593,14 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   int rc = CVB_OK;
   // ---- input maps: 5D (C, W, H, B, plane)
   {
-    const cuuint32_t box[5] = {(cuuint32_t)bk, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)NB, 1};
+    const cuuint32_t box[5] = {(cuuint32_t)bk, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)NB, (cuuint32_t)(a.a_fused ? 2 : 1)};
     const long long pix = (long long)in.c_pitch * 2;  // bytes per pixel
-    if (s == 1) {
+    if (win > 0) {
+      // overlapping-window view: element (k, w, h, b, p) = padded_input[p][b][h][w + k / C][k % C]; consecutive w overlap
+      const cuuint64_t dims[5] = {(cuuint64_t)cin, (cuuint64_t)Wo, (cuuint64_t)in.H, (cuuint64_t)in.B, 2};
+      const cuuint64_t str[4] = {(cuuint64_t)pix, (cuuint64_t)(pix * in.W), (cuuint64_t)(pix * in.W * in.H), (cuuint64_t)in.plane_stride};
+      rc = encode_map(&a.tmA[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, in.base, dims, str, box, swizzle_for_bytes(bk * 2));
+    } else if (s == 1) {
       const cuuint64_t dims[5] = {(cuuint64_t)cin, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.B, 2};
       const cuuint64_t str[4] = {(cuuint64_t)pix, (cuuint64_t)(pix * in.W), (cuuint64_t)(pix * in.W * in.H), (cuuint64_t)in.plane_stride};
       rc = encode_map(&a.tmA[0], CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, in.base, dims, str, box, swizzle_for_bytes(bk * 2));
@@ -602,7 +625,7 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
     const long long K = (long long)a.taps * cin;
     const cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)d->cout_pad, 2};
     const cuuint64_t str[2] = {(cuuint64_t)(K * 2), (cuuint64_t)(K * 2 * d->cout_pad)};
-    const cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)bn, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)bk, (cuuint32_t)bn, 2};
     rc = encode_map(&a.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(d->weights), dims, str, box, swizzle_for_bytes(bk * 2));
   }
   // ---- output map: 5D (C, W, H, B, plane)

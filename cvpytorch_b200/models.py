@@ -90,10 +90,11 @@ class YOLOv5CSPDarknet(_GraphCache):
 
     def emit(self, g, img_nchw_getter, H, W, name='backbone'):
         """img_nchw_getter() -> contiguous fp32 CUDA tensor [B,3,H,W] at run time.  Returns list of Val."""
-        x0 = g.new_act(H // 2, W // 2, 16)
+        # space-to-depth input in the zero-padded "row window" layout: one 128-byte K chunk = 4 adjacent s2d pixels
+        x0 = g.new_act(H // 2, W // 2 + 3, 16)
         g.fn(lambda: ops.stem_s2d(img_nchw_getter(), x0.view()))
         w, b = folded(self.stem.conv, self.stem.bn)
-        x = g.conv(x0, ops.stem_weights_to_s2d(w), b, 3, 1, 1, 'silu', name=name + '.stem')
+        x = g.conv(x0, ops.stem_weights_to_s2d(w), b, 3, 1, 1, 'silu', name=name + '.stem', w_window=4)
         outs = []
         for i in range(1, 5):
             stage = getattr(self, f'stage{i}')

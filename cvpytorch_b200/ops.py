@@ -104,6 +104,16 @@ def pack_conv_weights(w64, b64, cin_pad=None, device='cuda'):
     return packed.to(device), bias.to(device)
 
 
+def window_weights(w64, window):
+    """[O,C,kh,kw] -> [O, window*C, kh, 1]: the kw taps of a filter row laid side by side (zeros for kx >= kw), matching
+    CvbConvDesc.w_window (k = ky*window*C + kx*C + c)."""
+    O, C, kh, kw = w64.shape
+    out = torch.zeros((O, window * C, kh, 1), dtype=torch.float64)
+    for kx in range(kw):
+        out[:, kx * C:(kx + 1) * C, :, 0] = w64[:, :, :, kx]
+    return out
+
+
 def stem_weights_to_s2d(w64):
     """6x6/s2/p2 stem kernel [O,3,6,6] -> equivalent 3x3/s1/p1 kernel over the 16-channel space-to-depth input.
 
@@ -126,7 +136,7 @@ class ConvPlan:
     """Owns a CvbConvPlan handle (host-side TMA descriptors + launch shape) and keeps its tensors alive."""
 
     def __init__(self, inp, out, weights, bias, k, stride=1, pad=0, dilation=1, act=None, residual=None,
-                 up_partial=None, block_n=0, sm_limit=0, keepalive=()):
+                 up_partial=None, block_n=0, sm_limit=0, keepalive=(), w_window=0):
         d = CvbConvDesc()
         d.inp, d.out = inp, out
         d.weights = weights.data_ptr()
@@ -139,6 +149,7 @@ class ConvPlan:
         d.residual = residual if residual is not None else null_view()
         d.up_partial = up_partial if up_partial is not None else null_view()
         d.block_n, d.sm_limit = block_n, sm_limit
+        d.w_window = w_window
         self._keep = (weights, bias) + tuple(keepalive)
         self.handle = c_void_p()
         _lib.check(_lib.lib().cvb_conv_plan_create(byref(d), byref(self.handle)), 'cvb_conv_plan_create')

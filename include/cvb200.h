@@ -73,6 +73,12 @@ typedef struct CvbConvDesc {
   CvbView up_partial;   /* base == NULL -> none; fp32 [B, ceil(H/2), ceil(W/2), C]   */
   int32_t block_n;      /* 0 = auto, else 32/64/128/256                              */
   int32_t sm_limit;     /* 0 = all SMs; else cap on the persistent grid              */
+  int32_t w_window;     /* 0 = off.  n > 0 ("row window" mode for tiny cin, used by the stem): `in` describes a
+                           tensor that is physically zero-padded along W (1 column left, n-2 right: in.W =
+                           out.W + n - 1, c_pitch == C) and the GEMM K chunk of filter row ky is the n adjacent
+                           pixels starting at the output column, i.e. the packed weights are
+                           [2][cout_pad][kh * n*C] with k = ky*n*C + kx*C + c and zeros for kx >= kw.
+                           n*C must be 32 or 64. */
 } CvbConvDesc;
 
 typedef struct CvbConvPlan CvbConvPlan;
@@ -96,6 +102,8 @@ int cvb_f32nhwc_to_nchw(const CvbView* src, float* dst, void* stream);
  * Stem input adapter: NCHW fp32 [B,3,H,W] -> space-to-depth split16 [B,H/2,W/2,16] (12 used,
  * channel = (dy*2+dx)*3 + c, 4 zero pad) so that the 6x6/s2/p2 stem conv
  * (src/models/backbones/det/yolov5_csp_darknet.py:36-45) becomes a 3x3/s1/p1 tensor-core conv.
+ * dst may also be the zero-padded row-window layout [B,H/2,W/2+3,16] (data in columns 1..W/2; the pad columns must
+ * already be zero) consumed by a CvbConvDesc with w_window = 4.
  */
 int cvb_stem_s2d(const float* src, int32_t B, int32_t H, int32_t W, const CvbView* dst, void* stream);
 

@@ -129,20 +129,24 @@ def test_conv_dilated(cuda):
     assert _run_conv(64, 64, 3, 1, 2, 1, 24, 24, dil=2) < TOL
 
 
-def test_stem_s2d_equals_6x6_conv(cuda):
-    """space-to-depth + 3x3 conv == the reference's 6x6/s2/p2 stem conv (yolov5_csp_darknet.py:36-45)."""
+@pytest.mark.parametrize('window', [0, 4])
+@pytest.mark.parametrize('shape', [(2, 64, 96), (1, 128, 136), (3, 32, 40)])
+def test_stem_s2d_equals_6x6_conv(cuda, window, shape):
+    """space-to-depth + 3x3 conv == the reference's 6x6/s2/p2 stem conv (yolov5_csp_darknet.py:36-45); window=4 is the
+    zero-padded row-window layout (one 128-byte K chunk = 4 adjacent s2d pixels) the model graph uses."""
     from cvpytorch_b200 import ops
     g = torch.Generator().manual_seed(5)
-    B, H, W = 2, 64, 96
+    B, H, W = shape
     x = torch.randn(B, 3, H, W, generator=g)
     w = torch.randn(32, 3, 6, 6, generator=g) / 108 ** 0.5
     b = torch.randn(32, generator=g)
     ref = F.silu(F.conv2d(x.cuda(), w.cuda(), b.cuda(), 2, 2))
-    t = ops.SplitTensor(B, H // 2, W // 2, 16)
+    t = ops.SplitTensor(B, H // 2, W // 2 + (3 if window else 0), 16)
     ops.stem_s2d(x.cuda().contiguous(), t.view())
-    wp, bp = ops.pack_conv_weights(ops.stem_weights_to_s2d(w.double()), b.double())
+    w3 = ops.stem_weights_to_s2d(w.double())
+    wp, bp = ops.pack_conv_weights(ops.window_weights(w3, window) if window else w3, b.double())
     out = ops.SplitTensor(B, H // 2, W // 2, 32)
-    plan = ops.ConvPlan(t.view(), out.view(), wp, bp, 3, 1, 1, 1, 'silu')
+    plan = ops.ConvPlan(t.view(), out.view(), wp, bp, 3, 1, 1, 1, 'silu', w_window=window)
     plan.run()
     y = ops.split_to_nchw(out.view())
     torch.cuda.synchronize()
