@@ -191,73 +191,97 @@ __global__ void sppf_pool_kernel(const __half* __restrict__ x, int H, int W, int
 // index arithmetic is 32-bit and per row.  While the scores are in registers the CTA also builds the NMS score
 // histogram of its image in shared memory (64 KB) and flushes the non-empty bins once -- this replaces the separate
 // counting pass over the 548 MB prediction tensor and keeps the hot bins out of global atomics.
-constexpr int kDecodePix = 256;  // pixels per CTA (x na anchors rows)
+constexpr int kDecodePix = 512;      // pixels per CTA (x na anchor rows)
+constexpr int kDecodeThreads = 512;  // 16 warps
+constexpr int kDecodeRows = 4;       // rows in flight per warp (all loads issued before the first use)
 
-__global__ void __launch_bounds__(256) yolo_decode_kernel(const float* __restrict__ raw, int ny, int nx, int pitch, int na, int no,
-                                                          const float* __restrict__ anchors_px, float stride, float* __restrict__ z,
-                                                          long long z_rows, long long z_off, float* __restrict__ xperm,
-                                                          uint32_t* __restrict__ hist, float conf, int multi_label) {
+__global__ void __launch_bounds__(kDecodeThreads) yolo_decode_kernel(const float* __restrict__ raw, int ny, int nx, int pitch, int na,
+                                                                     int no, const float* __restrict__ anchors_px, float stride,
+                                                                     float* __restrict__ z, long long z_rows, long long z_off,
+                                                                     float* __restrict__ xperm, uint32_t* __restrict__ hist, float conf,
+                                                                     int multi_label) {
   extern __shared__ uint32_t s_hist[];  // [kNmsBins] when hist != nullptr
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = kDecodeThreads / 32;
   const int b = blockIdx.y;
   const int npix = ny * nx;
   const int pix0 = blockIdx.x * kDecodePix;
-  const int pix1 = min(npix, pix0 + kDecodePix);
+  const int cpix = min(npix, pix0 + kDecodePix) - pix0;
   if (hist != nullptr) {
-    for (int i = threadIdx.x; i < kNmsBins; i += blockDim.x) s_hist[i] = 0;
+    for (int i = threadIdx.x; i < kNmsBins; i += kDecodeThreads) s_hist[i] = 0;
     __syncthreads();
   }
-  const int nrows = (pix1 - pix0) * na;
-  for (int rr = warp; rr < nrows; rr += 8) {
-    const int a = rr / (pix1 - pix0);
-    const int pix = pix0 + rr - a * (pix1 - pix0);
-    const int py = pix / nx, px = pix - py * nx;
-    const float* src = raw + ((size_t)b * npix + pix) * pitch + a * no;
-    const size_t orow = (size_t)a * npix + pix;
-    float* zdst = z ? z + ((size_t)b * z_rows + z_off + orow) * no : nullptr;
-    float* xdst = xperm ? xperm + ((size_t)b * na * npix + orow) * no : nullptr;
-    float obj = 0.0f, best = -1.0f;
-    for (int c0 = 0; c0 < no; c0 += 32) {
-      const int c = c0 + lane;
-      float o = 0.0f;
-      if (c < no) {
-        const float v = __ldg(src + c);
-        if (xdst) xdst[c] = v;
-        // reference: y = x.sigmoid(); xy = (y*2 - 0.5 + grid) * stride; wh = (y*2)**2 * anchor_grid   (yolov5_detect.py:50-53)
-        const float y = 1.0f / (1.0f + expf(-v));
-        o = y;
-        if (c < 2) {
-          o = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(y, 2.0f), 0.5f), c == 0 ? (float)px : (float)py), stride);
-        } else if (c < 4) {
-          const float t2 = __fmul_rn(y, 2.0f);
-          o = __fmul_rn(__fmul_rn(t2, t2), __ldg(anchors_px + a * 2 + (c - 2)));
-        }
-        if (zdst) zdst[c] = o;
+  const int nrows = cpix * na;
+  const int nchunk = (no + 31) >> 5;  // <= 3 supported in registers (no <= 96); larger class counts loop
+  for (int r0 = warp * kDecodeRows; r0 < nrows; r0 += NW * kDecodeRows) {
+    float v[kDecodeRows][3];
+    int av[kDecodeRows], pv[kDecodeRows];
+#pragma unroll
+    for (int i = 0; i < kDecodeRows; ++i) {
+      const int rr = min(r0 + i, nrows - 1);
+      const int a = rr / cpix;
+      const int pix = pix0 + rr - a * cpix;
+      av[i] = a;
+      pv[i] = pix;
+      const float* src = raw + ((size_t)b * npix + pix) * pitch + a * no;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int c = k * 32 + lane;
+        v[i][k] = (k < nchunk && c < no) ? __ldg(src + c) : 0.0f;
       }
-      if (hist != nullptr) {
-        if (c0 == 0) obj = __shfl_sync(0xffffffffu, o, 4);
-        if (obj > conf && c >= 5 && c < no) {
-          const float sc = __fmul_rn(o, obj);  // same fp32 product the NMS kernels recompute from z (yolov5.py:106)
-          if (multi_label) {
-            if (sc > conf) atomicAdd(&s_hist[min(__float_as_uint(sc) >> 17, (uint32_t)(kNmsBins - 1))], 1u);
-          } else {
-            best = fmaxf(best, sc);
+    }
+#pragma unroll
+    for (int i = 0; i < kDecodeRows; ++i) {
+      if (r0 + i >= nrows) break;
+      const int a = av[i], pix = pv[i];
+      const int py = pix / nx, px = pix - py * nx;
+      const size_t orow = (size_t)a * npix + pix;
+      float* zdst = z ? z + ((size_t)b * z_rows + z_off + orow) * no : nullptr;
+      float* xdst = xperm ? xperm + ((size_t)b * na * npix + orow) * no : nullptr;
+      float obj = 0.0f, best = -1.0f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int c = k * 32 + lane;
+        float o = 0.0f;
+        if (k < nchunk && c < no) {
+          const float x = v[i][k];
+          if (xdst) xdst[c] = x;
+          // reference: y = x.sigmoid(); xy = (y*2 - 0.5 + grid) * stride; wh = (y*2)**2 * anchor_grid   (yolov5_detect.py:50-53)
+          const float y = 1.0f / (1.0f + expf(-x));
+          o = y;
+          if (c < 2) {
+            o = __fmul_rn(__fadd_rn(__fsub_rn(__fmul_rn(y, 2.0f), 0.5f), c == 0 ? (float)px : (float)py), stride);
+          } else if (c < 4) {
+            const float t2 = __fmul_rn(y, 2.0f);
+            o = __fmul_rn(__fmul_rn(t2, t2), __ldg(anchors_px + a * 2 + (c - 2)));
+          }
+          if (zdst) zdst[c] = o;
+        }
+        if (hist != nullptr) {
+          if (k == 0) obj = __shfl_sync(0xffffffffu, o, 4);
+          if (obj > conf && c >= 5 && c < no && k < nchunk) {
+            const float sc = __fmul_rn(o, obj);  // same fp32 product the NMS kernels recompute from z (yolov5.py:106)
+            if (multi_label) {
+              if (sc > conf) atomicAdd(&s_hist[min(__float_as_uint(sc) >> 17, (uint32_t)(kNmsBins - 1))], 1u);
+            } else {
+              best = fmaxf(best, sc);
+            }
           }
         }
       }
-    }
-    if (hist != nullptr && !multi_label && obj > conf) {
+      if (hist != nullptr && !multi_label && obj > conf) {
 #pragma unroll
-      for (int o2 = 16; o2 > 0; o2 >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o2));
-      if (lane == 0 && best > conf) atomicAdd(&s_hist[min(__float_as_uint(best) >> 17, (uint32_t)(kNmsBins - 1))], 1u);
+        for (int o2 = 16; o2 > 0; o2 >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o2));
+        if (lane == 0 && best > conf) atomicAdd(&s_hist[min(__float_as_uint(best) >> 17, (uint32_t)(kNmsBins - 1))], 1u);
+      }
     }
   }
   if (hist != nullptr) {
     __syncthreads();
     uint32_t* gh = hist + (size_t)b * kNmsBins;
-    for (int i = threadIdx.x; i < kNmsBins; i += blockDim.x) {
-      const uint32_t v = s_hist[i];
-      if (v) atomicAdd(&gh[i], v);
+    for (int i = threadIdx.x; i < kNmsBins; i += kDecodeThreads) {
+      const uint32_t c = s_hist[i];
+      if (c) atomicAdd(&gh[i], c);
     }
   }
 }
@@ -369,7 +393,8 @@ extern "C" int cvb_yolo_decode(const CvbView* raw, int32_t na, int32_t no, const
     attr_set = true;
   }
   dim3 grid(ceil_div(raw->H * raw->W, kDecodePix), raw->B);
-  yolo_decode_kernel<<<grid, 256, smem, as_stream(stream)>>>(static_cast<const float*>(raw->base), raw->H, raw->W, raw->c_pitch, na, no,
+  CVB_REQUIRE(no <= 96, "yolo_decode: at most 91 classes supported (no=%d)", no);
+  yolo_decode_kernel<<<grid, kDecodeThreads, smem, as_stream(stream)>>>(static_cast<const float*>(raw->base), raw->H, raw->W, raw->c_pitch, na, no,
                                                             anchors_px, stride, z, z_rows, z_off, xperm,
                                                             static_cast<uint32_t*>(nms_workspace), conf_thres, multi_label);
   CVB_CHECK_CUDA(cudaGetLastError());

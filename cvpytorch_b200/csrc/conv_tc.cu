@@ -51,6 +51,8 @@ struct alignas(64) ConvKArgs {
   uint32_t a_box_bytes;
   uint32_t a_lo_off;   // smem offset of the lo plane of A inside a stage (== a_box_bytes when hi+lo arrive in ONE TMA box)
   int a_fused;         // 1: one 5D box {K, TW, TH, NB, 2 planes} per stage instead of two
+  int b_resident;      // 1: the whole weight slab of this CTA's n-tile stays in smem; the ring streams A only
+  int out_bufs;        // 1 or 2 output staging tiles (2: the TMA store of group g overlaps the conversion of g+1)
   int8_t tap_map[kMaxTaps];
   int8_t tap_dh[kMaxTaps];
   int8_t tap_dw[kMaxTaps];
@@ -119,15 +121,18 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int STAGES = a.stages;
+  const int stage_bytes = a.b_resident ? 2 * A_BYTES : STAGE_BYTES;
   uint8_t* stage_base = smem;
-  uint8_t* out_stage = smem + STAGES * STAGE_BYTES;
-  float* bias_s = reinterpret_cast<float*>(out_stage + Cfg::OUT_STAGE_BYTES);
+  uint8_t* b_res = smem + STAGES * stage_bytes;                                  // resident weights: k_iters x {hi, lo} tiles
+  uint8_t* out_stage0 = b_res + (a.b_resident ? a.taps * a.chunks * 2 * B_BYTES : 0);
+  float* bias_s = reinterpret_cast<float*>(out_stage0 + a.out_bufs * Cfg::OUT_STAGE_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + BLOCK_N);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* bfull = tempty + 2;  // resident weights have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -147,6 +152,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         mbar_init(&tfull[s], 1);
         mbar_init(&tempty[s], kEpiThreads / 32);
       }
+      mbar_init(bfull, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -161,13 +167,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   const int m_tiles = a.tiles_w * a.tiles_h * a.tiles_b;
   const int total_tiles = m_tiles * a.tiles_n;
   const int k_iters = a.taps * a.chunks;
+  // Tile order: tile = mt * tiles_n + nt.  Every CTA strides by gridDim.x; in resident mode gridDim.x is a multiple of
+  // tiles_n, so nt = tile % tiles_n is the same for all tiles of a CTA and its weight slab is loaded exactly once.
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t tx_bytes = 2 * a.a_box_bytes + 2 * B_BYTES;
+      const uint32_t tx_bytes = 2 * a.a_box_bytes + (a.b_resident ? 0 : 2 * B_BYTES);
+      if (a.b_resident && (int)blockIdx.x < total_tiles) {
+        const int n0r = ((int)blockIdx.x % a.tiles_n) * BLOCK_N;
+        mbar_expect_tx(bfull, (uint32_t)(k_iters * 2 * B_BYTES));
+        for (int it = 0; it < k_iters; ++it) {
+          const int tap = it / a.chunks, ck = it - tap * a.chunks;
+          tma_load_3d(&a.tmB, bfull, b_res + it * 2 * B_BYTES, tap * a.cin + ck * BLOCK_K, n0r, 0);
+        }
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % a.tiles_n;
         const int mt = tile / a.tiles_n;
@@ -183,11 +199,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
           for (int ck = 0; ck < a.chunks; ++ck) {
             mbar_wait(&empty[stage], phase ^ 1, 100 + stage);
             mbar_expect_tx(&full[stage], tx_bytes);
-            uint8_t* sb = stage_base + stage * STAGE_BYTES;
+            uint8_t* sb = stage_base + stage * stage_bytes;
             tma_load_5d(mapA, &full[stage], sb, ck * BLOCK_K, cw, ch, b0, 0);  // fused: both planes in one box
             if (!a.a_fused) tma_load_5d(mapA, &full[stage], sb + A_BYTES, ck * BLOCK_K, cw, ch, b0, 1);
-            const int kc = tap * a.cin + ck * BLOCK_K;
-            tma_load_3d(&a.tmB, &full[stage], sb + 2 * A_BYTES, kc, n0, 0);    // box {K, N, 2 planes}: hi then lo
+            if (!a.b_resident) {
+              const int kc = tap * a.cin + ck * BLOCK_K;
+              tma_load_3d(&a.tmB, &full[stage], sb + 2 * A_BYTES, kc, n0, 0);  // box {K, N, 2 planes}: hi then lo
+            }
             if (++stage == STAGES) {
               stage = 0;
               phase ^= 1;
@@ -205,6 +223,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       uint32_t acc_phase = 0;
       const int n_main = a.n_main;
       const uint32_t set_cols = (uint32_t)((n_main + 1) * BLOCK_N);
+      if (a.b_resident && (int)blockIdx.x < total_tiles) mbar_wait(bfull, 0, 250);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(&tempty[acc], acc_phase ^ 1, 200 + acc);
         tc_fence_after();
@@ -217,11 +236,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         for (int it = 0; it < k_iters; ++it) {
           mbar_wait(&full[stage], phase, 300 + stage);
           tc_fence_after();
-          const uint32_t sa = smem_u32(stage_base + stage * STAGE_BYTES);
+          const uint32_t sa = smem_u32(stage_base + stage * stage_bytes);
+          const uint32_t sbw = a.b_resident ? smem_u32(b_res + it * 2 * B_BYTES) : sa + 2 * A_BYTES;
           const uint64_t dah = make_kmajor_desc<SWZ>(sa);
           const uint64_t dal = make_kmajor_desc<SWZ>(sa + a.a_lo_off);
-          const uint64_t dbh = make_kmajor_desc<SWZ>(sa + 2 * A_BYTES);
-          const uint64_t dbl = make_kmajor_desc<SWZ>(sa + 2 * A_BYTES + B_BYTES);
+          const uint64_t dbh = make_kmajor_desc<SWZ>(sbw);
+          const uint64_t dbl = make_kmajor_desc<SWZ>(sbw + B_BYTES);
           const uint32_t d_main = d_base + (uint32_t)(r * BLOCK_N);
           const bool first_main = it < n_main;
 #pragma unroll
@@ -261,6 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     int acc = 0;
     uint32_t acc_phase = 0;
     int cur_n0 = -1;
+    uint32_t gcount = 0;
     const int n_main = a.n_main;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % a.tiles_n;
@@ -291,8 +312,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
 #pragma unroll 1
       for (int g = 0; g < BLOCK_N / OUT_GROUP_CH; ++g) {
-        if (tid_e == 0) tma_store_wait_read0();  // previous TMA store has finished reading the staging tile
+        // the staging tile written now was last read by the TMA store issued out_bufs groups ago
+        if (tid_e == 0) {
+          if (a.out_bufs == 2) tma_store_wait_read1();
+          else tma_store_wait_read0();
+        }
         named_bar_sync(1, kEpiThreads);
+        uint8_t* out_stage = out_stage0 + (gcount & (a.out_bufs - 1)) * Cfg::OUT_STAGE_BYTES;
+        ++gcount;
         const int col = g * OUT_GROUP_CH + half * CW;
         float f[CW];
         {
@@ -673,12 +700,34 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
     a.up_H = u.H;
     a.up_W = u.W;
   }
-  // ---- pipeline depth and launch shape
-  const int fixed = 1024 + ke.out_stage_bytes + ke.tail_bytes;
-  int stages = (kSmemBudget - fixed) / ke.stage_bytes;
-  if (stages > 8) stages = 8;
+  // ---- shared-memory plan: ring depth, resident weights, output staging
   const int k_iters = a.taps * a.chunks;
-  if (stages > 2 * k_iters && 2 * k_iters >= 2) stages = 2 * k_iters;  // never need more than two tiles worth
+  const int a_stage = 2 * kTileM * bk * 2;   // hi + lo activation tiles of one K chunk
+  const int b_stage = 2 * bn * bk * 2;       // hi + lo weight tiles of one K chunk
+  const int base = 1024 + ke.tail_bytes;
+  int stages = 0;
+  a.b_resident = 0;
+  a.out_bufs = 1;
+  const bool can_pin_n = (a.tiles_n == 1 || a.tiles_n == 2 || a.tiles_n == 4);
+  if (!d->no_resident && can_pin_n && (long long)k_iters * b_stage <= 65536) {
+    // small weight slab: keep it in smem for the whole kernel, stream only activations, double-buffer the output tile
+    const int st = (kSmemBudget - base - k_iters * b_stage - 2 * ke.out_stage_bytes) / a_stage;
+    if (st >= 3) {
+      stages = st;
+      a.b_resident = 1;
+      a.out_bufs = 2;
+    }
+  }
+  if (stages == 0) {
+    const int st2 = (kSmemBudget - base - 2 * ke.out_stage_bytes) / (a_stage + b_stage);
+    if (st2 >= 3) {
+      stages = st2;
+      a.out_bufs = 2;
+    } else {
+      stages = (kSmemBudget - base - ke.out_stage_bytes) / (a_stage + b_stage);
+    }
+  }
+  if (stages > 8) stages = 8;
   if (stages < 2) {
     delete p;
     return set_error(CVB_ERR_INVALID, "conv: tile does not fit in shared memory (block_n=%d block_k=%d)", bn, bk);
@@ -697,7 +746,7 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
     a.n_main = n_main;
     a.nbuf = (2 * (n_main + 1) * bn <= 512) ? 2 : 1;
   }
-  p->smem = fixed + stages * ke.stage_bytes;
+  p->smem = base + stages * (a_stage + (a.b_resident ? 0 : b_stage)) + (a.b_resident ? k_iters * b_stage : 0) + a.out_bufs * ke.out_stage_bytes;
   p->fn = ke.fn;
 
   static std::mutex mu;
@@ -723,6 +772,10 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   int sms = g_num_sms;
   if (d->sm_limit > 0 && d->sm_limit < sms) sms = d->sm_limit;
   p->grid = (int)(total < sms ? total : sms);
+  if (a.b_resident && a.tiles_n > 1) {
+    p->grid -= p->grid % a.tiles_n;  // every CTA keeps one n-tile (tile % tiles_n constant along its stride)
+    if (p->grid < a.tiles_n) p->grid = a.tiles_n;
+  }
   *out_plan = p;
   return CVB_OK;
 }

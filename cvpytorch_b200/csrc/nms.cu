@@ -73,67 +73,124 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const float* __r
     __syncthreads();
   }
   const uint32_t tb = EMIT ? ws.tbin[b] : 0u;
-  for (int anchor = row0 + warp; anchor < row1; anchor += kScanThreads / 32) {
-    const float* r = pred + ((size_t)b * A + anchor) * no;
-    const float obj = __ldg(r + 4);
-    if (!(obj > conf)) continue;
-    if (multi_label) {
-      for (int c0 = 0; c0 < nc; c0 += 32) {
-        const int c = c0 + lane;
-        bool pass = false;
-        uint32_t bits = 0;
-        if (c < nc) {
-          const float s = __fmul_rn(__ldg(r + 5 + c), obj);
-          if (s > conf) {
-            bits = __float_as_uint(s);
-            const uint32_t bin = score_bin(bits);
-            if (EMIT) pass = bin >= tb;
-            else atomicAdd(&ws.hist[(size_t)b * kBins + bin], 1u);
-          }
+  constexpr int R = 4;  // rows in flight per warp: all loads of a batch are issued before the first use
+  for (int base = row0 + warp * R; base < row1; base += (kScanThreads / 32) * R) {
+    float obj[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int anchor = min(base + i, row1 - 1);
+      obj[i] = __ldg(pred + ((size_t)b * A + anchor) * no + 4);
+    }
+    if (multi_label && nc <= 96) {
+      float v[R][3];
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const int anchor = min(base + i, row1 - 1);
+        const float* r = pred + ((size_t)b * A + anchor) * no + 5;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int c = k * 32 + lane;
+          v[i][k] = (obj[i] > conf && c < nc) ? __ldg(r + c) : 0.0f;
         }
-        if (EMIT) {
-          const uint32_t m = __ballot_sync(0xffffffffu, pass);
-          if (m) {
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&s_cnt, (uint32_t)__popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (pass) {
-              const uint32_t id = (uint32_t)anchor * (uint32_t)nc + (uint32_t)c;
-              stage[base + __popc(m & ((1u << lane) - 1))] = ((uint64_t)bits << 32) | (uint64_t)(0xFFFFFFFFu - id);
+      }
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const int anchor = base + i;
+        if (anchor >= row1 || !(obj[i] > conf)) continue;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const int c = k * 32 + lane;
+          if (k * 32 >= nc) break;
+          bool pass = false;
+          uint32_t bits = 0;
+          if (c < nc) {
+            const float sc = __fmul_rn(v[i][k], obj[i]);
+            if (sc > conf) {
+              bits = __float_as_uint(sc);
+              const uint32_t bin = score_bin(bits);
+              if (EMIT) pass = bin >= tb;
+              else atomicAdd(&ws.hist[(size_t)b * kBins + bin], 1u);
+            }
+          }
+          if (EMIT) {
+            const uint32_t m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+              uint32_t sb = 0;
+              if (lane == 0) sb = atomicAdd(&s_cnt, (uint32_t)__popc(m));
+              sb = __shfl_sync(0xffffffffu, sb, 0);
+              if (pass) {
+                const uint32_t id = (uint32_t)anchor * (uint32_t)nc + (uint32_t)c;
+                stage[sb + __popc(m & ((1u << lane) - 1))] = ((uint64_t)bits << 32) | (uint64_t)(0xFFFFFFFFu - id);
+              }
             }
           }
         }
       }
-    } else {
-      // best class only: conf, j = x[:, 5:].max(1)  (first maximum wins ties)
-      float best = -1.0f;
-      int bi = 0x7fffffff;
-      for (int c = lane; c < nc; c += 32) {
-        const float s = __fmul_rn(__ldg(r + 5 + c), obj);
-        if (s > best) {
-          best = s;
-          bi = c;
-        }
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ob > best || (ob == best && oi < bi)) {
-          best = ob;
-          bi = oi;
-        }
-      }
-      if (lane == 0 && best > conf) {
-        const uint32_t bits = __float_as_uint(best);
-        const uint32_t bin = score_bin(bits);
-        if (EMIT) {
-          if (bin >= tb) {
-            const uint32_t id = (uint32_t)anchor * (uint32_t)nc + (uint32_t)bi;
-            stage[atomicAdd(&s_cnt, 1u)] = ((uint64_t)bits << 32) | (uint64_t)(0xFFFFFFFFu - id);
+      continue;
+    }
+    for (int i = 0; i < R; ++i) {
+      const int anchor = base + i;
+      if (anchor >= row1 || !(obj[i] > conf)) continue;
+      const float* r = pred + ((size_t)b * A + anchor) * no;
+      const float ob = obj[i];
+      if (multi_label) {
+        for (int c0 = 0; c0 < nc; c0 += 32) {
+          const int c = c0 + lane;
+          bool pass = false;
+          uint32_t bits = 0;
+          if (c < nc) {
+            const float sc = __fmul_rn(__ldg(r + 5 + c), ob);
+            if (sc > conf) {
+              bits = __float_as_uint(sc);
+              const uint32_t bin = score_bin(bits);
+              if (EMIT) pass = bin >= tb;
+              else atomicAdd(&ws.hist[(size_t)b * kBins + bin], 1u);
+            }
           }
-        } else {
-          atomicAdd(&ws.hist[(size_t)b * kBins + bin], 1u);
+          if (EMIT) {
+            const uint32_t m = __ballot_sync(0xffffffffu, pass);
+            if (m) {
+              uint32_t sb = 0;
+              if (lane == 0) sb = atomicAdd(&s_cnt, (uint32_t)__popc(m));
+              sb = __shfl_sync(0xffffffffu, sb, 0);
+              if (pass) {
+                const uint32_t id = (uint32_t)anchor * (uint32_t)nc + (uint32_t)c;
+                stage[sb + __popc(m & ((1u << lane) - 1))] = ((uint64_t)bits << 32) | (uint64_t)(0xFFFFFFFFu - id);
+              }
+            }
+          }
+        }
+      } else {
+        // best class only: conf, j = x[:, 5:].max(1)  (first maximum wins ties)
+        float best = -1.0f;
+        int bi = 0x7fffffff;
+        for (int c = lane; c < nc; c += 32) {
+          const float sc = __fmul_rn(__ldg(r + 5 + c), ob);
+          if (sc > best) {
+            best = sc;
+            bi = c;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob2 = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ob2 > best || (ob2 == best && oi < bi)) {
+            best = ob2;
+            bi = oi;
+          }
+        }
+        if (lane == 0 && best > conf) {
+          const uint32_t bits = __float_as_uint(best);
+          const uint32_t bin = score_bin(bits);
+          if (EMIT) {
+            if (bin >= tb) {
+              const uint32_t id = (uint32_t)anchor * (uint32_t)nc + (uint32_t)bi;
+              stage[atomicAdd(&s_cnt, 1u)] = ((uint64_t)bits << 32) | (uint64_t)(0xFFFFFFFFu - id);
+            }
+          } else {
+            atomicAdd(&ws.hist[(size_t)b * kBins + bin], 1u);
+          }
         }
       }
     }

@@ -73,6 +73,7 @@ typedef struct CvbConvDesc {
   CvbView up_partial;   /* base == NULL -> none; fp32 [B, ceil(H/2), ceil(W/2), C]   */
   int32_t block_n;      /* 0 = auto, else 32/64/128/256                              */
   int32_t sm_limit;     /* 0 = all SMs; else cap on the persistent grid              */
+  int32_t no_resident;  /* 1 = never pin the weights in shared memory (tuning / testing)  */
   int32_t w_window;     /* 0 = off.  n > 0 ("row window" mode for tiny cin, used by the stem): `in` describes a
                            tensor that is physically zero-padded along W (1 column left, n-2 right: in.W =
                            out.W + n - 1, c_pitch == C) and the GEMM K chunk of filter row ky is the n adjacent

@@ -14,7 +14,7 @@ def _rel(a, b):
     return float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-12))
 
 
-def _run_conv(cin, cout, k, s, p, B, H, W, act='silu', residual=False, up=False, f32_out=False, block_n=0, seed=0, dil=1):
+def _run_conv(cin, cout, k, s, p, B, H, W, act='silu', residual=False, up=False, f32_out=False, block_n=0, seed=0, dil=1, no_resident=0):
     from cvpytorch_b200 import ops
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(B, cin, H, W, generator=g)
@@ -47,7 +47,7 @@ def _run_conv(cin, cout, k, s, p, B, H, W, act='silu', residual=False, up=False,
         ref = ref + r.cuda()
     plan = ops.ConvPlan(tin.view(), tout.view(0, cout), wp, bp, k, s, p, dil, act,
                         residual=res_t.view() if res_t else None, up_partial=up_t.view() if up_t else None,
-                        block_n=block_n)
+                        block_n=block_n, no_resident=no_resident)
     plan.run()
     out = ops.f32nhwc_to_nchw(tout.view(0, cout)) if f32_out else ops.split_to_nchw(tout.view(0, cout))
     torch.cuda.synchronize()
@@ -123,6 +123,17 @@ def test_conv_many_tiles_persistent(cuda):
     assert _run_conv(64, 64, 1, 1, 0, 8, 80, 80) < TOL
     assert _run_conv(64, 64, 3, 1, 1, 8, 80, 80) < TOL
     assert _run_conv(128, 256, 3, 2, 1, 8, 80, 80) < TOL
+
+
+def test_conv_resident_weights_vs_streamed(cuda):
+    """small weight slabs stay resident in smem (ring streams activations only); both modes must agree with the reference,
+    including the pinned-n-tile case (tiles_n = 2 / 4) and many tiles per CTA."""
+    for cfg in [(64, 64, 1, 1, 0, 8, 80, 80), (128, 128, 1, 1, 0, 4, 80, 80), (64, 256, 1, 1, 0, 4, 40, 40), (32, 32, 3, 1, 1, 2, 64, 64),
+                (64, 255, 1, 1, 0, 2, 40, 40)]:
+        for nr in (0, 1):
+            f32 = cfg[1] == 255
+            assert _run_conv(*cfg, no_resident=nr, f32_out=f32, act=None if f32 else 'silu') < TOL, (cfg, nr)
+    assert _run_conv(64, 256, 1, 1, 0, 4, 40, 40, block_n=64) < TOL  # tiles_n = 4, weights pinned per CTA
 
 
 def test_conv_dilated(cuda):
