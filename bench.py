@@ -86,15 +86,50 @@ def synthetic_frames(batch, seed=1029):
     return torch.randn(batch, 3, 640, 640)
 
 
+def usable_cores():
+    """Host threads this process may really use: affinity mask, capped by the cgroup CPU quota if one is set."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    for path in ('/sys/fs/cgroup/cpu.max', '/sys/fs/cgroup/cpu/cpu.cfs_quota_us'):
+        try:
+            txt = open(path).read().split()
+            if path.endswith('cpu.max'):
+                if txt[0] != 'max':
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]))))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    n = min(n, max(1, q // int(open('/sys/fs/cgroup/cpu/cpu.cfs_period_us').read())))
+        except Exception:
+            pass
+    return max(1, n)
+
+
+def pick_cpu_threads(probe):
+    """All the host threads the CPU arm can use *productively*: oversubscribed intra-op pools are slower than fewer
+    threads, so time a small probe at n, n/2, n/4, ... and keep the fastest (reported as `cores`)."""
+    n = usable_cores()
+    cands = sorted({max(1, n >> k) for k in range(0, 4)} | {min(n, 32), min(n, 16)}, reverse=True)
+    best, best_t = cands[0], float('inf')
+    for c in cands:
+        torch.set_num_threads(c)
+        probe()
+        t0 = time.perf_counter()
+        probe()
+        dt = time.perf_counter() - t0
+        if dt < best_t * 0.95:
+            best, best_t = c, dt
+    return best
+
+
 def cpu_reference_throughput(steps, warmup, batch=8):
     """The reference's algorithm (oracle port: torch CPU fp32 conv/BN/SiLU graph + numpy NMS) on all host cores."""
     from cvpytorch_b200 import synth
     from oracle import nms_oracle as NO
     from oracle import yolov5_oracle as YO
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     sd = synth.yolov5s_state_dict(True)
     x = synthetic_frames(batch)
+    cores = pick_cpu_threads(lambda: YO.forward(x[:2], sd))
+    torch.set_num_threads(cores)
 
     def step():
         z, _ = YO.forward(x, sd)
@@ -285,7 +320,7 @@ def run_b200_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=64, help='images per GPU per step (BASELINE: 64)')

@@ -306,12 +306,36 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       const __half* res_row = nullptr;
       if (a.resid != nullptr && valid) res_row = a.resid + ((size_t)((size_t)ob * a.Ho + oh) * a.Wo + ow) * a.resid_pitch + n0;
 
-      mbar_wait(&tfull[acc], acc_phase, 400 + acc);
-      tc_fence_after();
       const uint32_t t_set = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (n_main + 1) * BLOCK_N);
 
 #pragma unroll 1
       for (int g = 0; g < BLOCK_N / OUT_GROUP_CH; ++g) {
+        const int col = g * OUT_GROUP_CH + half * CW;
+        const bool ch_ok = (n0 + col + CW <= a.cout);
+        // epilogue operands that do not depend on the accumulator are requested first, so their latency hides behind
+        // the accumulator wait / barrier / tcgen05.ld below
+        float4 upv[CW / 4];
+        uint4 rhv[CW / 8], rlv[CW / 8];
+        const bool has_up = (up_row != nullptr) && ch_ok;
+        const bool has_res = (res_row != nullptr) && ch_ok;
+        if (has_up) {
+          const float4* p = reinterpret_cast<const float4*>(up_row + col);
+#pragma unroll
+          for (int j = 0; j < CW / 4; ++j) upv[j] = __ldg(p + j);
+        }
+        if (has_res) {
+          const uint4* ph = reinterpret_cast<const uint4*>(res_row + col);
+          const uint4* pl = reinterpret_cast<const uint4*>(res_row + a.resid_plane + col);
+#pragma unroll
+          for (int j = 0; j < CW / 8; ++j) {
+            rhv[j] = __ldg(ph + j);
+            rlv[j] = __ldg(pl + j);
+          }
+        }
+        if (g == 0) {
+          mbar_wait(&tfull[acc], acc_phase, 400 + acc);
+          tc_fence_after();
+        }
         // the staging tile written now was last read by the TMA store issued out_bufs groups ago
         if (tid_e == 0) {
           if (a.out_bufs == 2) tma_store_wait_read1();
@@ -320,7 +344,6 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         named_bar_sync(1, kEpiThreads);
         uint8_t* out_stage = out_stage0 + (gcount & (a.out_bufs - 1)) * Cfg::OUT_STAGE_BYTES;
         ++gcount;
-        const int col = g * OUT_GROUP_CH + half * CW;
         float f[CW];
         {
           uint32_t v[CW];
@@ -335,16 +358,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int j = 0; j < CW; ++j) f[j] = __fadd_rn(f[j], __uint_as_float(v[j]));
           }
         }
-        const bool ch_ok = (n0 + col + CW <= a.cout);
-        if (up_row != nullptr && ch_ok) {
-          const float4* p = reinterpret_cast<const float4*>(up_row + col);
+        if (has_up) {
 #pragma unroll
           for (int j = 0; j < CW / 4; ++j) {
-            const float4 u = __ldg(p + j);
-            f[4 * j + 0] += u.x;
-            f[4 * j + 1] += u.y;
-            f[4 * j + 2] += u.z;
-            f[4 * j + 3] += u.w;
+            f[4 * j + 0] += upv[j].x;
+            f[4 * j + 1] += upv[j].y;
+            f[4 * j + 2] += upv[j].z;
+            f[4 * j + 3] += upv[j].w;
           }
         }
         if (a.act == CVB_ACT_SILU) {
@@ -357,15 +377,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
           for (int j = 0; j < CW; ++j) f[j] = f[j] + bias_s[col + j];
         }
-        if (res_row != nullptr && ch_ok) {
-          const uint4* ph = reinterpret_cast<const uint4*>(res_row + col);
-          const uint4* pl = reinterpret_cast<const uint4*>(res_row + a.resid_plane + col);
+        if (has_res) {
 #pragma unroll
           for (int j = 0; j < CW / 8; ++j) {
-            const uint4 hv = __ldg(ph + j);
-            const uint4 lv = __ldg(pl + j);
-            const __half2* h2 = reinterpret_cast<const __half2*>(&hv);
-            const __half2* l2 = reinterpret_cast<const __half2*>(&lv);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&rhv[j]);
+            const __half2* l2 = reinterpret_cast<const __half2*>(&rlv[j]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 hf = __half22float2(h2[e]);
