@@ -86,5 +86,5 @@ def test_decode_matches_reference_formula(cuda):
     ref = y.view(B, -1, no)
     got = z[:, 5:].cpu()
     err = float((got - ref).abs().max() / ref.abs().max())
-    assert err < 1e-6, err
+    assert err < 5e-6, err  # sigmoid = ex2.approx + rcp.approx (|rel err| ~ 2^-22)
     assert float(z[:, :5].abs().max()) == 0.0
