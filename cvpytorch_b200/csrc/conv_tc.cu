@@ -52,6 +52,7 @@ struct alignas(64) ConvKArgs {
   uint32_t a_lo_off;   // smem offset of the lo plane of A inside a stage (== a_box_bytes when hi+lo arrive in ONE TMA box)
   int a_fused;         // 1: one 5D box {K, TW, TH, NB, 2 planes} per stage instead of two
   int b_resident;      // 1: the whole weight slab of this CTA's n-tile stays in smem; the ring streams A only
+  int resid_first;     // 1: out = act(conv + bias + residual) (ResNet bottleneck); 0: out = act(conv + bias) + residual (Darknet)
   int out_bufs;        // 1 or 2 output staging tiles (2: the TMA store of group g overlaps the conversion of g+1)
   int8_t tap_map[kMaxTaps];
   int8_t tap_dh[kMaxTaps];
@@ -367,16 +368,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             f[4 * j + 3] += upv[j].w;
           }
         }
-        if (a.act == CVB_ACT_SILU) {
+        float rsum[CW];  // residual (hi + lo) of this thread's pixel, 0 when absent
 #pragma unroll
-          for (int j = 0; j < CW; ++j) f[j] = silu_fast(f[j] + bias_s[col + j]);
-        } else if (a.act == CVB_ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < CW; ++j) f[j] = fmaxf(f[j] + bias_s[col + j], 0.0f);
-        } else {
-#pragma unroll
-          for (int j = 0; j < CW; ++j) f[j] = f[j] + bias_s[col + j];
-        }
+        for (int j = 0; j < CW; ++j) rsum[j] = 0.0f;
         if (has_res) {
 #pragma unroll
           for (int j = 0; j < CW / 8; ++j) {
@@ -386,10 +380,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             for (int e = 0; e < 4; ++e) {
               const float2 hf = __half22float2(h2[e]);
               const float2 lf = __half22float2(l2[e]);
-              f[8 * j + 2 * e + 0] += hf.x + lf.x;
-              f[8 * j + 2 * e + 1] += hf.y + lf.y;
+              rsum[8 * j + 2 * e + 0] = hf.x + lf.x;
+              rsum[8 * j + 2 * e + 1] = hf.y + lf.y;
             }
           }
+        }
+        const bool rf = a.resid_first != 0;
+        if (a.act == CVB_ACT_SILU) {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            const float t = f[j] + bias_s[col + j];
+            f[j] = rf ? silu_fast(t + rsum[j]) : silu_fast(t) + rsum[j];
+          }
+        } else if (a.act == CVB_ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) {
+            const float t = f[j] + bias_s[col + j];
+            f[j] = rf ? fmaxf(t + rsum[j], 0.0f) : fmaxf(t, 0.0f) + rsum[j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < CW; ++j) f[j] = f[j] + bias_s[col + j] + rsum[j];
         }
         if constexpr (OUT_F32) {
           // row = 32 fp32 = 128 B = 8 chunks of 16 B, 128B swizzle: chunk ^= row & 7; this warp owns chunks half*4 .. +3
@@ -703,6 +714,7 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
     a.resid = static_cast<const __half*>(r.base);
     a.resid_plane = r.plane_stride / 2;
     a.resid_pitch = r.c_pitch;
+    a.resid_first = d->residual_before_act ? 1 : 0;
   }
   if (d->up_partial.base) {
     const CvbView& u = d->up_partial;

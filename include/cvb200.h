@@ -51,7 +51,9 @@ typedef struct CvbView {
 
 /*
  * Fused conv2d + folded-BN bias + activation (+ residual) (+ nearest-upsampled fp32 partial).
- *   out = act( conv(in, W) + up2x(partial) + bias ) + residual
+ *   out = act( conv(in, W) + up2x(partial) + bias ) + residual          (residual_before_act = 0, Darknet bottleneck)
+ *   out = act( conv(in, W) + up2x(partial) + bias + residual )          (residual_before_act = 1, ResNet bottleneck:
+ *                                                                        torchvision Bottleneck.forward `out += identity; relu`)
  * replaces: ConvModule.forward  src/models/bricks/conv_module.py:201-214 (conv -> BN -> act),
  *           Conv.forward        src/models/modules/yolo11_modules.py:27-39,
  *           the shortcut add of DarknetBottleneck.forward src/models/modules/yolo_modules.py:95-104,
@@ -74,6 +76,7 @@ typedef struct CvbConvDesc {
   int32_t block_n;      /* 0 = auto, else 32/64/128/256                              */
   int32_t sm_limit;     /* 0 = all SMs; else cap on the persistent grid              */
   int32_t no_resident;  /* 1 = never pin the weights in shared memory (tuning / testing)  */
+  int32_t residual_before_act; /* see formula above */
   int32_t w_window;     /* 0 = off.  n > 0 ("row window" mode for tiny cin, used by the stem): `in` describes a
                            tensor that is physically zero-padded along W (1 column left, n-2 right: in.W =
                            out.W + n - 1, c_pitch == C) and the GEMM K chunk of filter row ky is the n adjacent
