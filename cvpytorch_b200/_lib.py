@@ -42,7 +42,12 @@ SYMBOLS = {
     'cvb_nchw_to_split': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, POINTER(CvbView), c_void_p]),
     'cvb_split_to_nchw': (c_int32, [POINTER(CvbView), c_void_p, c_void_p]),
     'cvb_f32nhwc_to_nchw': (c_int32, [POINTER(CvbView), c_void_p, c_void_p]),
-    'cvb_stem_s2d': (c_int32, [c_void_p, c_int32, c_int32, c_int32, POINTER(CvbView), c_void_p]),
+    'cvb_stem_s2d': (c_int32, [c_void_p, c_int32, c_int32, c_int32, POINTER(CvbView), c_int32, c_void_p]),
+    'cvb_maxpool3x3s2': (c_int32, [POINTER(CvbView), POINTER(CvbView), c_void_p]),
+    'cvb_split_to_f32nhwc': (c_int32, [POINTER(CvbView), POINTER(CvbView), c_void_p]),
+    'cvb_groupnorm_workspace_bytes': (c_size_t, [c_int32, c_int32]),
+    'cvb_groupnorm_relu': (c_int32, [POINTER(CvbView), c_int32, c_void_p, c_void_p, c_float, c_int32, POINTER(CvbView), c_void_p,
+                                     c_size_t, c_void_p]),
     'cvb_sppf_pool': (c_int32, [POINTER(CvbView), POINTER(CvbView), POINTER(CvbView), POINTER(CvbView), c_void_p]),
     'cvb_yolo_decode': (c_int32, [POINTER(CvbView), c_int32, c_int32, c_void_p, c_float, c_void_p, c_int64,
                                   c_int64, c_void_p, c_void_p, c_float, c_int32, c_void_p]),
@@ -50,6 +55,10 @@ SYMBOLS = {
     'cvb_nms_workspace_bytes': (c_size_t, [c_int32, c_int32, c_int32]),
     'cvb_yolo_nms': (c_int32, [c_void_p, POINTER(CvbNmsParams), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                c_void_p, c_void_p]),
+    'cvb_fcos_decode': (c_int32, [POINTER(CvbView), POINTER(CvbView), c_int32, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int64,
+                                  c_int64, c_void_p]),
+    'cvb_fcos_nms': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_float, c_int32, c_void_p, c_void_p, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p]),
     'cvb_last_error_string': (c_char_p, []),
     'cvb_version': (c_int32, []),
     'cvb_launch_count': (c_int64, []),

@@ -294,6 +294,168 @@ __global__ void __launch_bounds__(kDecodeThreads) yolo_decode_kernel(const float
   }
 }
 
+// ------------------------------------------------------------------ 3x3 / stride 2 / pad 1 max pool (ResNet stem)
+// one thread per (output pixel, 8-channel vector); max over hi+lo values, result re-split exactly (max is one of the inputs)
+__global__ void maxpool3x3s2_kernel(const __half* __restrict__ x, int B, int H, int W, int C, int xp, long long xplane,
+                                    __half* __restrict__ y, int Ho, int Wo, int yp, long long yplane) {
+  const int cv = C / 8;
+  const long long n = (long long)B * Ho * Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    long long t = i / cv;
+    const int wo = (int)(t % Wo);
+    t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    float best[8];
+    uint4 bh = make_uint4(0, 0, 0, 0), bl = make_uint4(0, 0, 0, 0);
+    uint32_t* bhw = reinterpret_cast<uint32_t*>(&bh);
+    uint32_t* blw = reinterpret_cast<uint32_t*>(&bl);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) best[k] = -CUDART_INF_F;
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int h = 2 * ho + dy;
+      if (h < 0 || h >= H) continue;
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int w = 2 * wo + dx;
+        if (w < 0 || w >= W) continue;
+        const size_t o = (((size_t)b * H + h) * W + w) * xp + c8 * 8;
+        const uint4 hv = __ldg(reinterpret_cast<const uint4*>(x + o));
+        const uint4 lv = __ldg(reinterpret_cast<const uint4*>(x + o + xplane));
+        const uint32_t* hw = reinterpret_cast<const uint32_t*>(&hv);
+        const uint32_t* lw = reinterpret_cast<const uint32_t*>(&lv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+          const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+          const float v0 = hf.x + lf.x, v1 = hf.y + lf.y;
+          if (v0 > best[2 * e]) {
+            best[2 * e] = v0;
+            bhw[e] = (bhw[e] & 0xFFFF0000u) | (hw[e] & 0xFFFFu);
+            blw[e] = (blw[e] & 0xFFFF0000u) | (lw[e] & 0xFFFFu);
+          }
+          if (v1 > best[2 * e + 1]) {
+            best[2 * e + 1] = v1;
+            bhw[e] = (bhw[e] & 0xFFFFu) | (hw[e] & 0xFFFF0000u);
+            blw[e] = (blw[e] & 0xFFFFu) | (lw[e] & 0xFFFF0000u);
+          }
+        }
+      }
+    }
+    const size_t oo = (((size_t)b * Ho + ho) * Wo + wo) * yp + c8 * 8;
+    *reinterpret_cast<uint4*>(y + oo) = bh;
+    *reinterpret_cast<uint4*>(y + oo + yplane) = bl;
+  }
+}
+
+// ------------------------------------------------------------------ split16 -> fp32 NHWC (FPN partials)
+__global__ void split_to_f32_kernel(const __half* __restrict__ x, long long npix, int C, int xp, long long xplane, float* __restrict__ y,
+                                    int yp) {
+  const int cv = C / 8;
+  const long long n = npix * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    const long long p = i / cv;
+    const uint4 hv = __ldg(reinterpret_cast<const uint4*>(x + p * xp + c8 * 8));
+    const uint4 lv = __ldg(reinterpret_cast<const uint4*>(x + p * xp + c8 * 8 + xplane));
+    const uint32_t* hw = reinterpret_cast<const uint32_t*>(&hv);
+    const uint32_t* lw = reinterpret_cast<const uint32_t*>(&lv);
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+      const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+      o[2 * e] = hf.x + lf.x;
+      o[2 * e + 1] = hf.y + lf.y;
+    }
+    float4* dst = reinterpret_cast<float4*>(y + p * yp + c8 * 8);
+    dst[0] = make_float4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+  }
+}
+
+// ------------------------------------------------------------------ GroupNorm(+ReLU) for 8 channels per group (FCOS towers)
+// pass 1: per (image, group) sum and sum of squares (fp32 per thread over <= 64 values, double across threads)
+__global__ void gn_stats_kernel(const __half* __restrict__ x, int npix, int C, int xp, long long xplane, double* __restrict__ stats) {
+  const int groups = C / 8;
+  const int b = blockIdx.y;
+  const int g = threadIdx.x % groups;           // blockDim.x is a multiple of groups
+  const int lanes = blockDim.x / groups;        // pixels handled concurrently by the CTA
+  const int pl = threadIdx.x / groups;
+  const int chunk = (npix + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * chunk, p1 = min(npix, p0 + chunk);
+  double s = 0.0, ss = 0.0;
+  float fs = 0.0f, fss = 0.0f;
+  int cnt = 0;
+  for (int p = p0 + pl; p < p1; p += lanes) {
+    const size_t o = ((size_t)b * npix + p) * xp + g * 8;
+    const uint4 hv = __ldg(reinterpret_cast<const uint4*>(x + o));
+    const uint4 lv = __ldg(reinterpret_cast<const uint4*>(x + o + xplane));
+    const uint32_t* hw = reinterpret_cast<const uint32_t*>(&hv);
+    const uint32_t* lw = reinterpret_cast<const uint32_t*>(&lv);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+      const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+      const float v0 = hf.x + lf.x, v1 = hf.y + lf.y;
+      fs += v0 + v1;
+      fss += v0 * v0 + v1 * v1;
+    }
+    if (++cnt == 8) {
+      s += fs;
+      ss += fss;
+      fs = fss = 0.0f;
+      cnt = 0;
+    }
+  }
+  s += fs;
+  ss += fss;
+  atomicAdd(&stats[((size_t)b * groups + g) * 2 + 0], s);
+  atomicAdd(&stats[((size_t)b * groups + g) * 2 + 1], ss);
+}
+
+// pass 2: y = relu((x - mean) * rstd * gamma + beta), re-split to hi/lo
+__global__ void gn_apply_kernel(const __half* __restrict__ x, int npix, int C, int xp, long long xplane, const double* __restrict__ stats,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int relu,
+                                __half* __restrict__ y, int yp, long long yplane) {
+  const int groups = C / 8;
+  const int b = blockIdx.y;
+  const long long n = (long long)npix * groups;
+  const double inv_n = 1.0 / ((double)npix * 8.0);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(i % groups);
+    const long long p = i / groups;
+    const double m = stats[((size_t)b * groups + g) * 2] * inv_n;
+    const double var = fmax(stats[((size_t)b * groups + g) * 2 + 1] * inv_n - m * m, 0.0);
+    const float mean = (float)m, rstd = (float)(1.0 / sqrt(var + (double)eps));
+    const size_t o = ((size_t)b * npix + p) * xp + g * 8;
+    const uint4 hv = __ldg(reinterpret_cast<const uint4*>(x + o));
+    const uint4 lv = __ldg(reinterpret_cast<const uint4*>(x + o + xplane));
+    const uint32_t* hw = reinterpret_cast<const uint32_t*>(&hv);
+    const uint32_t* lw = reinterpret_cast<const uint32_t*>(&lv);
+    uint32_t oh[4], ol[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+      const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+      float v0 = ((hf.x + lf.x) - mean) * rstd * __ldg(gamma + g * 8 + 2 * e) + __ldg(beta + g * 8 + 2 * e);
+      float v1 = ((hf.y + lf.y) - mean) * rstd * __ldg(gamma + g * 8 + 2 * e + 1) + __ldg(beta + g * 8 + 2 * e + 1);
+      if (relu) {
+        v0 = fmaxf(v0, 0.0f);
+        v1 = fmaxf(v1, 0.0f);
+      }
+      __half h0, l0, h1, l1;
+      split_f32(v0, &h0, &l0);
+      split_f32(v1, &h1, &l1);
+      oh[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      ol[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    const size_t oo = ((size_t)b * npix + p) * yp + g * 8;
+    *reinterpret_cast<uint4*>(y + oo) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+    *reinterpret_cast<uint4*>(y + oo + yplane) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+  }
+}
+
 static int check_split_view(const CvbView* v, const char* what) {
   CVB_REQUIRE(v != nullptr && v->base != nullptr, "%s: null view", what);
   CVB_REQUIRE(v->c_pitch >= v->C && v->plane_stride % 2 == 0, "%s: bad view", what);
@@ -338,12 +500,12 @@ extern "C" int cvb_f32nhwc_to_nchw(const CvbView* src, float* dst, void* stream)
   return CVB_OK;
 }
 
-extern "C" int cvb_stem_s2d(const float* src, int32_t B, int32_t H, int32_t W, const CvbView* dst, void* stream) {
+extern "C" int cvb_stem_s2d(const float* src, int32_t B, int32_t H, int32_t W, const CvbView* dst, int32_t pad_left, void* stream) {
   int rc = check_split_view(dst, "stem_s2d");
   if (rc) return rc;
   CVB_REQUIRE(src && H % 2 == 0 && W % 2 == 0, "stem_s2d: H and W must be even");
-  CVB_REQUIRE(dst->B == B && dst->H == H / 2 && (dst->W == W / 2 || dst->W == W / 2 + 3) && dst->C == 16 && dst->c_pitch == 16,
-              "stem_s2d: dst must be [B,H/2,W/2,16] or the zero-padded row-window layout [B,H/2,W/2+3,16]");
+  CVB_REQUIRE(dst->B == B && dst->H == H / 2 && dst->W >= W / 2 + pad_left && pad_left >= 0 && dst->C == 16 && dst->c_pitch == 16,
+              "stem_s2d: dst must be [B,H/2,>=W/2+pad_left,16]");
   CVB_REQUIRE((reinterpret_cast<uintptr_t>(src) & 7) == 0 && (reinterpret_cast<uintptr_t>(dst->base) & 15) == 0 && dst->plane_stride % 16 == 0,
               "stem_s2d: alignment");
   const long long n = (long long)B * (H / 2) * (W / 2);
@@ -351,7 +513,7 @@ extern "C" int cvb_stem_s2d(const float* src, int32_t B, int32_t H, int32_t W, c
   long long grid = (n + block - 1) / block;
   if (grid > 148 * 32) grid = 148 * 32;
   stem_s2d_kernel<<<(int)grid, block, 0, as_stream(stream)>>>(src, B, H, W, static_cast<__half*>(dst->base), dst->c_pitch,
-                                                             dst->plane_stride / 2, dst->W, dst->W == W / 2 ? 0 : 1);
+                                                             dst->plane_stride / 2, dst->W, pad_left);
   CVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return CVB_OK;
@@ -407,5 +569,77 @@ extern "C" int cvb_yolo_decode(const CvbView* raw, int32_t na, int32_t no, const
                                                             static_cast<uint32_t*>(nms_workspace), conf_thres, multi_label);
   CVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
+  return CVB_OK;
+}
+
+static int check_vec_view(const CvbView* v, const char* what) {
+  int rc = check_split_view(v, what);
+  if (rc) return rc;
+  CVB_REQUIRE(v->C % 8 == 0 && v->c_pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(v->base) & 15) == 0 && v->plane_stride % 16 == 0,
+              "%s: channels/pitch must be multiples of 8 and 16-byte aligned", what);
+  return CVB_OK;
+}
+
+extern "C" int cvb_maxpool3x3s2(const CvbView* x, const CvbView* y, void* stream) {
+  int rc = check_vec_view(x, "maxpool x");
+  if (!rc) rc = check_vec_view(y, "maxpool y");
+  if (rc) return rc;
+  const int Ho = (x->H + 2 - 3) / 2 + 1, Wo = (x->W + 2 - 3) / 2 + 1;
+  CVB_REQUIRE(y->B == x->B && y->H == Ho && y->W == Wo && y->C == x->C, "maxpool3x3s2: output must be [%d,%d,%d,%d]", x->B, Ho, Wo, x->C);
+  const long long n = (long long)x->B * Ho * Wo * (x->C / 8);
+  long long grid = (n + 255) / 256;
+  if (grid > 148 * 32) grid = 148 * 32;
+  maxpool3x3s2_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(static_cast<const __half*>(x->base), x->B, x->H, x->W, x->C, x->c_pitch,
+                                                               x->plane_stride / 2, static_cast<__half*>(y->base), Ho, Wo, y->c_pitch,
+                                                               y->plane_stride / 2);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}
+
+extern "C" int cvb_split_to_f32nhwc(const CvbView* x, const CvbView* y, void* stream) {
+  int rc = check_vec_view(x, "split_to_f32 x");
+  if (rc) return rc;
+  CVB_REQUIRE(y && y->base && y->B == x->B && y->H == x->H && y->W == x->W && y->C == x->C && y->c_pitch % 4 == 0 &&
+                  (reinterpret_cast<uintptr_t>(y->base) & 15) == 0,
+              "split_to_f32: output view mismatch");
+  const long long npix = (long long)x->B * x->H * x->W;
+  long long grid = (npix * (x->C / 8) + 255) / 256;
+  if (grid > 148 * 32) grid = 148 * 32;
+  split_to_f32_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(static_cast<const __half*>(x->base), npix, x->C, x->c_pitch,
+                                                               x->plane_stride / 2, static_cast<float*>(y->base), y->c_pitch);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}
+
+extern "C" size_t cvb_groupnorm_workspace_bytes(int32_t B, int32_t groups) { return (size_t)B * groups * 2 * sizeof(double); }
+
+extern "C" int cvb_groupnorm_relu(const CvbView* x, int32_t groups, const float* gamma, const float* beta, float eps, int32_t relu,
+                                  const CvbView* y, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_vec_view(x, "groupnorm x");
+  if (!rc) rc = check_vec_view(y, "groupnorm y");
+  if (rc) return rc;
+  CVB_REQUIRE(gamma && beta && workspace, "groupnorm: null argument");
+  CVB_REQUIRE(groups > 0 && x->C == groups * 8, "groupnorm: only 8 channels per group are supported (C=%d, groups=%d)", x->C, groups);
+  CVB_REQUIRE(y->B == x->B && y->H == x->H && y->W == x->W && y->C == x->C, "groupnorm: output view mismatch");
+  CVB_REQUIRE(workspace_bytes >= cvb_groupnorm_workspace_bytes(x->B, groups) && (reinterpret_cast<uintptr_t>(workspace) & 7) == 0,
+              "groupnorm: workspace too small / misaligned");
+  cudaStream_t st = as_stream(stream);
+  CVB_CHECK_CUDA(cudaMemsetAsync(workspace, 0, cvb_groupnorm_workspace_bytes(x->B, groups), st));
+  const int npix = x->H * x->W;
+  const int threads = 256 / groups * groups > 0 ? (256 / groups) * groups : groups;
+  int chunks = (npix + 255) / 256;
+  if (chunks > 148 * 4) chunks = 148 * 4;
+  if (chunks < 1) chunks = 1;
+  gn_stats_kernel<<<dim3(chunks, x->B), threads, 0, st>>>(static_cast<const __half*>(x->base), npix, x->C, x->c_pitch, x->plane_stride / 2,
+                                                         static_cast<double*>(workspace));
+  long long g2 = ((long long)npix * groups + 255) / 256;
+  if (g2 > 148 * 8) g2 = 148 * 8;
+  gn_apply_kernel<<<dim3((int)g2, x->B), 256, 0, st>>>(static_cast<const __half*>(x->base), npix, x->C, x->c_pitch, x->plane_stride / 2,
+                                                      static_cast<const double*>(workspace), gamma, beta, eps, relu,
+                                                      static_cast<__half*>(y->base), y->c_pitch, y->plane_stride / 2);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(2);
   return CVB_OK;
 }

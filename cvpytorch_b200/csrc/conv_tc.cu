@@ -565,8 +565,8 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   CVB_REQUIRE(d->dilation >= 1, "conv: bad dilation");
   const int win = d->w_window;  // >0: K chunk of a filter row = `win` horizontally adjacent input pixels (see cvb200.h)
   if (win > 0) {
-    CVB_REQUIRE(d->stride == 1 && d->dilation == 1 && d->kw <= win && d->pad == (d->kw - 1) / 2 && d->pad == (d->kh - 1) / 2,
-                "conv: w_window needs a stride-1 'same' convolution with kw <= w_window");
+    CVB_REQUIRE(d->stride == 1 && d->dilation == 1 && d->kw <= win && d->pad >= 0 && d->pad < d->kh,
+                "conv: w_window needs a stride-1 convolution with kw <= w_window (filter row ky reads input row h + ky - pad)");
     CVB_REQUIRE(in.c_pitch == in.C && (win * in.C == 64 || win * in.C == 32), "conv: w_window needs contiguous pixels and window*C in {32,64}");
     CVB_REQUIRE(in.W > win - 1, "conv: padded input too narrow");
   }
@@ -577,7 +577,9 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   CVB_REQUIRE((reinterpret_cast<uintptr_t>(in.base) & 15) == 0 && (reinterpret_cast<uintptr_t>(out.base) & 15) == 0 &&
                   (reinterpret_cast<uintptr_t>(d->weights) & 15) == 0,
               "conv: pointers must be 16-byte aligned");
-  const int Ho = (in.H + 2 * d->pad - d->dilation * (d->kh - 1) - 1) / d->stride + 1;
+  // window mode: the caller fixes the output height (asymmetric vertical padding is expressed by `pad` = rows above; rows
+  // below come from TMA zero fill), e.g. the 7x7/s2/p3 ResNet stem == 4 filter rows over the space-to-depth input, pad 2.
+  const int Ho = win > 0 ? out.H : (in.H + 2 * d->pad - d->dilation * (d->kh - 1) - 1) / d->stride + 1;
   const int Wo = win > 0 ? in.W - (win - 1) : (in.W + 2 * d->pad - d->dilation * (d->kw - 1) - 1) / d->stride + 1;
   CVB_REQUIRE(Ho == out.H && Wo == out.W && in.B == out.B, "conv: output view %dx%dx%d does not match computed %dx%dx%d", out.B, out.H,
               out.W, in.B, Ho, Wo);

@@ -548,3 +548,341 @@ extern "C" int cvb_yolo_nms(const float* prediction, const CvbNmsParams* p, floa
   count_launch();
   return CVB_OK;
 }
+
+
+// =====================================================================================================================
+// FCOS post-processing (src/models/detects/fcos_detect.py:42-153)
+// =====================================================================================================================
+namespace cvb {
+
+__device__ __forceinline__ float sigmoid_mufu(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+
+// One warp per location: max over class sigmoids (first maximum wins), score = sqrt(cls * sigmoid(cnt)), class id + 1,
+// box = (cx - l, cy - t, cx + r, cy + b) with ltrb = exp(raw * scale_i) (ScaleExp, fcos_head.py:13-19) and the location
+// centre (x*stride + stride//2, y*stride + stride//2) (coords_fmap2orig :14-31).
+__global__ void __launch_bounds__(256) fcos_decode_kernel(const float* __restrict__ cls, int cls_pitch, const float* __restrict__ rc,
+                                                          int rc_pitch, int B, int h, int w, int nc, float stride, float scale,
+                                                          float* __restrict__ scores, int* __restrict__ classes,
+                                                          float* __restrict__ boxes, long long n_total, long long loc_off) {
+  const int lane = threadIdx.x & 31;
+  const long long npix = (long long)h * w;
+  const long long rows = (long long)B * npix;
+  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long row = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5); row < rows; row += wstride) {
+    const int b = (int)(row / npix);
+    const int pix = (int)(row - (long long)b * npix);
+    const float* c = cls + row * cls_pitch;
+    float best = -1.0f;
+    int bi = 0x7fffffff;
+    for (int k = lane; k < nc; k += 32) {
+      const float p = sigmoid_mufu(__ldg(c + k));
+      if (p > best) {
+        best = p;
+        bi = k;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ob > best || (ob == best && oi < bi)) {
+        best = ob;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      const float* r = rc + row * rc_pitch;
+      const float cnt = sigmoid_mufu(__ldg(r + 4));
+      const int py = pix / w, px = pix - py * w;
+      const float half = (float)(((int)stride) / 2);
+      const float cx = __fadd_rn(__fmul_rn((float)px, stride), half), cy = __fadd_rn(__fmul_rn((float)py, stride), half);
+      const float l = expf(__fmul_rn(__ldg(r + 0), scale)), t = expf(__fmul_rn(__ldg(r + 1), scale));
+      const float rr = expf(__fmul_rn(__ldg(r + 2), scale)), bb = expf(__fmul_rn(__ldg(r + 3), scale));
+      const size_t o = (size_t)b * n_total + loc_off + pix;
+      scores[o] = sqrtf(__fmul_rn(best, cnt));
+      classes[o] = bi + 1;
+      float4 bx = make_float4(__fsub_rn(cx, l), __fsub_rn(cy, t), __fadd_rn(cx, rr), __fadd_rn(cy, bb));
+      *reinterpret_cast<float4*>(boxes + o * 4) = bx;
+    }
+  }
+}
+
+constexpr int kFcosThreads = 512;
+constexpr int kFcosSel = 4096;  // candidates sorted in shared memory (top-k <= 2048 supported)
+
+struct FcosSmem {
+  uint64_t keys[kFcosSel];                 // 32 KB
+  uint32_t hist[kBins];                    // 64 KB; reused as the suppression mask [512][16] after selection
+  float4 kbox[2048];                       // kept (class-offset) boxes, 32 KB
+  float karea[2048];
+  float4 cbox[kFcosThreads];
+  float carea[kFcosThreads];
+  uint32_t cidx[kFcosThreads];
+  uint32_t keeplist[kFcosThreads];
+  uint32_t warp_cnt[kFcosThreads / 32];
+  float red[kFcosThreads / 32];
+  uint32_t n_sel, tbin, m_alive, new_kept, overflow;
+  float maxc;
+};
+
+// FCOS IoU: '+1' areas, plain intersection, box j is KEPT iff iou <= thr evaluated in float32 (fcos_detect.py:117,133-135)
+__device__ __forceinline__ bool fcos_suppressed(const float4& a, float aa, const float4& b, float ab, float thr32) {
+  const float xmin = fmaxf(b.x, a.x), ymin = fmaxf(b.y, a.y);
+  const float xmax = fminf(b.z, a.z), ymax = fminf(b.w, a.w);
+  const float inter = __fmul_rn(fmaxf(__fsub_rn(xmax, xmin), 0.0f), fmaxf(__fsub_rn(ymax, ymin), 0.0f));
+  const float iou = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
+  return !(iou <= thr32);
+}
+
+__global__ void __launch_bounds__(kFcosThreads) fcos_nms_kernel(const float* __restrict__ scores, const int* __restrict__ classes,
+                                                                const float* __restrict__ boxes, int N, float score_thres,
+                                                                float iou_thres, int topk, float* __restrict__ out_scores,
+                                                                int* __restrict__ out_classes, float* __restrict__ out_boxes,
+                                                                int* __restrict__ out_loc, int* __restrict__ out_count,
+                                                                int* __restrict__ status) {
+  extern __shared__ uint8_t fs_raw[];
+  FcosSmem& S = *reinterpret_cast<FcosSmem*>(fs_raw);
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* sc = scores + (size_t)b * N;
+  const int* cl = classes + (size_t)b * N;
+  const float4* bx = reinterpret_cast<const float4*>(boxes) + (size_t)b * N;
+
+  // ---- 1. top-k selection: histogram of score bits -> threshold bin -> collect -> bitonic sort (descending; ties: lower index)
+  for (int i = tid; i < kBins; i += kFcosThreads) S.hist[i] = 0;
+  if (tid == 0) {
+    S.n_sel = 0;
+    S.tbin = 0;
+    S.overflow = 0;
+  }
+  __syncthreads();
+  for (int i = tid; i < N; i += kFcosThreads) {
+    const float v = sc[i];
+    if (v >= 0.0f) atomicAdd(&S.hist[min(__float_as_uint(v) >> 17, (uint32_t)(kBins - 1))], 1u);  // NaN / negative never selected
+  }
+  __syncthreads();
+  if (warp == 0) {  // walk the bins top-down, 32 at a time
+    uint32_t run = 0;
+    for (int base = kBins - 32; base >= 0; base -= 32) {
+      const uint32_t v = S.hist[base + (31 - lane)];  // lane 0 = highest bin of the group
+      uint32_t inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      const uint32_t hit = __ballot_sync(0xffffffffu, run + inc >= (uint32_t)topk);
+      if (hit) {
+        const int l = __ffs(hit) - 1;
+        if (lane == 0) S.tbin = (uint32_t)(base + (31 - l));
+        break;
+      }
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+  }
+  __syncthreads();
+  const uint32_t tb = S.tbin;
+  for (int i0 = 0; i0 < N; i0 += kFcosThreads) {
+    const int i = i0 + tid;
+    bool pass = false;
+    uint32_t bits = 0;
+    if (i < N) {
+      const float v = sc[i];
+      bits = __float_as_uint(v);
+      pass = (v >= 0.0f) && (min(bits >> 17, (uint32_t)(kBins - 1)) >= tb);
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, pass);
+    if (m) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&S.n_sel, (uint32_t)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (pass) {
+        const uint32_t pos = base + __popc(m & ((1u << lane) - 1));
+        if (pos < (uint32_t)kFcosSel) S.keys[pos] = ((uint64_t)bits << 32) | (uint64_t)(0xFFFFFFFFu - (uint32_t)i);
+        else S.overflow = 1;
+      }
+    }
+  }
+  __syncthreads();
+  uint32_t nsel = min(S.n_sel, (uint32_t)kFcosSel);
+  if (S.overflow && status && tid == 0) atomicExch(&status[0], 1);
+  for (int i = nsel + tid; i < kFcosSel; i += kFcosThreads) S.keys[i] = 0ull;
+  for (int k = 2; k <= kFcosSel; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      __syncthreads();
+      for (int t = tid; t < kFcosSel / 2; t += kFcosThreads) {
+        const int i = 2 * j * (t / j) + (t % j);
+        cmpswap(S.keys, i, i + j, (i & k) == 0);
+      }
+    }
+  __syncthreads();
+  // candidates = sorted prefix of length min(topk, nsel) with score >= score_thres (fcos_detect.py:65-67,92-93)
+  int ncand = min((int)nsel, topk);
+  {
+    // scores are sorted descending: count the prefix that passes the threshold
+    int cntp = 0;
+    for (int i = tid; i < ncand; i += kFcosThreads) cntp += (__uint_as_float((uint32_t)(S.keys[i] >> 32)) >= score_thres) ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) cntp += __shfl_xor_sync(0xffffffffu, cntp, o);
+    if (lane == 0) S.warp_cnt[warp] = (uint32_t)cntp;
+    __syncthreads();
+    int tot = 0;
+    for (int i = 0; i < kFcosThreads / 32; ++i) tot += (int)S.warp_cnt[i];
+    ncand = tot;
+    __syncthreads();
+  }
+  // ---- 2. class offset = cls * (max coordinate of the candidate boxes + 1)   (batched_nms :141-153)
+  float mx = -3.402823466e38f;
+  for (int i = tid; i < ncand; i += kFcosThreads) {
+    const uint32_t loc = 0xFFFFFFFFu - (uint32_t)(S.keys[i] & 0xFFFFFFFFull);
+    const float4 q = bx[loc];
+    mx = fmaxf(mx, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w)));
+  }
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) S.red[warp] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    float m2 = S.red[0];
+    for (int i = 1; i < kFcosThreads / 32; ++i) m2 = fmaxf(m2, S.red[i]);
+    S.maxc = __fadd_rn(m2, 1.0f);
+  }
+  __syncthreads();
+  const float offmul = S.maxc;
+  uint32_t (*mask)[kFcosThreads / 32] = reinterpret_cast<uint32_t (*)[kFcosThreads / 32]>(S.hist);
+
+  // ---- 3. greedy NMS over the candidates in score order (chunks of 512, like the YOLO kernel)
+  int kept_n = 0;
+  for (int base = 0; base < ncand; base += kFcosThreads) {
+    const int i = base + tid;
+    bool alive = i < ncand;
+    float4 box = make_float4(0, 0, 0, 0);
+    float area = 0.0f;
+    uint32_t loc = 0;
+    if (alive) {
+      loc = 0xFFFFFFFFu - (uint32_t)(S.keys[i] & 0xFFFFFFFFull);
+      const float4 q = bx[loc];
+      const float off = __fmul_rn((float)cl[loc], offmul);
+      box = make_float4(__fadd_rn(q.x, off), __fadd_rn(q.y, off), __fadd_rn(q.z, off), __fadd_rn(q.w, off));
+      area = __fmul_rn(__fadd_rn(__fsub_rn(box.z, box.x), 1.0f), __fadd_rn(__fsub_rn(box.w, box.y), 1.0f));
+      for (int k = 0; k < kept_n; ++k)
+        if (fcos_suppressed(S.kbox[k], S.karea[k], box, area, iou_thres)) {
+          alive = false;
+          break;
+        }
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+    if (lane == 0) S.warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t v = (lane < kFcosThreads / 32) ? S.warp_cnt[lane] : 0;
+      uint32_t inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      if (lane < kFcosThreads / 32) S.warp_cnt[lane] = inc - v;
+      if (lane == 31) S.m_alive = inc;
+    }
+    __syncthreads();
+    const int m = (int)S.m_alive;
+    if (alive) {
+      const int pos = (int)S.warp_cnt[warp] + __popc(bal & ((1u << lane) - 1));
+      S.cbox[pos] = box;
+      S.carea[pos] = area;
+      S.cidx[pos] = (uint32_t)i;
+    }
+    __syncthreads();
+    const int words = (m + 31) >> 5;
+    if (tid < m) {
+      const float4 me = S.cbox[tid];
+      const float ma = S.carea[tid];
+      for (int wd = 0; wd < words; ++wd) {
+        uint32_t bits = 0;
+        const int c0 = wd << 5, c1 = min(m, c0 + 32);
+        for (int c = max(c0, tid + 1); c < c1; ++c)
+          if (fcos_suppressed(me, ma, S.cbox[c], S.carea[c], iou_thres)) bits |= 1u << (c & 31);
+        mask[tid][wd] = bits;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t removed = 0;
+      int nk = 0;
+      for (int r = 0; r < m; ++r) {
+        const uint32_t rw = __shfl_sync(0xffffffffu, removed, r >> 5);
+        if (!((rw >> (r & 31)) & 1u)) {
+          if (lane == 0) S.keeplist[nk] = (uint32_t)r;
+          ++nk;
+          if (lane < words) removed |= mask[r][lane];
+        }
+      }
+      if (lane == 0) S.new_kept = (uint32_t)nk;
+    }
+    __syncthreads();
+    const int nk = (int)S.new_kept;
+    for (int t = tid; t < nk; t += kFcosThreads) {
+      const int r = (int)S.keeplist[t];
+      const int o = kept_n + t;
+      S.kbox[o] = S.cbox[r];
+      S.karea[o] = S.carea[r];
+      const uint64_t key = S.keys[S.cidx[r]];
+      const uint32_t l2 = 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull);
+      out_scores[(size_t)b * topk + o] = __uint_as_float((uint32_t)(key >> 32));
+      out_classes[(size_t)b * topk + o] = cl[l2];
+      reinterpret_cast<float4*>(out_boxes)[(size_t)b * topk + o] = bx[l2];
+      out_loc[(size_t)b * topk + o] = (int)l2;
+    }
+    kept_n += nk;
+    __syncthreads();
+  }
+  if (tid == 0) out_count[b] = kept_n;
+}
+
+}  // namespace cvb
+
+extern "C" int cvb_fcos_decode(const CvbView* cls, const CvbView* regcnt, int32_t nc, float stride, float scale, float* scores,
+                               int32_t* classes, float* boxes, int64_t n_total, int64_t loc_off, void* stream) {
+  using namespace cvb;
+  CVB_REQUIRE(cls && regcnt && cls->base && regcnt->base && scores && classes && boxes, "fcos_decode: null argument");
+  CVB_REQUIRE(cls->B == regcnt->B && cls->H == regcnt->H && cls->W == regcnt->W && cls->c_pitch >= nc && regcnt->c_pitch >= 5,
+              "fcos_decode: view mismatch");
+  CVB_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0, "fcos_decode: boxes must be 16-byte aligned");
+  const long long rows = (long long)cls->B * cls->H * cls->W;
+  long long grid = (rows + 7) / 8;
+  if (grid > 148 * 16) grid = 148 * 16;
+  fcos_decode_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(static_cast<const float*>(cls->base), cls->c_pitch,
+                                                              static_cast<const float*>(regcnt->base), regcnt->c_pitch, cls->B, cls->H,
+                                                              cls->W, nc, stride, scale, scores, classes, boxes, n_total, loc_off);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}
+
+extern "C" int cvb_fcos_nms(const float* scores, const int32_t* classes, const float* boxes, int32_t B, int32_t N, float score_thres,
+                            float iou_thres, int32_t topk, float* out_scores, int32_t* out_classes, float* out_boxes, int32_t* out_loc,
+                            int32_t* out_count, int32_t* status, void* stream) {
+  using namespace cvb;
+  CVB_REQUIRE(scores && classes && boxes && out_scores && out_classes && out_boxes && out_loc && out_count, "fcos_nms: null argument");
+  CVB_REQUIRE(B > 0 && N > 0 && topk > 0 && topk <= 2048, "fcos_nms: bad sizes (topk <= 2048)");
+  CVB_REQUIRE((reinterpret_cast<uintptr_t>(boxes) & 15) == 0 && (reinterpret_cast<uintptr_t>(out_boxes) & 15) == 0, "fcos_nms: box arrays must be 16-byte aligned");
+  cudaStream_t st = as_stream(stream);
+  if (status) CVB_CHECK_CUDA(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st));
+  CVB_CHECK_CUDA(cudaMemsetAsync(out_scores, 0, (size_t)B * topk * sizeof(float), st));
+  CVB_CHECK_CUDA(cudaMemsetAsync(out_classes, 0, (size_t)B * topk * sizeof(int32_t), st));
+  CVB_CHECK_CUDA(cudaMemsetAsync(out_boxes, 0, (size_t)B * topk * 4 * sizeof(float), st));
+  CVB_CHECK_CUDA(cudaMemsetAsync(out_loc, 0xFF, (size_t)B * topk * sizeof(int32_t), st));
+  static bool attr_set = false;
+  if (!attr_set) {
+    CVB_CHECK_CUDA(cudaFuncSetAttribute(fcos_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FcosSmem)));
+    attr_set = true;
+  }
+  fcos_nms_kernel<<<B, kFcosThreads, sizeof(FcosSmem), st>>>(scores, classes, boxes, N, score_thres, iou_thres, topk, out_scores, out_classes,
+                                                            out_boxes, out_loc, out_count, status);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}

@@ -71,7 +71,7 @@ class GraphBuilder:
 
     # ---------------------------------------------------------------- ops
     def conv(self, x, w64, b64, k, stride=1, pad=0, act='silu', out=None, residual=None, up_partial=None,
-             f32_out=None, dilation=1, name='', block_n=0, w_window=0):
+             f32_out=None, dilation=1, name='', block_n=0, w_window=0, residual_before_act=False):
         """x: Val.  w64: [O,I,k,k] float64 (BN already folded), b64: [O] float64.
         out: Val (split16) or None (allocate).  f32_out: F32Tensor -> plain fp32 output."""
         O, I = w64.shape[0], w64.shape[1]
@@ -80,6 +80,7 @@ class GraphBuilder:
         Wo = (x.W + 2 * pad - dilation * (k - 1) - 1) // stride + 1
         if w_window:  # x is the zero-padded row-window layout (see include/cvb200.h)
             Wo = x.W - (w_window - 1)
+            Ho = out.H if out is not None else x.H
             wp, bp = ops.pack_conv_weights(ops.window_weights(w64, w_window), b64, device=self.device)
         else:
             wp, bp = ops.pack_conv_weights(w64, b64, device=self.device)
@@ -95,7 +96,7 @@ class GraphBuilder:
         plan = ops.ConvPlan(x.view(), out_view, wp, bp, k, stride, pad, dilation, act,
                             residual=residual.view() if residual is not None else None,
                             up_partial=up_partial.view(0, O) if up_partial is not None else None, block_n=block_n,
-                            w_window=w_window)
+                            w_window=w_window, residual_before_act=1 if residual_before_act else 0)
         self.steps.append(('conv', plan))
         self.n_convs += 1
         self.flops += 2 * self.B * Ho * Wo * O * I * k * k

@@ -194,12 +194,34 @@ def f32nhwc_to_nchw(src_view, out=None):
     return out
 
 
-def stem_s2d(x, dst_view):
+def stem_s2d(x, dst_view, pad_left=None):
+    """pad_left=None: 0 for a plain [B,H/2,W/2,16] target, 1 for the padded row-window layout (W/2+3 columns)."""
     _require_cuda(x, 'stem_s2d')
     assert x.dtype == torch.float32 and x.is_contiguous()
     B, C, H, W = x.shape
     assert C == 3
-    _lib.check(_lib.lib().cvb_stem_s2d(x.data_ptr(), B, H, W, byref(dst_view), _stream()), 'cvb_stem_s2d')
+    if pad_left is None:
+        pad_left = 0 if dst_view.W == W // 2 else 1
+    _lib.check(_lib.lib().cvb_stem_s2d(x.data_ptr(), B, H, W, byref(dst_view), pad_left, _stream()), 'cvb_stem_s2d')
+
+
+def maxpool3x3s2(x_view, y_view):
+    _lib.check(_lib.lib().cvb_maxpool3x3s2(byref(x_view), byref(y_view), _stream()), 'cvb_maxpool3x3s2')
+
+
+def split_to_f32(x_view, y_view):
+    _lib.check(_lib.lib().cvb_split_to_f32nhwc(byref(x_view), byref(y_view), _stream()), 'cvb_split_to_f32nhwc')
+
+
+class GroupNormWorkspace:
+    def __init__(self, B, groups, device='cuda'):
+        self.nbytes = int(_lib.lib().cvb_groupnorm_workspace_bytes(B, groups))
+        self.buf = torch.zeros(self.nbytes // 8, dtype=torch.float64, device=device)
+
+
+def groupnorm_relu(x_view, groups, gamma, beta, eps, y_view, ws, relu=True):
+    _lib.check(_lib.lib().cvb_groupnorm_relu(byref(x_view), groups, gamma.data_ptr(), beta.data_ptr(), float(eps), 1 if relu else 0,
+                                             byref(y_view), ws.buf.data_ptr(), ws.nbytes, _stream()), 'cvb_groupnorm_relu')
 
 
 def sppf_pool(x, y1, y2, y3):
@@ -250,3 +272,35 @@ def yolo_nms(prediction, ws, conf_thres=0.001, iou_thres=0.6, multi_label=True, 
                                        ws.det_count.data_ptr(), ws.ws_ptr, ws.ws_bytes, ws.status.data_ptr(), _stream()),
                'cvb_yolo_nms')
     return ws.det, ws.det_idx, ws.det_count
+
+
+# --------------------------------------------------------------------------------------- FCOS post-processing
+class FcosWorkspace:
+    """Caller-owned buffers of the FCOS decode + top-k + NMS stage (fixed capacity, no host sync)."""
+
+    def __init__(self, B, N, topk=1000, device='cuda'):
+        self.B, self.N, self.topk = B, N, topk
+        self.scores = torch.zeros((B, N), dtype=torch.float32, device=device)
+        self.classes = torch.zeros((B, N), dtype=torch.int32, device=device)
+        self.boxes = torch.zeros((B, N, 4), dtype=torch.float32, device=device)
+        self.out_scores = torch.zeros((B, topk), dtype=torch.float32, device=device)
+        self.out_classes = torch.zeros((B, topk), dtype=torch.int32, device=device)
+        self.out_boxes = torch.zeros((B, topk, 4), dtype=torch.float32, device=device)
+        self.out_loc = torch.zeros((B, topk), dtype=torch.int32, device=device)
+        self.out_count = torch.zeros((B,), dtype=torch.int32, device=device)
+        self.status = torch.zeros((4,), dtype=torch.int32, device=device)
+
+
+def fcos_decode(cls_view, regcnt_view, nc, stride, scale, ws, loc_off):
+    _lib.check(_lib.lib().cvb_fcos_decode(byref(cls_view), byref(regcnt_view), nc, float(stride), float(scale), ws.scores.data_ptr(),
+                                          ws.classes.data_ptr(), ws.boxes.data_ptr(), ws.N, loc_off, _stream()), 'cvb_fcos_decode')
+
+
+def fcos_nms(ws, score_thres=0.05, iou_thres=0.6, scores=None, classes=None, boxes=None):
+    s = ws.scores if scores is None else scores
+    c = ws.classes if classes is None else classes
+    b = ws.boxes if boxes is None else boxes
+    _lib.check(_lib.lib().cvb_fcos_nms(s.data_ptr(), c.data_ptr(), b.data_ptr(), ws.B, ws.N, float(score_thres), float(iou_thres), ws.topk,
+                                       ws.out_scores.data_ptr(), ws.out_classes.data_ptr(), ws.out_boxes.data_ptr(), ws.out_loc.data_ptr(),
+                                       ws.out_count.data_ptr(), ws.status.data_ptr(), _stream()), 'cvb_fcos_nms')
+    return ws.out_scores, ws.out_classes, ws.out_boxes, ws.out_loc, ws.out_count

@@ -26,18 +26,19 @@ def _gen(key):
 
 
 def base_state_dict(template):
-    """template: {key: tensor} with the reference's key names/shapes.  Returns un-calibrated synthetic values."""
+    """template: {key: tensor} with the reference's key names/shapes.  Returns un-calibrated synthetic values:
+    conv weights ~ N(0, 1/fan_in), norm-layer gamma ~ U(0.5,1.5) / beta ~ N(0,0.2), conv biases 0, running stats (0,1)."""
     out = {}
     for k, v in template.items():
         g = _gen(k)
+        stem = k.rsplit('.', 1)[0]
+        is_norm = (stem + '.weight') in template and template[stem + '.weight'].dim() == 1
         if k.endswith('num_batches_tracked'):
             out[k] = torch.zeros((), dtype=torch.long)
         elif k.endswith('anchors'):
             out[k] = v.clone().float()
-        elif k.endswith('.bn.weight'):
-            out[k] = torch.rand(v.shape, generator=g) + 0.5
-        elif k.endswith('.bn.bias'):
-            out[k] = torch.randn(v.shape, generator=g) * 0.2
+        elif k.endswith('.scale'):
+            out[k] = torch.ones(v.shape)
         elif k.endswith('running_mean'):
             out[k] = torch.zeros(v.shape)
         elif k.endswith('running_var'):
@@ -45,6 +46,10 @@ def base_state_dict(template):
         elif k.endswith('.weight') and v.dim() == 4:
             fan_in = v.shape[1] * v.shape[2] * v.shape[3]
             out[k] = torch.randn(v.shape, generator=g) / math.sqrt(fan_in)
+        elif k.endswith('.weight') and v.dim() == 1:
+            out[k] = torch.rand(v.shape, generator=g) + 0.5
+        elif k.endswith('.bias') and is_norm:
+            out[k] = torch.randn(v.shape, generator=g) * 0.2
         elif k.endswith('.bias'):
             out[k] = torch.zeros(v.shape)
         else:
@@ -120,4 +125,57 @@ def build_yolov5s(calibrated=True, device=None):
     model.eval()
     if device is not None:
         model.to(device)
+    return model
+
+
+# ================================================================================================= FCOS-R50
+FCOS_CALIB_PATH = os.path.join(os.path.dirname(CALIB_PATH), 'fcos_calib.npz')
+FCOS_CFG = {'BACKBONE': {'name': 'ResNet', 'subtype': 'resnet50', 'out_stages': [2, 3, 4], 'output_stride': 32, 'pretrained': True},
+            'NECK': {'name': 'FCOSFPN', 'in_channels': [512, 1024, 2048], 'out_channels': 256},
+            'HEAD': {'name': 'FCOSHead', 'in_channel': 256, 'GN': True, 'cnt_on_reg': True, 'prior': 0.01},
+            'LOSS': {'name': 'FCOSLoss', 'strides': [8, 16, 32, 64, 128]},
+            'DETECT': {'name': 'FCOSDetect', 'score_threshold': 0.05, 'nms_iou_threshold': 0.6, 'max_detection_boxes_num': 1000,
+                       'strides': [8, 16, 32, 64, 128]}}  # conf/coco_fcos.yml:58-64
+
+
+def fcos_template_state_dict(num_classes=80):
+    from . import fcos_models as FM
+    bb = FM.build_backbone({**FCOS_CFG['BACKBONE'], 'pretrained': False})
+    nk = FM.build_neck(FCOS_CFG['NECK'])
+    hd = FM.build_head({**FCOS_CFG['HEAD'], 'num_classes': num_classes})
+    t = {}
+    for p, m in (('backbone.', bb), ('neck.', nk), ('head.', hd)):
+        for k, v in m.state_dict().items():
+            t[p + k] = v
+    return t
+
+
+def fcos_apply_calibration(sd, calib):
+    for k in list(sd.keys()):
+        if k.endswith('running_mean') or k.endswith('running_var'):
+            sd[k] = torch.from_numpy(np.asarray(calib[k])).float().clone()
+    sc = np.asarray(calib['head_scale'])  # (cls, cnt, reg)
+    sd['head.cls_logits.weight'] = sd['head.cls_logits.weight'] * float(sc[0])
+    sd['head.cnt_logits.weight'] = sd['head.cnt_logits.weight'] * float(sc[1])
+    sd['head.reg_pred.weight'] = sd['head.reg_pred.weight'] * float(sc[2])
+    sd['head.cls_logits.bias'] = torch.full_like(sd['head.cls_logits.bias'], -math.log((1 - 0.01) / 0.01))  # fcos_head.py:61
+    sd['head.reg_pred.bias'] = torch.full_like(sd['head.reg_pred.bias'], 2.0)  # ltrb ~ exp(2 +- 1) px so neighbouring boxes overlap
+    return sd
+
+
+def fcos_state_dict(calibrated=True):
+    sd = base_state_dict(fcos_template_state_dict())
+    if calibrated:
+        if not os.path.exists(FCOS_CALIB_PATH):
+            raise FileNotFoundError(f'{FCOS_CALIB_PATH} missing: run tools/make_golden.py in the build container')
+        sd = fcos_apply_calibration(sd, np.load(FCOS_CALIB_PATH))
+    return sd
+
+
+def build_fcos(calibrated=True):
+    from . import fcos_models as FM
+    dictionary = [{f'c{i}': 1.0} for i in range(80)]
+    model = FM.FCOS(dictionary=dictionary, model_cfg=dict(FCOS_CFG))
+    model.load_state_dict(fcos_state_dict(calibrated), strict=True)
+    model.eval()
     return model

@@ -82,7 +82,9 @@ typedef struct CvbConvDesc {
                            out.W + n - 1, c_pitch == C) and the GEMM K chunk of filter row ky is the n adjacent
                            pixels starting at the output column, i.e. the packed weights are
                            [2][cout_pad][kh * n*C] with k = ky*n*C + kx*C + c and zeros for kx >= kw.
-                           n*C must be 32 or 64. */
+                           n*C must be 32 or 64.  Filter row ky reads input row h + ky - pad (rows outside the tensor are zero);
+                           out.H is taken from the output view (allows the asymmetric 2-above/1-below padding of the
+                           7x7/s2/p3 ResNet stem expressed as 4 rows over the space-to-depth input). */
 } CvbConvDesc;
 
 typedef struct CvbConvPlan CvbConvPlan;
@@ -106,10 +108,29 @@ int cvb_f32nhwc_to_nchw(const CvbView* src, float* dst, void* stream);
  * Stem input adapter: NCHW fp32 [B,3,H,W] -> space-to-depth split16 [B,H/2,W/2,16] (12 used,
  * channel = (dy*2+dx)*3 + c, 4 zero pad) so that the 6x6/s2/p2 stem conv
  * (src/models/backbones/det/yolov5_csp_darknet.py:36-45) becomes a 3x3/s1/p1 tensor-core conv.
- * dst may also be the zero-padded row-window layout [B,H/2,W/2+3,16] (data in columns 1..W/2; the pad columns must
- * already be zero) consumed by a CvbConvDesc with w_window = 4.
+ * dst may also be a zero-padded row-window layout [B,H/2,W/2+3,16] (data in columns pad_left..pad_left+W/2-1; the pad
+ * columns must already be zero) consumed by a CvbConvDesc with w_window = 4: pad_left = 1 for the YOLOv5 6x6 stem,
+ * pad_left = 2 for the ResNet 7x7/s2/p3 stem (== 4x4 taps over the space-to-depth input, torchvision resnet conv1).
  */
-int cvb_stem_s2d(const float* src, int32_t B, int32_t H, int32_t W, const CvbView* dst, void* stream);
+int cvb_stem_s2d(const float* src, int32_t B, int32_t H, int32_t W, const CvbView* dst, int32_t pad_left, void* stream);
+
+/*
+ * ResNet stem max pool 3x3 / stride 2 / pad 1 on a split16 tensor.
+ * replaces: nn.MaxPool2d(3, 2, 1) of torchvision.models.resnet (src/models/backbones/seg/resnet.py:80-83).
+ */
+int cvb_maxpool3x3s2(const CvbView* x, const CvbView* y, void* stream);
+
+/* split16 -> fp32 NHWC copy (an FPN level that is both a conv input and an upsampled partial of the next level) */
+int cvb_split_to_f32nhwc(const CvbView* x, const CvbView* y, void* stream);
+
+/*
+ * GroupNorm with 8 channels per group (+ optional ReLU), per-sample statistics, split16 in/out.
+ * replaces: nn.GroupNorm(32, 256) + nn.ReLU of the FCOS head towers (src/models/heads/fcos_head.py:39-50).
+ * workspace: cvb_groupnorm_workspace_bytes(B, groups) bytes (fp64 sums), caller-owned.
+ */
+size_t cvb_groupnorm_workspace_bytes(int32_t B, int32_t groups);
+int cvb_groupnorm_relu(const CvbView* x, int32_t groups, const float* gamma, const float* beta, float eps, int32_t relu,
+                       const CvbView* y, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
  * SPPF pooling: y1=maxpool5(x), y2=maxpool5(y1), y3=maxpool5(y2) (stride 1, pad 2), written to
@@ -157,6 +178,29 @@ size_t cvb_nms_workspace_bytes(int32_t B, int32_t A, int32_t nc);
 int cvb_nms_workspace_reset(void* workspace, size_t workspace_bytes, int32_t B, void* stream);
 int cvb_yolo_nms(const float* prediction, const CvbNmsParams* p, float* det, int32_t* det_idx, int32_t* det_count,
                  void* workspace, size_t workspace_bytes, int32_t* status, void* stream);
+
+/*
+ * FCOS decode of one pyramid level.  cls: fp32 NHWC [B,h,w,>=nc] logits; regcnt: fp32 NHWC [B,h,w,>=5] = (l,t,r,b raw
+ * regression, centerness logit).  Writes at location offset loc_off (of n_total locations per image):
+ *   scores[B,n_total] = sqrt(max_c sigmoid(cls) * sigmoid(cnt)), classes[B,n_total] = argmax + 1 (first maximum),
+ *   boxes[B,n_total,4] = (cx - exp(l*scale), cy - exp(t*scale), cx + exp(r*scale), cy + exp(b*scale)),
+ *   (cx, cy) = (x*stride + stride/2, y*stride + stride/2).
+ * replaces: FCOSDetect.forward / _reshape_cat_out / _coords2boxes / coords_fmap2orig
+ *           (src/models/detects/fcos_detect.py:42-62,14-31,155-186) and ScaleExp (src/models/heads/fcos_head.py:13-19).
+ */
+int cvb_fcos_decode(const CvbView* cls, const CvbView* regcnt, int32_t nc, float stride, float scale, float* scores,
+                    int32_t* classes, float* boxes, int64_t n_total, int64_t loc_off, void* stream);
+
+/*
+ * FCOS post-processing, one image per CTA, no host sync: top-k by score (ties: lower location index), score >= thres,
+ * class offset = cls * (max candidate coordinate + 1), greedy NMS with '+1' areas keeping boxes with iou <= thres (fp32).
+ * Outputs are fixed capacity [B,topk] (+ out_count[B]); out_loc = kept location indices ("NMS-surviving box index").
+ * replaces: torch.topk + FCOSDetect._post_process / batched_nms / box_nms (src/models/detects/fcos_detect.py:64-153; the
+ *           reference's python while-loop with .item() per kept box, and its torch.stack that needs equal counts).
+ */
+int cvb_fcos_nms(const float* scores, const int32_t* classes, const float* boxes, int32_t B, int32_t N, float score_thres,
+                 float iou_thres, int32_t topk, float* out_scores, int32_t* out_classes, float* out_boxes, int32_t* out_loc,
+                 int32_t* out_count, int32_t* status, void* stream);
 
 /* Library info / errors */
 const char* cvb_last_error_string(void);
