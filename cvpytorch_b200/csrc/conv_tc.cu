@@ -559,8 +559,8 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   const CvbView& in = d->in;
   const CvbView& out = d->out;
   CVB_REQUIRE(in.base && out.base && d->weights && d->bias, "conv: null tensor pointer");
-  CVB_REQUIRE(d->kh >= 1 && d->kw >= 1 && d->kh * d->kw <= kMaxTaps, "conv: kernel %dx%d unsupported (max %d taps)", d->kh, d->kw,
-              kMaxTaps);
+  CVB_REQUIRE(d->kh >= 1 && d->kw >= 1 && (d->w_window > 0 ? d->kh : d->kh * d->kw) <= kMaxTaps,
+              "conv: kernel %dx%d unsupported (max %d taps)", d->kh, d->kw, kMaxTaps);
   CVB_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride %d unsupported", d->stride);
   CVB_REQUIRE(d->dilation >= 1, "conv: bad dilation");
   const int win = d->w_window;  // >0: K chunk of a filter row = `win` horizontally adjacent input pixels (see cvb200.h)

@@ -112,7 +112,7 @@ class ResNet(_GraphCache):
         g.conv(x0, resnet_stem_weights_to_s2d(w), b, 4, 1, 2, 'relu', out=c1, w_window=4, name=name + '.stem')
         Hp, Wp = (H // 2 + 2 - 3) // 2 + 1, (W // 2 + 2 - 3) // 2 + 1
         x = g.new_act(Hp, Wp, 64)
-        g.fn(lambda: ops.maxpool3x3s2(c1.view(), x.view()))
+        g.fn(lambda c1=c1, x=x: ops.maxpool3x3s2(c1.view(), x.view()))  # bind now: `x` is re-assigned below
         outs = []
         for li in range(1, 5):
             for bi, blk in enumerate(getattr(self, f'layer{li}')):
