@@ -55,6 +55,10 @@ SYMBOLS = {
     'cvb_nms_workspace_bytes': (c_size_t, [c_int32, c_int32, c_int32]),
     'cvb_yolo_nms': (c_int32, [c_void_p, POINTER(CvbNmsParams), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
                                c_void_p, c_void_p]),
+    'cvb_dwconv3x3': (c_int32, [POINTER(CvbView), c_void_p, c_void_p, c_int32, c_int32, POINTER(CvbView), c_void_p]),
+    'cvb_global_avgpool': (c_int32, [POINTER(CvbView), POINTER(CvbView), c_void_p]),
+    'cvb_bilinear_resize': (c_int32, [POINTER(CvbView), POINTER(CvbView), c_void_p]),
+    'cvb_upsample_argmax': (c_int32, [POINTER(CvbView), c_int32, c_void_p, c_int32, c_int32, c_void_p]),
     'cvb_fcos_decode': (c_int32, [POINTER(CvbView), POINTER(CvbView), c_int32, c_float, c_float, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_int64, c_void_p]),
     'cvb_fcos_nms': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_float, c_int32, c_void_p, c_void_p, c_void_p,

@@ -456,6 +456,201 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x, int npix, int C, i
   }
 }
 
+// ------------------------------------------------------------------ depthwise 3x3 conv (+folded BN bias, ReLU), dilated
+// One thread per (output pixel, 8-channel vector): 9 taps x (hi, lo) 16-byte loads, fp32 accumulate, hi/lo split on store.
+// weights: fp32 [9][C] (tap-major, BN scale folded), bias fp32 [C].  HBM/L2-bound (AI ~ 2 flop/B): no tensor cores.
+__global__ void dwconv3x3_kernel(const __half* __restrict__ x, int B, int H, int W, int C, int xp, long long xplane,
+                                 const float* __restrict__ wgt, const float* __restrict__ bias, int dil, int relu,
+                                 __half* __restrict__ y, int yp, long long yplane) {
+  const int cv = C / 8;
+  const long long n = (long long)B * H * W * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    long long t = i / cv;
+    const int w = (int)(t % W);
+    t /= W;
+    const int h = (int)(t % H);
+    const int b = (int)(t / H);
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = __ldg(bias + c8 * 8 + k);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int hh = h + (ky - 1) * dil;
+      if (hh < 0 || hh >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ww = w + (kx - 1) * dil;
+        if (ww < 0 || ww >= W) continue;
+        const size_t o = (((size_t)b * H + hh) * W + ww) * xp + c8 * 8;
+        const uint4 hv = __ldg(reinterpret_cast<const uint4*>(x + o));
+        const uint4 lv = __ldg(reinterpret_cast<const uint4*>(x + o + xplane));
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wgt + (ky * 3 + kx) * C + c8 * 8));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wgt + (ky * 3 + kx) * C + c8 * 8 + 4));
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const uint32_t* hw = reinterpret_cast<const uint32_t*>(&hv);
+        const uint32_t* lw = reinterpret_cast<const uint32_t*>(&lv);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+          const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+          acc[2 * e] = fmaf(hf.x + lf.x, wv[2 * e], acc[2 * e]);
+          acc[2 * e + 1] = fmaf(hf.y + lf.y, wv[2 * e + 1], acc[2 * e + 1]);
+        }
+      }
+    }
+    uint32_t oh[4], ol[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float v0 = acc[2 * e], v1 = acc[2 * e + 1];
+      if (relu) {
+        v0 = fmaxf(v0, 0.0f);
+        v1 = fmaxf(v1, 0.0f);
+      }
+      __half h0, l0, h1, l1;
+      split_f32(v0, &h0, &l0);
+      split_f32(v1, &h1, &l1);
+      oh[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      ol[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    const size_t oo = (((size_t)b * H + h) * W + w) * yp + c8 * 8;
+    *reinterpret_cast<uint4*>(y + oo) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+    *reinterpret_cast<uint4*>(y + oo + yplane) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+  }
+}
+
+// ------------------------------------------------------------------ global average pool -> [B,1,1,C]
+__global__ void global_avgpool_kernel(const __half* __restrict__ x, int npix, int C, int xp, long long xplane, __half* __restrict__ y,
+                                      int yp, long long yplane) {
+  // grid (C/8, B), block 256: each thread strides over pixels for one 8-channel vector; block reduce
+  __shared__ float red[8][256];
+  const int c8 = blockIdx.x, b = blockIdx.y;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int p = threadIdx.x; p < npix; p += blockDim.x) {
+    const size_t o = ((size_t)b * npix + p) * xp + c8 * 8;
+    const uint4 hv = __ldg(reinterpret_cast<const uint4*>(x + o));
+    const uint4 lv = __ldg(reinterpret_cast<const uint4*>(x + o + xplane));
+    const uint32_t* hw = reinterpret_cast<const uint32_t*>(&hv);
+    const uint32_t* lw = reinterpret_cast<const uint32_t*>(&lv);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+      const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+      acc[2 * e] += hf.x + lf.x;
+      acc[2 * e + 1] += hf.y + lf.y;
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) red[k][threadIdx.x] = acc[k];
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red[k][threadIdx.x] += red[k][threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x < 8) {
+    __half h, l;
+    split_f32(red[threadIdx.x][0] / (float)npix, &h, &l);
+    y[(size_t)b * yp + c8 * 8 + threadIdx.x] = h;
+    y[(size_t)b * yp + c8 * 8 + threadIdx.x + yplane] = l;
+  }
+}
+
+// ------------------------------------------------------------------ bilinear resize (align_corners = False), split16 -> split16
+// PyTorch semantics (F.interpolate / upsample_bilinear2d): src = max((dst + 0.5) * in/out - 0.5, 0), i1 = min(i0 + 1, in - 1).
+__device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, int* i0, int* i1, float* l1) {
+  float s = fmaxf(((float)dst + 0.5f) * scale - 0.5f, 0.0f);
+  int a = (int)s;
+  if (a > in_size - 1) a = in_size - 1;
+  *i0 = a;
+  *i1 = a + ((a < in_size - 1) ? 1 : 0);
+  *l1 = s - (float)a;
+}
+
+__global__ void bilinear_resize_kernel(const __half* __restrict__ x, int B, int Hi, int Wi, int C, int xp, long long xplane,
+                                       __half* __restrict__ y, int Ho, int Wo, int yp, long long yplane) {
+  const int cv = C / 8;
+  const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
+  const long long n = (long long)B * Ho * Wo * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % cv);
+    long long t = i / cv;
+    const int wo = (int)(t % Wo);
+    t /= Wo;
+    const int ho = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    int h0, h1, w0, w1;
+    float lh, lw_;
+    bilinear_src(ho, sh, Hi, &h0, &h1, &lh);
+    bilinear_src(wo, sw, Wi, &w0, &w1, &lw_);
+    const float wgt[4] = {(1.0f - lh) * (1.0f - lw_), (1.0f - lh) * lw_, lh * (1.0f - lw_), lh * lw_};
+    const int hs[4] = {h0, h0, h1, h1}, ws[4] = {w0, w1, w0, w1};
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const size_t o = (((size_t)b * Hi + hs[k]) * Wi + ws[k]) * xp + c8 * 8;
+      const uint4 hv = __ldg(reinterpret_cast<const uint4*>(x + o));
+      const uint4 lv = __ldg(reinterpret_cast<const uint4*>(x + o + xplane));
+      const uint32_t* hw = reinterpret_cast<const uint32_t*>(&hv);
+      const uint32_t* lw = reinterpret_cast<const uint32_t*>(&lv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hw[e]));
+        const float2 lf = __half22float2(*reinterpret_cast<const __half2*>(&lw[e]));
+        acc[2 * e] = fmaf(hf.x + lf.x, wgt[k], acc[2 * e]);
+        acc[2 * e + 1] = fmaf(hf.y + lf.y, wgt[k], acc[2 * e + 1]);
+      }
+    }
+    uint32_t oh[4], ol[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      __half a0, b0, a1, b1;
+      split_f32(acc[2 * e], &a0, &b0);
+      split_f32(acc[2 * e + 1], &a1, &b1);
+      oh[e] = (uint32_t)__half_as_ushort(a0) | ((uint32_t)__half_as_ushort(a1) << 16);
+      ol[e] = (uint32_t)__half_as_ushort(b0) | ((uint32_t)__half_as_ushort(b1) << 16);
+    }
+    const size_t oo = (((size_t)b * Ho + ho) * Wo + wo) * yp + c8 * 8;
+    *reinterpret_cast<uint4*>(y + oo) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+    *reinterpret_cast<uint4*>(y + oo + yplane) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+  }
+}
+
+// ------------------------------------------------------------------ fused bilinear upsample + argmax over classes
+// logits fp32 NHWC [B,hi,wi,pitch>=nc] -> labels int64 [B,Ho,Wo].  The [B,nc,Ho,Wo] fp32 tensor the reference materialises
+// (2.55 GB at 16x19x1024x2048, segmentors/encoder_decoder.py:132-133) never exists.  First maximum wins (torch.argmax).
+__global__ void upsample_argmax_kernel(const float* __restrict__ lg, int B, int Hi, int Wi, int pitch, int nc, long long* __restrict__ out,
+                                       int Ho, int Wo) {
+  const float sh = (float)Hi / (float)Ho, sw = (float)Wi / (float)Wo;
+  const long long n = (long long)B * Ho * Wo;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int wo = (int)(i % Wo);
+    long long t = i / Wo;
+    const int ho = (int)(t % Ho);
+    const int b = (int)(t / Ho);
+    int h0, h1, w0, w1;
+    float lh, lw_;
+    bilinear_src(ho, sh, Hi, &h0, &h1, &lh);
+    bilinear_src(wo, sw, Wi, &w0, &w1, &lw_);
+    const float* p00 = lg + (((size_t)b * Hi + h0) * Wi + w0) * pitch;
+    const float* p01 = lg + (((size_t)b * Hi + h0) * Wi + w1) * pitch;
+    const float* p10 = lg + (((size_t)b * Hi + h1) * Wi + w0) * pitch;
+    const float* p11 = lg + (((size_t)b * Hi + h1) * Wi + w1) * pitch;
+    const float a00 = (1.0f - lh) * (1.0f - lw_), a01 = (1.0f - lh) * lw_, a10 = lh * (1.0f - lw_), a11 = lh * lw_;
+    float best = -CUDART_INF_F;
+    int bi = 0;
+    for (int c = 0; c < nc; ++c) {
+      const float v = a00 * __ldg(p00 + c) + a01 * __ldg(p01 + c) + a10 * __ldg(p10 + c) + a11 * __ldg(p11 + c);
+      if (v > best) {
+        best = v;
+        bi = c;
+      }
+    }
+    out[i] = (long long)bi;
+  }
+}
+
 static int check_split_view(const CvbView* v, const char* what) {
   CVB_REQUIRE(v != nullptr && v->base != nullptr, "%s: null view", what);
   CVB_REQUIRE(v->c_pitch >= v->C && v->plane_stride % 2 == 0, "%s: bad view", what);
@@ -641,5 +836,65 @@ extern "C" int cvb_groupnorm_relu(const CvbView* x, int32_t groups, const float*
                                                       static_cast<__half*>(y->base), y->c_pitch, y->plane_stride / 2);
   CVB_CHECK_CUDA(cudaGetLastError());
   count_launch(2);
+  return CVB_OK;
+}
+
+extern "C" int cvb_dwconv3x3(const CvbView* x, const float* weights, const float* bias, int32_t dilation, int32_t relu, const CvbView* y,
+                             void* stream) {
+  int rc = check_vec_view(x, "dwconv x");
+  if (!rc) rc = check_vec_view(y, "dwconv y");
+  if (rc) return rc;
+  CVB_REQUIRE(weights && bias && dilation >= 1, "dwconv3x3: bad argument");
+  CVB_REQUIRE(y->B == x->B && y->H == x->H && y->W == x->W && y->C == x->C, "dwconv3x3: output view mismatch (stride 1, 'same' padding)");
+  CVB_REQUIRE((reinterpret_cast<uintptr_t>(weights) & 15) == 0, "dwconv3x3: weights must be 16-byte aligned");
+  const long long n = (long long)x->B * x->H * x->W * (x->C / 8);
+  long long grid = (n + 255) / 256;
+  if (grid > 148 * 32) grid = 148 * 32;
+  dwconv3x3_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(static_cast<const __half*>(x->base), x->B, x->H, x->W, x->C, x->c_pitch,
+                                                            x->plane_stride / 2, weights, bias, dilation, relu, static_cast<__half*>(y->base),
+                                                            y->c_pitch, y->plane_stride / 2);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}
+
+extern "C" int cvb_global_avgpool(const CvbView* x, const CvbView* y, void* stream) {
+  int rc = check_vec_view(x, "avgpool x");
+  if (!rc) rc = check_split_view(y, "avgpool y");
+  if (rc) return rc;
+  CVB_REQUIRE(y->B == x->B && y->H == 1 && y->W == 1 && y->C == x->C, "global_avgpool: output must be [B,1,1,C]");
+  global_avgpool_kernel<<<dim3(x->C / 8, x->B), 256, 0, as_stream(stream)>>>(static_cast<const __half*>(x->base), x->H * x->W, x->C, x->c_pitch,
+                                                                            x->plane_stride / 2, static_cast<__half*>(y->base), y->c_pitch,
+                                                                            y->plane_stride / 2);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}
+
+extern "C" int cvb_bilinear_resize(const CvbView* x, const CvbView* y, void* stream) {
+  int rc = check_vec_view(x, "bilinear x");
+  if (!rc) rc = check_vec_view(y, "bilinear y");
+  if (rc) return rc;
+  CVB_REQUIRE(y->B == x->B && y->C == x->C, "bilinear_resize: batch/channel mismatch");
+  const long long n = (long long)y->B * y->H * y->W * (y->C / 8);
+  long long grid = (n + 255) / 256;
+  if (grid > 148 * 32) grid = 148 * 32;
+  bilinear_resize_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(static_cast<const __half*>(x->base), x->B, x->H, x->W, x->C, x->c_pitch,
+                                                                  x->plane_stride / 2, static_cast<__half*>(y->base), y->H, y->W, y->c_pitch,
+                                                                  y->plane_stride / 2);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}
+
+extern "C" int cvb_upsample_argmax(const CvbView* logits, int32_t nc, int64_t* labels, int32_t Ho, int32_t Wo, void* stream) {
+  CVB_REQUIRE(logits && logits->base && labels && nc > 0 && logits->c_pitch >= nc && Ho > 0 && Wo > 0, "upsample_argmax: bad argument");
+  const long long n = (long long)logits->B * Ho * Wo;
+  long long grid = (n + 255) / 256;
+  if (grid > 148 * 32) grid = 148 * 32;
+  upsample_argmax_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(static_cast<const float*>(logits->base), logits->B, logits->H, logits->W,
+                                                                  logits->c_pitch, nc, reinterpret_cast<long long*>(labels), Ho, Wo);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
   return CVB_OK;
 }

@@ -76,16 +76,45 @@ def resnet_stem_weights_to_s2d(w64):
     return out
 
 
+def deep_stem_weights_to_s2d(w64):
+    """3x3/s2/p1 kernel [O,3,3,3] -> 2x2 kernel over the 16-channel space-to-depth input (rows h-1..h, cols w-1..w):
+    filter row ky = 2*(a-1)+dy+1 with a in 0..1; (a=0,dy=0) has no source tap."""
+    O, I, kh, kw = w64.shape
+    assert (I, kh, kw) == (3, 3, 3)
+    out = torch.zeros((O, 16, 2, 2), dtype=torch.float64)
+    for a in range(2):
+        for dy in range(2):
+            ky = 2 * (a - 1) + dy + 1
+            if not 0 <= ky < 3:
+                continue
+            for b in range(2):
+                for dx in range(2):
+                    kx = 2 * (b - 1) + dx + 1
+                    if not 0 <= kx < 3:
+                        continue
+                    for c in range(3):
+                        out[:, (dy * 2 + dx) * 3 + c, a, b] = w64[:, c, ky, kx]
+    return out
+
+
 class ResNet(_GraphCache):
     def __init__(self, subtype='resnet50', out_stages=[2, 3, 4], output_stride=32, frozen_stages=-1, norm_eval=False, conv_cfg=None,
                  norm_cfg=dict(type='BN', requires_grad=True), classifier=False, num_classes=1000, backbone_path=None, pretrained=True):
         super().__init__()
-        if subtype != 'resnet50':
-            raise NotImplementedError(f'{subtype}: only resnet50 (non-deep stem) is on the B200 hot path in this round')
-        if classifier or output_stride != 32:
-            raise NotImplementedError('classifier head / dilated variants are not on the B200 hot path')
+        if subtype not in ('resnet50', 'resnet50v1c'):
+            raise NotImplementedError(f'{subtype}: only resnet50 / resnet50v1c are on the B200 hot path in this round')
+        if classifier:
+            raise NotImplementedError('classifier head is not on the B200 hot path')
+        # output_stride 8/16 is accepted and ignored exactly like the reference does for resnet50 (its dilation branch only
+        # matches 'resnet18'/'resnet34' subtypes, src/models/backbones/seg/resnet.py:102-118; SURVEY.md 3.3).
         self.subtype, self.out_stages = subtype, out_stages
-        self.stem = nn.Sequential(nn.Conv2d(3, 64, 7, 2, 3, bias=False), nn.BatchNorm2d(64), nn.ReLU(inplace=True))
+        self.deep_stem = subtype.endswith('c')
+        if self.deep_stem:  # resnet.py:67-79
+            self.stem = nn.Sequential(nn.Conv2d(3, 32, 3, 2, 1, bias=False), nn.BatchNorm2d(32), nn.ReLU(inplace=True),
+                                      nn.Conv2d(32, 32, 3, 1, 1, bias=False), nn.BatchNorm2d(32), nn.ReLU(inplace=True),
+                                      nn.Conv2d(32, 64, 3, 1, 1, bias=False), nn.BatchNorm2d(64), nn.ReLU(inplace=True))
+        else:
+            self.stem = nn.Sequential(nn.Conv2d(3, 64, 7, 2, 3, bias=False), nn.BatchNorm2d(64), nn.ReLU(inplace=True))
         self.maxpool = nn.MaxPool2d(3, 2, 1)
         inplanes = 64
         for li, (planes, blocks, stride) in enumerate(((64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)), start=1):
@@ -106,10 +135,18 @@ class ResNet(_GraphCache):
 
     def emit(self, g, img_getter, H, W, name='backbone'):
         x0 = g.new_act(H // 2, W // 2 + 3, 16)
-        g.fn(lambda: ops.stem_s2d(img_getter(), x0.view(), pad_left=2))
-        w, b = folded(self.stem[0], self.stem[1])
-        c1 = g.new_act(H // 2, W // 2, 64)
-        g.conv(x0, resnet_stem_weights_to_s2d(w), b, 4, 1, 2, 'relu', out=c1, w_window=4, name=name + '.stem')
+        if self.deep_stem:
+            g.fn(lambda: ops.stem_s2d(img_getter(), x0.view(), pad_left=1))
+            w, b = folded(self.stem[0], self.stem[1])
+            t = g.new_act(H // 2, W // 2, 32)
+            g.conv(x0, deep_stem_weights_to_s2d(w), b, 2, 1, 1, 'relu', out=t, w_window=4, name=name + '.stem.0')
+            t = g.conv(t, *folded(self.stem[3], self.stem[4]), 3, 1, 1, 'relu', name=name + '.stem.3')
+            c1 = g.conv(t, *folded(self.stem[6], self.stem[7]), 3, 1, 1, 'relu', name=name + '.stem.6')
+        else:
+            g.fn(lambda: ops.stem_s2d(img_getter(), x0.view(), pad_left=2))
+            w, b = folded(self.stem[0], self.stem[1])
+            c1 = g.new_act(H // 2, W // 2, 64)
+            g.conv(x0, resnet_stem_weights_to_s2d(w), b, 4, 1, 2, 'relu', out=c1, w_window=4, name=name + '.stem')
         Hp, Wp = (H // 2 + 2 - 3) // 2 + 1, (W // 2 + 2 - 3) // 2 + 1
         x = g.new_act(Hp, Wp, 64)
         g.fn(lambda c1=c1, x=x: ops.maxpool3x3s2(c1.view(), x.view()))  # bind now: `x` is re-assigned below

@@ -57,8 +57,11 @@ class ConvModule(_EmitModule):
                  conv_cfg=None, norm_cfg=None, act_cfg=dict(type='ReLU'), inplace=True, with_spectral_norm=False,
                  padding_mode='zeros', order=('conv', 'norm', 'act')):
         super().__init__()
-        if groups != 1 or with_spectral_norm or padding_mode != 'zeros' or tuple(order) != ('conv', 'norm', 'act'):
+        if with_spectral_norm or padding_mode != 'zeros' or tuple(order) != ('conv', 'norm', 'act'):
             raise NotImplementedError('ConvModule variant not on the B200 hot path')
+        if groups != 1 and not (groups == in_channels == out_channels and kernel_size == 3 and stride == 1 and padding == dilation):
+            raise NotImplementedError('grouped conv: only depthwise 3x3 / stride 1 / padding == dilation is on the B200 hot path')
+        self.groups = groups
         if conv_cfg is not None and conv_cfg.get('type') not in (None, 'Conv2d', 'Conv', 'B200Conv2d'):
             raise NotImplementedError(f'conv_cfg {conv_cfg}')
         if norm_cfg is not None and norm_cfg.get('type') not in ('BN', 'BN2d'):
@@ -69,7 +72,7 @@ class ConvModule(_EmitModule):
             bias = not self.with_norm  # conv_module.py:108-110
         self.in_channels, self.out_channels = in_channels, out_channels
         self.kernel_size, self.stride, self.padding, self.dilation = kernel_size, stride, padding, dilation
-        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, dilation, bias=bias)
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size, stride, padding, dilation, groups=groups, bias=bias)
         if self.with_norm:
             self.bn = nn.BatchNorm2d(out_channels, eps=norm_cfg.get('eps', 1e-5), momentum=norm_cfg.get('momentum', 0.1))
         self.act_name = _act_name(act_cfg)
@@ -77,7 +80,35 @@ class ConvModule(_EmitModule):
 
     def emit(self, g, x, name='', **kw):
         w, b = folded(self.conv, self.bn if self.with_norm else None)
+        if self.groups != 1:  # depthwise: HBM-bound SIMT kernel (no tensor cores for 9 MACs per output)
+            if self.act_name not in (None, 'relu'):
+                raise NotImplementedError('depthwise conv: ReLU / no activation only')
+            out = kw.get('out') or g.new_act(x.H, x.W, x.c)
+            w9c, bias = ops.pack_dw_weights(w, b, device=g.device)
+            g.buffers.append((w9c, bias))
+            dil, relu = self.dilation, self.act_name == 'relu'
+            g.fn(lambda: ops.dwconv3x3(x.view(), w9c, bias, dil, out.view(), relu))
+            return out
         return g.conv(x, w, b, self.kernel_size, self.stride, self.padding, self.act_name, dilation=self.dilation, name=name, **kw)
+
+
+class DepthwiseSeparableConvModule(_EmitModule):
+    """src/models/bricks/depthwise_separable_conv_module.py:10-99: depthwise ConvModule + pointwise ConvModule."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, norm_cfg=None, act_cfg=dict(type='ReLU'),
+                 dw_norm_cfg='default', dw_act_cfg='default', pw_norm_cfg='default', pw_act_cfg='default', **kwargs):
+        super().__init__()
+        dw_norm_cfg = dw_norm_cfg if dw_norm_cfg != 'default' else norm_cfg
+        dw_act_cfg = dw_act_cfg if dw_act_cfg != 'default' else act_cfg
+        pw_norm_cfg = pw_norm_cfg if pw_norm_cfg != 'default' else norm_cfg
+        pw_act_cfg = pw_act_cfg if pw_act_cfg != 'default' else act_cfg
+        self.depthwise_conv = ConvModule(in_channels, in_channels, kernel_size, stride=stride, padding=padding, dilation=dilation,
+                                         groups=in_channels, norm_cfg=dw_norm_cfg, act_cfg=dw_act_cfg, **kwargs)
+        self.pointwise_conv = ConvModule(in_channels, out_channels, 1, norm_cfg=pw_norm_cfg, act_cfg=pw_act_cfg, **kwargs)
+
+    def emit(self, g, x, name='', out=None):
+        d = self.depthwise_conv.emit(g, x, name + '.depthwise_conv')
+        return self.pointwise_conv.emit(g, d, name + '.pointwise_conv', out=out)
 
 
 class Conv(_EmitModule):

@@ -304,3 +304,29 @@ def fcos_nms(ws, score_thres=0.05, iou_thres=0.6, scores=None, classes=None, box
                                        ws.out_scores.data_ptr(), ws.out_classes.data_ptr(), ws.out_boxes.data_ptr(), ws.out_loc.data_ptr(),
                                        ws.out_count.data_ptr(), ws.status.data_ptr(), _stream()), 'cvb_fcos_nms')
     return ws.out_scores, ws.out_classes, ws.out_boxes, ws.out_loc, ws.out_count
+
+
+# --------------------------------------------------------------------------------------- DeepLab helpers
+def pack_dw_weights(w64, b64, device='cuda'):
+    """depthwise [C,1,3,3] float64 (BN folded) -> fp32 [9, C] tap-major + fp32 bias [C]."""
+    C = w64.shape[0]
+    return w64.reshape(C, 9).t().contiguous().float().to(device), b64.float().to(device)
+
+
+def dwconv3x3(x_view, w9c, bias, dilation, y_view, relu=True):
+    _lib.check(_lib.lib().cvb_dwconv3x3(byref(x_view), w9c.data_ptr(), bias.data_ptr(), dilation, 1 if relu else 0, byref(y_view), _stream()),
+               'cvb_dwconv3x3')
+
+
+def global_avgpool(x_view, y_view):
+    _lib.check(_lib.lib().cvb_global_avgpool(byref(x_view), byref(y_view), _stream()), 'cvb_global_avgpool')
+
+
+def bilinear_resize(x_view, y_view):
+    _lib.check(_lib.lib().cvb_bilinear_resize(byref(x_view), byref(y_view), _stream()), 'cvb_bilinear_resize')
+
+
+def upsample_argmax(logits_view, nc, labels):
+    B, Ho, Wo = labels.shape
+    assert labels.dtype == torch.int64 and labels.is_contiguous()
+    _lib.check(_lib.lib().cvb_upsample_argmax(byref(logits_view), nc, labels.data_ptr(), Ho, Wo, _stream()), 'cvb_upsample_argmax')

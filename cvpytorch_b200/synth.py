@@ -179,3 +179,51 @@ def build_fcos(calibrated=True):
     model.load_state_dict(fcos_state_dict(calibrated), strict=True)
     model.eval()
     return model
+
+
+# ================================================================================================= DeepLabv3+ R50v1c
+DEEPLAB_CALIB_PATH = os.path.join(os.path.dirname(CALIB_PATH), 'deeplab_calib.npz')
+DEEPLAB_CFG = {'BACKBONE': {'name': 'ResNet', 'subtype': 'resnet50v1c', 'out_stages': [1, 4], 'output_stride': 8, 'pretrained': True},
+               'NECK': None, 'AUX_HEAD': None,
+               'HEAD': {'name': 'Deeplabv3PlusHead', 'num_classes': 19, 'in_channels': 2048, 'channels': 512, 'dilations': [1, 12, 24, 36],
+                        'low_in_channels': 256, 'low_channels': 48},
+               'LOSS': {'name': 'CrossEntropyLoss2d'}}  # conf/seg/deeplabv3plus/cityscapes_deeplabv3plus_r50.yml:57-62
+
+
+def deeplab_template_state_dict():
+    from . import seg_models as SM
+    bb = SM.build_backbone({**DEEPLAB_CFG['BACKBONE'], 'pretrained': False})
+    hd = SM.build_head(DEEPLAB_CFG['HEAD'])
+    t = {}
+    for p, m in (('backbone.', bb), ('head.', hd)):
+        for k, v in m.state_dict().items():
+            t[p + k] = v
+    return t
+
+
+def deeplab_apply_calibration(sd, calib):
+    for k in list(sd.keys()):
+        if k.endswith('running_mean') or k.endswith('running_var'):
+            sd[k] = torch.from_numpy(np.asarray(calib[k])).float().clone()
+    sd['head.cls_seg.weight'] = sd['head.cls_seg.weight'] * float(np.asarray(calib['cls_scale']))
+    g = _gen('head.cls_seg.bias.synth')
+    sd['head.cls_seg.bias'] = torch.randn(sd['head.cls_seg.bias'].shape, generator=g) * 0.5
+    return sd
+
+
+def deeplab_state_dict(calibrated=True):
+    sd = base_state_dict(deeplab_template_state_dict())
+    if calibrated:
+        if not os.path.exists(DEEPLAB_CALIB_PATH):
+            raise FileNotFoundError(f'{DEEPLAB_CALIB_PATH} missing: run tools/make_golden_deeplab.py in the build container')
+        sd = deeplab_apply_calibration(sd, np.load(DEEPLAB_CALIB_PATH))
+    return sd
+
+
+def build_deeplab(calibrated=True):
+    from . import seg_models as SM
+    dictionary = [{f'c{i}': 1.0} for i in range(19)]
+    model = SM.EncoderDecoder(dictionary=dictionary, model_cfg=dict(DEEPLAB_CFG))
+    model.load_state_dict(deeplab_state_dict(calibrated), strict=True)
+    model.eval()
+    return model

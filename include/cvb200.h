@@ -133,6 +133,27 @@ int cvb_groupnorm_relu(const CvbView* x, int32_t groups, const float* gamma, con
                        const CvbView* y, void* workspace, size_t workspace_bytes, void* stream);
 
 /*
+ * Depthwise 3x3 convolution (stride 1, padding = dilation) + folded-BN bias + optional ReLU, split16 in/out.
+ * weights: fp32 [9][C] tap-major (BN scale folded by the caller), bias fp32 [C].
+ * replaces: the depthwise ConvModule of DepthwiseSeparableConvModule (src/models/bricks/depthwise_separable_conv_module.py:73-99)
+ *           used by DepthwiseSeparableASPPModule / Deeplabv3PlusHead.fuse (src/models/heads/seg/deeplabv3plus_head.py:14-54).
+ */
+int cvb_dwconv3x3(const CvbView* x, const float* weights, const float* bias, int32_t dilation, int32_t relu, const CvbView* y,
+                  void* stream);
+
+/* nn.AdaptiveAvgPool2d(1) of the ASPP image-pool branch (src/models/heads/seg/deeplabv3_head.py:59-62): [B,H,W,C] -> [B,1,1,C] */
+int cvb_global_avgpool(const CvbView* x, const CvbView* y, void* stream);
+
+/* F.interpolate(mode='bilinear', align_corners=False) on split16 tensors, any size (deeplabv3plus_head.py:57,63) */
+int cvb_bilinear_resize(const CvbView* x, const CvbView* y, void* stream);
+
+/*
+ * Fused bilinear upsample (align_corners=False) + argmax over classes: fp32 NHWC logits [B,h,w,>=nc] -> int64 labels [B,Ho,Wo].
+ * replaces: F.interpolate(preds, size=targets.shape[-2:]) + torch.argmax(dim=1) (src/models/segmentors/encoder_decoder.py:132-133).
+ */
+int cvb_upsample_argmax(const CvbView* logits, int32_t nc, int64_t* labels, int32_t Ho, int32_t Wo, void* stream);
+
+/*
  * SPPF pooling: y1=maxpool5(x), y2=maxpool5(y1), y3=maxpool5(y2) (stride 1, pad 2), written to
  * three channel slices.  replaces: SPPF.forward src/models/modules/yolo_modules.py:185-194 /
  * src/models/modules/yolo11_modules.py:282-288 (3 x nn.MaxPool2d + torch.cat).

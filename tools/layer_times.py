@@ -14,13 +14,17 @@ from cvpytorch_b200 import synth  # noqa: E402
 
 def main():
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    which = sys.argv[2] if len(sys.argv) > 2 else 'yolov5s'
     reps = 5
     dev = torch.device('cuda:0')
-    model = synth.build_yolov5s(True)
-    G = model.build_graph(B, 640, 640, dev)
+    if which == 'fcos':
+        model, S = synth.build_fcos(True), 800
+    else:
+        model, S = synth.build_yolov5s(True), 640
+    G = model.build_graph(B, S, S, dev)
     g = G['g']
     torch.manual_seed(1029)
-    G['holder']['x'] = torch.randn(B, 3, 640, 640, device=dev)
+    G['holder']['x'] = torch.randn(B, 3, S, S, device=dev)
     g.run()
     torch.cuda.synchronize()
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
@@ -49,7 +53,7 @@ def main():
             name, cin, cout, k, s, Ho, Wo = g.layer_log[li]
             li += 1
             flops = 2.0 * B * Ho * Wo * cout * cin * k * k
-            in_elems = B * (Ho * s) * (Wo * s) * cin
+            in_elems = B * (Ho * s) * (Wo * s) * cin  # (stem rows report the s2d view)
             byts = 4.0 * (in_elems + B * Ho * Wo * cout) + 4.0 * cout * cin * k * k
             t_tensor = 3 * flops / (P * 1e12) * 1e3
             t_hbm = byts / (BW * 1e9) * 1e3
@@ -60,7 +64,7 @@ def main():
         else:
             rows.append(f'{"<aux step>":34s} {"":31s} {ms:8.4f} ms')
     print('\n'.join(rows))
-    print(f'sum of per-step medians: {tot:.3f} ms  (B={B}); sum of per-layer conv bounds {tot_bound:.3f} ms; peaks: {P} TF/s, {BW} GB/s')
+    print(f'sum of per-step medians: {tot:.3f} ms  (B={B}, {which}) -> {B / tot * 1e3:.0f} img/s; sum of per-layer conv bounds {tot_bound:.3f} ms; peaks: {P} TF/s, {BW} GB/s')
 
 
 if __name__ == '__main__':
