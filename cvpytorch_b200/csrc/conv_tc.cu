@@ -20,6 +20,7 @@
 //   warps 2..9  epilogue (two warps per TMEM lane quarter): tcgen05.ld -> +partial +bias -> act -> +residual -> hi/lo split -> swizzled smem -> TMA store
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <new>
 
@@ -766,7 +767,12 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   {
     // accumulation chains of at most ~48 MMAs (see the MMA issuer); all accumulator sets must fit the 512 TMEM columns
     const int chain = a.taps * cin / 16;
-    int n_main = (chain + 47) / 48;
+    static const int max_chain = [] {
+      const char* e = getenv("CVB_MAX_CHAIN");  // tuning knob: longer chains = fewer accumulators = room for double buffering
+      const int v = e ? atoi(e) : 0;
+      return v >= 8 ? v : 48;
+    }();
+    int n_main = (chain + max_chain - 1) / max_chain;
     if (n_main > 3) n_main = 3;
     while ((n_main + 1) * bn > 512) --n_main;
     if (n_main < 1) {
