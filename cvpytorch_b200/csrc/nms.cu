@@ -26,25 +26,54 @@ constexpr int kCap = 65536;    // candidate key capacity per image
 constexpr int kChunk = 4096;   // keys sorted per CTA in shared memory
 constexpr int kGreedyThreads = 512;
 
+constexpr int kCapA = 4096;    // phase-A (early exit) candidate capacity = one shared-memory sort chunk
+constexpr int kTargetA = 3072; // phase A takes the smallest set of top score bins holding >= this many candidates
+
+// Two-phase scheme: greedy NMS only needs candidates in score order until max_det boxes are kept, so phase A runs the
+// whole pipeline on the top ~3k candidates (one smem sort chunk per image); only images that did not reach max_det there
+// (and have more candidates) go through phase B = the full top-max_nms path.  `done[b]` is decided on the device.
 struct NmsWs {
-  uint32_t* hist;   // [B][kBins]
-  uint32_t* cnt;    // [B]
-  uint32_t* tbin;   // [B]
-  uint64_t* keys;   // [B][kCap]
+  uint32_t* hist;   // [B][kBins]                          (shared by both phases)
+  uint32_t* cnt;    // [B]      candidates emitted in this phase
+  uint32_t* tbin;   // [B]      threshold bin of this phase
+  uint64_t* keys;   // [B][cap]
+  uint32_t* done;   // [B]      set by phase A's greedy kernel
+  uint32_t* total;  // [B]      number of candidates of the image (all bins)
+  int cap;          // kCapA or kCap
+  int phase;        // 0 = A, 1 = B
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static NmsWs carve_ws(void* ws, int B) {
+static size_t ws_head_bytes(int B) { return align_up((size_t)B * kBins * 4, 256) + 6 * align_up((size_t)B * 4, 256); }
+
+static NmsWs carve_ws(void* ws, int B, int phase) {
   NmsWs w;
   uint8_t* p = static_cast<uint8_t*>(ws);
+  const size_t slot = align_up((size_t)B * 4, 256);
   w.hist = reinterpret_cast<uint32_t*>(p);
   p += align_up((size_t)B * kBins * 4, 256);
-  w.cnt = reinterpret_cast<uint32_t*>(p);
-  p += align_up((size_t)B * 4, 256);
-  w.tbin = reinterpret_cast<uint32_t*>(p);
-  p += align_up((size_t)B * 4, 256);
-  w.keys = reinterpret_cast<uint64_t*>(p);
+  uint32_t* cntB = reinterpret_cast<uint32_t*>(p);
+  uint32_t* tbinB = reinterpret_cast<uint32_t*>(p + slot);
+  uint32_t* cntA = reinterpret_cast<uint32_t*>(p + 2 * slot);
+  uint32_t* tbinA = reinterpret_cast<uint32_t*>(p + 3 * slot);
+  w.done = reinterpret_cast<uint32_t*>(p + 4 * slot);
+  w.total = reinterpret_cast<uint32_t*>(p + 5 * slot);
+  p += 6 * slot;
+  uint64_t* keysB = reinterpret_cast<uint64_t*>(p);
+  uint64_t* keysA = keysB + (size_t)B * kCap;
+  w.phase = phase;
+  if (phase == 0) {
+    w.cnt = cntA;
+    w.tbin = tbinA;
+    w.keys = keysA;
+    w.cap = kCapA;
+  } else {
+    w.cnt = cntB;
+    w.tbin = tbinB;
+    w.keys = keysB;
+    w.cap = kCap;
+  }
   return w;
 }
 
@@ -72,6 +101,7 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const float* __r
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
   }
+  if (EMIT && ws.phase == 1 && ws.done[b]) return;  // phase A already produced this image's result
   const uint32_t tb = EMIT ? ws.tbin[b] : 0u;
   constexpr int R = 4;  // rows in flight per warp: all loads of a batch are issued before the first use
   for (int base = row0 + warp * R; base < row1; base += (kScanThreads / 32) * R) {
@@ -202,15 +232,15 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const float* __r
     if (threadIdx.x == 0) s_base = atomicAdd(&ws.cnt[b], n);
     __syncthreads();
     const uint32_t base = s_base;
-    if (base + n > (uint32_t)kCap && status && threadIdx.x == 0) atomicExch(&status[0], 1);
-    uint64_t* keys = ws.keys + (size_t)b * kCap;
+    if (base + n > (uint32_t)ws.cap && ws.phase == 1 && status && threadIdx.x == 0) atomicExch(&status[0], 1);
+    uint64_t* keys = ws.keys + (size_t)b * ws.cap;
     for (uint32_t i = threadIdx.x; i < n; i += kScanThreads)
-      if (base + i < (uint32_t)kCap) keys[base + i] = stage[i];
+      if (base + i < (uint32_t)ws.cap) keys[base + i] = stage[i];
   }
 }
 
 // ------------------------------------------------------------------ threshold bin: smallest set of top bins holding >= max_nms
-__global__ void nms_threshold_kernel(NmsWs ws, int max_nms) {
+__global__ void nms_threshold_kernel(NmsWs ws, int target) {
   __shared__ uint32_t part[256];
   const int b = blockIdx.x;
   const uint32_t* h = ws.hist + (size_t)b * kBins;
@@ -229,13 +259,14 @@ __global__ void nms_threshold_kernel(NmsWs ws, int max_nms) {
       run += v;
     }
     ws.tbin[b] = 0;  // default: everything
+    ws.total[b] = run;
   }
   __syncthreads();
   uint32_t run = part[t];
-  if (run < (uint32_t)max_nms) {
+  if (run < (uint32_t)target) {
     for (int i = 0; i < per; ++i) {
       run += h[hi_bin - i];
-      if (run >= (uint32_t)max_nms) {
+      if (run >= (uint32_t)target) {
         ws.tbin[b] = (uint32_t)(hi_bin - i);  // exactly one thread crosses the threshold
         break;
       }
@@ -246,7 +277,8 @@ __global__ void nms_threshold_kernel(NmsWs ws, int max_nms) {
 // ------------------------------------------------------------------ segmented bitonic sort (descending)
 __device__ __forceinline__ uint32_t seg_npad(const NmsWs& ws, int b, uint32_t* n_out) {
   uint32_t n = ws.cnt[b];
-  if (n > (uint32_t)kCap) n = kCap;
+  if (n > (uint32_t)ws.cap) n = ws.cap;
+  if (ws.phase == 1 && ws.done[b]) n = 0;  // nothing to sort: every chunk beyond the first returns immediately
   *n_out = n;
   return n <= 1 ? 1u : (1u << (32 - __clz(n - 1)));
 }
@@ -267,7 +299,8 @@ __global__ void __launch_bounds__(1024) bitonic_local_sort_kernel(NmsWs ws) {
   const uint32_t npad = seg_npad(ws, b, &n);
   const uint32_t start = blockIdx.x * kChunk;
   if (start >= npad) return;
-  uint64_t* keys = ws.keys + (size_t)b * kCap;
+  if (ws.phase == 1 && ws.done[b]) return;
+  uint64_t* keys = ws.keys + (size_t)b * ws.cap;
   for (int i = threadIdx.x; i < kChunk; i += blockDim.x) s[i] = (start + i < n) ? keys[start + i] : 0ull;
   for (int k = 2; k <= kChunk; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
@@ -290,7 +323,7 @@ __global__ void bitonic_global_step_kernel(NmsWs ws, uint32_t k, uint32_t j) {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t i = 2 * j * (t / j) + (t % j);
   if (i >= npad) return;
-  uint64_t* keys = ws.keys + (size_t)b * kCap;
+  uint64_t* keys = ws.keys + (size_t)b * ws.cap;
   const uint64_t x = keys[i], y = keys[i + j];
   const bool desc = (i & k) == 0;
   if (desc ? (x < y) : (x > y)) {
@@ -308,7 +341,7 @@ __global__ void __launch_bounds__(1024) bitonic_local_merge_kernel(NmsWs ws, uin
   if (k > npad) return;
   const uint32_t start = blockIdx.x * kChunk;
   if (start >= npad) return;
-  uint64_t* keys = ws.keys + (size_t)b * kCap;
+  uint64_t* keys = ws.keys + (size_t)b * ws.cap;
   for (int i = threadIdx.x; i < kChunk; i += blockDim.x) s[i] = keys[start + i];
   for (int j = kChunk >> 1; j > 0; j >>= 1) {
     __syncthreads();
@@ -356,10 +389,15 @@ __global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const float*
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int no = nc + 5;
+  if (ws.phase == 1 && ws.done[b]) return;
   uint32_t n = ws.cnt[b];
-  if (n > (uint32_t)kCap) n = kCap;
+  if (ws.phase == 0 && n > (uint32_t)ws.cap) {  // phase A overflowed its chunk: its key set is incomplete, leave it to phase B
+    if (tid == 0) ws.done[b] = 0;
+    return;
+  }
+  if (n > (uint32_t)ws.cap) n = ws.cap;
   if (n > (uint32_t)max_nms) n = max_nms;
-  const uint64_t* keys = ws.keys + (size_t)b * kCap;
+  const uint64_t* keys = ws.keys + (size_t)b * ws.cap;
   int kept_n = 0;
 
   for (uint32_t base = 0; base < n && kept_n < max_det; base += kGreedyThreads) {
@@ -467,7 +505,11 @@ __global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const float*
     kept_n += nk;
     __syncthreads();
   }
-  if (tid == 0) det_count[b] = kept_n;
+  if (tid == 0) {
+    det_count[b] = kept_n;
+    // phase A is final when max_det boxes were kept, or when it already saw every candidate of the image
+    if (ws.phase == 0) ws.done[b] = (kept_n >= max_det || ws.cnt[b] == ws.total[b]) ? 1u : 0u;
+  }
 }
 
 }  // namespace cvb
@@ -478,13 +520,12 @@ extern "C" size_t cvb_nms_workspace_bytes(int32_t B, int32_t A, int32_t nc) {
   (void)A;
   (void)nc;
   if (B <= 0) return 0;
-  return align_up((size_t)B * kBins * 4, 256) + 2 * align_up((size_t)B * 4, 256) + (size_t)B * kCap * 8;
+  return ws_head_bytes(B) + (size_t)B * (kCap + kCapA) * 8;
 }
 
 extern "C" int cvb_nms_workspace_reset(void* workspace, size_t workspace_bytes, int32_t B, void* stream) {
   CVB_REQUIRE(workspace && B > 0 && workspace_bytes >= cvb_nms_workspace_bytes(B, 1, 1), "nms reset: bad workspace");
-  const size_t head_bytes = align_up((size_t)B * kBins * 4, 256) + 2 * align_up((size_t)B * 4, 256);
-  CVB_CHECK_CUDA(cudaMemsetAsync(workspace, 0, head_bytes, as_stream(stream)));
+  CVB_CHECK_CUDA(cudaMemsetAsync(workspace, 0, ws_head_bytes(B), as_stream(stream)));
   return CVB_OK;
 }
 
@@ -497,9 +538,8 @@ extern "C" int cvb_yolo_nms(const float* prediction, const CvbNmsParams* p, floa
   CVB_REQUIRE(workspace_bytes >= cvb_nms_workspace_bytes(p->B, p->A, p->nc), "nms: workspace too small");
   CVB_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "nms: workspace must be 256-byte aligned");
   cudaStream_t st = as_stream(stream);
-  NmsWs ws = carve_ws(workspace, p->B);
-  const size_t head_bytes = align_up((size_t)p->B * kBins * 4, 256) + 2 * align_up((size_t)p->B * 4, 256);
-  if (!p->hist_ready) CVB_CHECK_CUDA(cudaMemsetAsync(workspace, 0, head_bytes, st));
+  NmsWs wsA = carve_ws(workspace, p->B, 0), wsB = carve_ws(workspace, p->B, 1);
+  if (!p->hist_ready) CVB_CHECK_CUDA(cudaMemsetAsync(workspace, 0, ws_head_bytes(p->B), st));
   if (status) CVB_CHECK_CUDA(cudaMemsetAsync(status, 0, 4 * sizeof(int32_t), st));
   CVB_CHECK_CUDA(cudaMemsetAsync(det, 0, (size_t)p->B * p->max_det * 6 * sizeof(float), st));
   CVB_CHECK_CUDA(cudaMemsetAsync(det_idx, 0xFF, (size_t)p->B * p->max_det * sizeof(int32_t), st));
@@ -507,43 +547,45 @@ extern "C" int cvb_yolo_nms(const float* prediction, const CvbNmsParams* p, floa
   dim3 sgrid(ceil_div(p->A, kRowsPerCta), p->B);
   const size_t stage_bytes = (size_t)kRowsPerCta * p->nc * sizeof(uint64_t);
   CVB_REQUIRE(stage_bytes <= 160 * 1024, "nms: too many classes (%d) for the shared-memory candidate stage", p->nc);
-  static bool scan_attr_set = false;
-  if (!scan_attr_set) {
+  const size_t gsmem = sizeof(GreedySmem) + (size_t)p->max_det * (sizeof(float4) + sizeof(float));
+  CVB_REQUIRE(gsmem <= 200 * 1024, "nms: max_det too large");
+  static bool attr_set = false;
+  if (!attr_set) {
     CVB_CHECK_CUDA(cudaFuncSetAttribute(nms_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    scan_attr_set = true;
+    CVB_CHECK_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
   }
   if (!p->hist_ready) {
-    nms_scan_kernel<false><<<sgrid, kScanThreads, 0, st>>>(prediction, p->B, p->A, p->nc, p->conf_thres, p->multi_label, ws, status);
+    nms_scan_kernel<false><<<sgrid, kScanThreads, 0, st>>>(prediction, p->B, p->A, p->nc, p->conf_thres, p->multi_label, wsB, status);
     count_launch();
   }
-  nms_threshold_kernel<<<p->B, 256, 0, st>>>(ws, p->max_nms);
-  nms_scan_kernel<true><<<sgrid, kScanThreads, stage_bytes, st>>>(prediction, p->B, p->A, p->nc, p->conf_thres, p->multi_label, ws, status);
+  // ---- phase A: the top ~3k candidates of every image (one shared-memory sort chunk), early exit at max_det
+  const int targetA = p->max_nms < kTargetA ? p->max_nms : kTargetA;
+  nms_threshold_kernel<<<p->B, 256, 0, st>>>(wsA, targetA);
+  nms_scan_kernel<true><<<sgrid, kScanThreads, stage_bytes, st>>>(prediction, p->B, p->A, p->nc, p->conf_thres, p->multi_label, wsA, status);
+  bitonic_local_sort_kernel<<<dim3(1, p->B), 1024, 0, st>>>(wsA);
+  nms_greedy_kernel<<<p->B, kGreedyThreads, gsmem, st>>>(prediction, p->A, p->nc, wsA, p->iou_thres, p->max_nms, p->max_det, p->max_wh, det,
+                                                         det_idx, det_count);
   CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch(4);
+  // ---- phase B: full top-max_nms path for the images phase A could not finish (every kernel returns at once otherwise)
+  nms_threshold_kernel<<<p->B, 256, 0, st>>>(wsB, p->max_nms);
+  nms_scan_kernel<true><<<sgrid, kScanThreads, stage_bytes, st>>>(prediction, p->B, p->A, p->nc, p->conf_thres, p->multi_label, wsB, status);
   count_launch(2);
-
   dim3 lgrid(kCap / kChunk, p->B);
-  bitonic_local_sort_kernel<<<lgrid, 1024, 0, st>>>(ws);
+  bitonic_local_sort_kernel<<<lgrid, 1024, 0, st>>>(wsB);
   count_launch();
   for (uint32_t k = 2 * kChunk; k <= (uint32_t)kCap; k <<= 1) {
     for (uint32_t j = k >> 1; j >= (uint32_t)kChunk; j >>= 1) {
       dim3 ggrid(kCap / 2 / 256, p->B);
-      bitonic_global_step_kernel<<<ggrid, 256, 0, st>>>(ws, k, j);
+      bitonic_global_step_kernel<<<ggrid, 256, 0, st>>>(wsB, k, j);
       count_launch();
     }
-    bitonic_local_merge_kernel<<<lgrid, 1024, 0, st>>>(ws, k);
+    bitonic_local_merge_kernel<<<lgrid, 1024, 0, st>>>(wsB, k);
     count_launch();
   }
-  CVB_CHECK_CUDA(cudaGetLastError());
-
-  const size_t smem = sizeof(GreedySmem) + (size_t)p->max_det * (sizeof(float4) + sizeof(float));
-  static bool attr_set = false;
-  if (!attr_set) {
-    CVB_CHECK_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
-  CVB_REQUIRE(smem <= 200 * 1024, "nms: max_det too large");
-  nms_greedy_kernel<<<p->B, kGreedyThreads, smem, st>>>(prediction, p->A, p->nc, ws, p->iou_thres, p->max_nms, p->max_det,
-                                                        p->max_wh, det, det_idx, det_count);
+  nms_greedy_kernel<<<p->B, kGreedyThreads, gsmem, st>>>(prediction, p->A, p->nc, wsB, p->iou_thres, p->max_nms, p->max_det, p->max_wh, det,
+                                                         det_idx, det_count);
   CVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return CVB_OK;
