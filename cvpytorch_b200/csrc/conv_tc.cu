@@ -39,6 +39,7 @@ struct alignas(64) ConvKArgs {
   CUtensorMap tmA[4];  // input, one per (row parity, col parity) for stride 2; only [0] for stride 1
   CUtensorMap tmB;     // weights [2][cout_pad][K]
   CUtensorMap tmO;     // output (5D; plane dim = 1 for fp32)
+  CUtensorMap tmR;     // residual (same box as the output tile), loaded by TMA into a staging tile
   int tiles_w, tiles_h, tiles_b, tiles_n;
   int TW, TH, NB;
   int Ho, Wo, Bn;
@@ -53,6 +54,7 @@ struct alignas(64) ConvKArgs {
   uint32_t a_lo_off;   // smem offset of the lo plane of A inside a stage (== a_box_bytes when hi+lo arrive in ONE TMA box)
   int a_fused;         // 1: one 5D box {K, TW, TH, NB, 2 planes} per stage instead of two
   int b_resident;      // 1: the whole weight slab of this CTA's n-tile stays in smem; the ring streams A only
+  int resid_tma;       // 1: the residual tile arrives by TMA (issued one group ahead by the epilogue), 0: per-thread loads
   int resid_first;     // 1: out = act(conv + bias + residual) (ResNet bottleneck); 0: out = act(conv + bias) + residual (Darknet)
   float rz_gain;       // 1 + (MMAs per hi*hi chain) * c: undoes the mean shrink of round-toward-zero accumulation
   int out_bufs;        // 1 or 2 output staging tiles (2: the TMA store of group g overlaps the conversion of g+1)
@@ -128,14 +130,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   uint8_t* stage_base = smem;
   uint8_t* b_res = smem + STAGES * stage_bytes;                                  // resident weights: k_iters x {hi, lo} tiles
   uint8_t* out_stage0 = b_res + (a.b_resident ? a.taps * a.chunks * 2 * B_BYTES : 0);
-  float* bias_s = reinterpret_cast<float*>(out_stage0 + a.out_bufs * Cfg::OUT_STAGE_BYTES);
+  uint8_t* res_stage = out_stage0 + a.out_bufs * Cfg::OUT_STAGE_BYTES;           // residual tile (same layout as an output tile)
+  float* bias_s = reinterpret_cast<float*>(res_stage + (a.resid_tma ? Cfg::OUT_STAGE_BYTES : 0));
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + BLOCK_N);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = tfull + 2;
   uint64_t* bfull = tempty + 2;  // resident weights have landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+  uint64_t* rfull = bfull + 1;   // residual tile has landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rfull + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -144,6 +148,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     tma_prefetch_desc(&a.tmA[0]);
     tma_prefetch_desc(&a.tmB);
     tma_prefetch_desc(&a.tmO);
+    if (a.resid_tma) tma_prefetch_desc(&a.tmR);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -156,6 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         mbar_init(&tempty[s], kEpiThreads / 32);
       }
       mbar_init(bfull, 1);
+      mbar_init(rfull, 1);
       fence_barrier_init();
     }
     __syncwarp();
@@ -285,7 +291,20 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     uint32_t acc_phase = 0;
     int cur_n0 = -1;
     uint32_t gcount = 0;
+    uint32_t res_phase = 0;
     const int n_main = a.n_main;
+    constexpr int kGroups = BLOCK_N / OUT_GROUP_CH;
+    // residual tile of (tile, group): two TMA boxes (hi, lo) with the output tile's geometry; OOB parts are zero-filled
+    auto issue_residual = [&](int tile_i, int g) {
+      const int nt_ = tile_i % a.tiles_n, mt_ = tile_i / a.tiles_n;
+      const int wt_ = mt_ % a.tiles_w, t2_ = mt_ / a.tiles_w;
+      const int ht_ = t2_ % a.tiles_h, bt_ = t2_ / a.tiles_h;
+      const int c0 = nt_ * BLOCK_N + g * OUT_GROUP_CH;
+      mbar_expect_tx(rfull, (uint32_t)(2 * a.rows_valid * OUT_ROW_BYTES));
+      tma_load_5d(&a.tmR, rfull, res_stage, c0, wt_ * a.TW, ht_ * a.TH, bt_ * a.NB, 0);
+      tma_load_5d(&a.tmR, rfull, res_stage + Cfg::OUT_PLANE_BYTES, c0, wt_ * a.TW, ht_ * a.TH, bt_ * a.NB, 1);
+    };
+    if (a.resid_tma && tid_e == 0 && (int)blockIdx.x < total_tiles) issue_residual(blockIdx.x, 0);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % a.tiles_n;
       const int mt = tile / a.tiles_n;
@@ -320,19 +339,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         float4 upv[CW / 4];
         uint4 rhv[CW / 8], rlv[CW / 8];
         const bool has_up = (up_row != nullptr) && ch_ok;
-        const bool has_res = (res_row != nullptr) && ch_ok;
+        const bool has_res = a.resid_tma ? true : ((res_row != nullptr) && ch_ok);
         if (has_up) {
           const float4* p = reinterpret_cast<const float4*>(up_row + col);
 #pragma unroll
           for (int j = 0; j < CW / 4; ++j) upv[j] = __ldg(p + j);
         }
-        if (has_res) {
+        if (has_res && !a.resid_tma) {
           const uint4* ph = reinterpret_cast<const uint4*>(res_row + col);
           const uint4* pl = reinterpret_cast<const uint4*>(res_row + a.resid_plane + col);
 #pragma unroll
           for (int j = 0; j < CW / 8; ++j) {
             rhv[j] = __ldg(ph + j);
             rlv[j] = __ldg(pl + j);
+          }
+        }
+        if constexpr (!OUT_F32) {
+          if (a.resid_tma) {  // same swizzled chunk addressing as the output staging tile below
+            mbar_wait(rfull, res_phase, 500);
+            res_phase ^= 1;
+            const uint8_t* rh = res_stage + row * OUT_ROW_BYTES;
+#pragma unroll
+            for (int j = 0; j < CW / 8; ++j) {
+              const int cj = half * (CW / 8) + j;
+              int chunk;
+              if constexpr (OUT_GROUP_CH == 64) chunk = cj ^ (row & 7);
+              else chunk = cj ^ ((row >> 1) & 3);
+              rhv[j] = *reinterpret_cast<const uint4*>(rh + (chunk << 4));
+              rlv[j] = *reinterpret_cast<const uint4*>(rh + Cfg::OUT_PLANE_BYTES + (chunk << 4));
+            }
           }
         }
         if (g == 0) {
@@ -439,6 +474,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             if constexpr (!OUT_F32) tma_store_5d(&a.tmO, out_stage + Cfg::OUT_PLANE_BYTES, c0, w0, h0, b0, 1);
           }
           tma_store_commit();
+          if (a.resid_tma) {  // every epilogue thread has consumed the residual tile (barrier above): fetch the next one
+            if (g + 1 < kGroups) issue_residual(tile, g + 1);
+            else if (tile + (int)gridDim.x < total_tiles) issue_residual(tile + (int)gridDim.x, 0);
+          }
         }
       }
       // all tcgen05.ld of this accumulator set are complete -> hand it back to the MMA warp
@@ -719,6 +758,23 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
     a.resid = static_cast<const __half*>(r.base);
     a.resid_plane = r.plane_stride / 2;
     a.resid_pitch = r.c_pitch;
+    static const bool resid_tma_on = [] {
+      const char* e = getenv("CVB_RESID_TMA");  // A/B knob: 0 = per-thread residual loads
+      return !(e && atoi(e) == 0);
+    }();
+    if (!f32 && resid_tma_on) {  // residual tile through TMA (same box / swizzle as the output tile)
+      const int gch = bn >= 64 ? 64 : 32;
+      const long long pixr = (long long)r.c_pitch * 2;
+      const cuuint64_t dims[5] = {(cuuint64_t)cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)out.B, 2};
+      const cuuint64_t str[4] = {(cuuint64_t)pixr, (cuuint64_t)(pixr * Wo), (cuuint64_t)(pixr * Wo * Ho), (cuuint64_t)r.plane_stride};
+      const cuuint32_t box[5] = {(cuuint32_t)gch, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)NB, 1};
+      rc = encode_map(&a.tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, r.base, dims, str, box, swizzle_for_bytes(gch * 2));
+      if (rc != CVB_OK) {
+        delete p;
+        return rc;
+      }
+      a.resid_tma = 1;
+    }
     a.resid_first = d->residual_before_act ? 1 : 0;
   }
   if (d->up_partial.base) {
@@ -737,7 +793,7 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   const int k_iters = a.taps * a.chunks;
   const int a_stage = 2 * kTileM * bk * 2;   // hi + lo activation tiles of one K chunk
   const int b_stage = 2 * bn * bk * 2;       // hi + lo weight tiles of one K chunk
-  const int base = 1024 + ke.tail_bytes;
+  const int base = 1024 + ke.tail_bytes + (a.resid_tma ? ke.out_stage_bytes : 0);
   int stages = 0;
   a.b_resident = 0;
   a.out_bufs = 1;
