@@ -34,6 +34,7 @@ constexpr int kMaxTaps = 9;
 constexpr int kEpiThreads = 256;          // 8 epilogue warps
 constexpr int kThreads = 64 + kEpiThreads;  // + TMA producer warp + MMA issuer warp
 constexpr int kSmemBudget = 232448;  // 227 KB opt-in limit per CTA on sm_100
+constexpr int kSmemBudget2 = 115712;  // per CTA when two share an SM: (228 KB - 2 x 1 KB reserved) / 2
 
 struct alignas(64) ConvKArgs {
   CUtensorMap tmA[4];  // input, one per (row parity, col parity) for stride 2; only [0] for stride 1
@@ -54,6 +55,7 @@ struct alignas(64) ConvKArgs {
   uint32_t a_lo_off;   // smem offset of the lo plane of A inside a stage (== a_box_bytes when hi+lo arrive in ONE TMA box)
   int a_fused;         // 1: one 5D box {K, TW, TH, NB, 2 planes} per stage instead of two
   int b_resident;      // 1: the whole weight slab of this CTA's n-tile stays in smem; the ring streams A only
+  int tmem_cols;       // allocated TMEM columns: nbuf x (n_main + 1) accumulators of BLOCK_N columns, rounded to a power of two
   int resid_tma;       // 1: the residual tile arrives by TMA (issued one group ahead by the epilogue), 0: per-thread loads
   int resid_first;     // 1: out = act(conv + bias + residual) (ResNet bottleneck); 0: out = act(conv + bias) + residual (Darknet)
   float rz_gain;       // 1 + (MMAs per hi*hi chain) * c: undoes the mean shrink of round-toward-zero accumulation
@@ -107,13 +109,12 @@ struct ConvCfg {
   static constexpr int OUT_ROW_BYTES = OUT_F32 ? 128 : OUT_GROUP_CH * 2;
   static constexpr int OUT_PLANE_BYTES = kTileM * OUT_ROW_BYTES;
   static constexpr int OUT_STAGE_BYTES = OUT_PLANE_BYTES * (OUT_F32 ? 1 : 2);
-  static constexpr int TMEM_COLS = 512;  // whole TMEM: nbuf x (n_main + 1) accumulators of BLOCK_N columns (1 CTA/SM)
   static constexpr int TAIL_BYTES = BLOCK_N * 4 + 64 * 8 + 16;  // bias + barriers + tmem slot
   static constexpr int smem_bytes(int stages) { return 1024 + stages * STAGE_BYTES + OUT_STAGE_BYTES + TAIL_BYTES; }
 };
 
 template <int BLOCK_N, int BLOCK_K, bool OUT_F32>
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ ConvKArgs a) {
+__global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_kernel(const __grid_constant__ ConvKArgs a) {
   using Cfg = ConvCfg<BLOCK_N, BLOCK_K, OUT_F32>;
   constexpr int SWZ = Cfg::SWZ;
   constexpr int A_BYTES = Cfg::A_BYTES;
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    tmem_alloc(tmem_slot, (uint32_t)a.tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -287,6 +288,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int th = r2 % a.TH;
     const int nb = r2 / a.TH;
     constexpr int CW = OUT_GROUP_CH / 2;  // columns per warp per group (32, or 16 for 32-wide groups)
+    constexpr int SUB = (BLOCK_N <= 64 && CW > 16) ? 16 : CW;  // columns held in registers at a time
     int acc = 0;
     uint32_t acc_phase = 0;
     int cur_n0 = -1;
@@ -332,42 +334,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 
 #pragma unroll 1
       for (int g = 0; g < BLOCK_N / OUT_GROUP_CH; ++g) {
-        const int col = g * OUT_GROUP_CH + half * CW;
-        const bool ch_ok = (n0 + col + CW <= a.cout);
-        // epilogue operands that do not depend on the accumulator are requested first, so their latency hides behind
-        // the accumulator wait / barrier / tcgen05.ld below
-        float4 upv[CW / 4];
-        uint4 rhv[CW / 8], rlv[CW / 8];
+        const int col0 = g * OUT_GROUP_CH + half * CW;
+        const bool ch_ok = (n0 + col0 + CW <= a.cout);
         const bool has_up = (up_row != nullptr) && ch_ok;
         const bool has_res = a.resid_tma ? true : ((res_row != nullptr) && ch_ok);
-        if (has_up) {
-          const float4* p = reinterpret_cast<const float4*>(up_row + col);
+        // the thread's CW columns are processed in sub-chunks of SUB columns (SUB < CW only for the small-N kernels that must
+        // stay within the two-CTAs-per-SM register budget).  Epilogue operands that do not depend on the accumulator are
+        // requested first, so their latency hides behind the accumulator wait / barrier / tcgen05.ld below
+        float4 upv[SUB / 4];
+        uint4 rhv[SUB / 8], rlv[SUB / 8];
+        auto load_extras = [&](int sc) {
+          const int col = col0 + sc * SUB;
+          if (has_up) {
+            const float4* p = reinterpret_cast<const float4*>(up_row + col);
 #pragma unroll
-          for (int j = 0; j < CW / 4; ++j) upv[j] = __ldg(p + j);
-        }
-        if (has_res && !a.resid_tma) {
-          const uint4* ph = reinterpret_cast<const uint4*>(res_row + col);
-          const uint4* pl = reinterpret_cast<const uint4*>(res_row + a.resid_plane + col);
-#pragma unroll
-          for (int j = 0; j < CW / 8; ++j) {
-            rhv[j] = __ldg(ph + j);
-            rlv[j] = __ldg(pl + j);
+            for (int j = 0; j < SUB / 4; ++j) upv[j] = __ldg(p + j);
           }
-        }
+          if (has_res && !a.resid_tma) {
+            const uint4* ph = reinterpret_cast<const uint4*>(res_row + col);
+            const uint4* pl = reinterpret_cast<const uint4*>(res_row + a.resid_plane + col);
+#pragma unroll
+            for (int j = 0; j < SUB / 8; ++j) {
+              rhv[j] = __ldg(ph + j);
+              rlv[j] = __ldg(pl + j);
+            }
+          }
+        };
+        load_extras(0);
         if constexpr (!OUT_F32) {
-          if (a.resid_tma) {  // same swizzled chunk addressing as the output staging tile below
+          if (a.resid_tma) {
             mbar_wait(rfull, res_phase, 500);
             res_phase ^= 1;
-            const uint8_t* rh = res_stage + row * OUT_ROW_BYTES;
-#pragma unroll
-            for (int j = 0; j < CW / 8; ++j) {
-              const int cj = half * (CW / 8) + j;
-              int chunk;
-              if constexpr (OUT_GROUP_CH == 64) chunk = cj ^ (row & 7);
-              else chunk = cj ^ ((row >> 1) & 3);
-              rhv[j] = *reinterpret_cast<const uint4*>(rh + (chunk << 4));
-              rlv[j] = *reinterpret_cast<const uint4*>(rh + Cfg::OUT_PLANE_BYTES + (chunk << 4));
-            }
           }
         }
         if (g == 0) {
@@ -382,87 +379,106 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         named_bar_sync(1, kEpiThreads);
         uint8_t* out_stage = out_stage0 + (gcount & (a.out_bufs - 1)) * Cfg::OUT_STAGE_BYTES;
         ++gcount;
-        float f[CW];
-        {
-          uint32_t v[CW];
-          tmem_ld_cols<CW>(t_set + (uint32_t)(n_main * BLOCK_N + col), v);  // cross terms first (smallest magnitude)
-          tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < CW; ++j) f[j] = __uint_as_float(v[j]);
-          const float gain = a.rz_gain;
-          for (int r = 0; r < n_main; ++r) {
-            tmem_ld_cols<CW>(t_set + (uint32_t)(r * BLOCK_N + col), v);
-            tmem_ld_wait();
+        for (int sc = 0; sc < CW / SUB; ++sc) {
+          const int col = col0 + sc * SUB;
+          if (sc > 0) load_extras(sc);
+          if constexpr (!OUT_F32) {
+            if (a.resid_tma) {  // same swizzled chunk addressing as the output staging tile below
+              const uint8_t* rh = res_stage + row * OUT_ROW_BYTES;
 #pragma unroll
-            for (int j = 0; j < CW; ++j) f[j] = fmaf(__uint_as_float(v[j]), gain, f[j]);
-          }
-        }
-        if (has_up) {
-#pragma unroll
-          for (int j = 0; j < CW / 4; ++j) {
-            f[4 * j + 0] += upv[j].x;
-            f[4 * j + 1] += upv[j].y;
-            f[4 * j + 2] += upv[j].z;
-            f[4 * j + 3] += upv[j].w;
-          }
-        }
-        float rsum[CW];  // residual (hi + lo) of this thread's pixel, 0 when absent
-#pragma unroll
-        for (int j = 0; j < CW; ++j) rsum[j] = 0.0f;
-        if (has_res) {
-#pragma unroll
-          for (int j = 0; j < CW / 8; ++j) {
-            const __half2* h2 = reinterpret_cast<const __half2*>(&rhv[j]);
-            const __half2* l2 = reinterpret_cast<const __half2*>(&rlv[j]);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 hf = __half22float2(h2[e]);
-              const float2 lf = __half22float2(l2[e]);
-              rsum[8 * j + 2 * e + 0] = hf.x + lf.x;
-              rsum[8 * j + 2 * e + 1] = hf.y + lf.y;
+              for (int j = 0; j < SUB / 8; ++j) {
+                const int cj = half * (CW / 8) + sc * (SUB / 8) + j;
+                int chunk;
+                if constexpr (OUT_GROUP_CH == 64) chunk = cj ^ (row & 7);
+                else chunk = cj ^ ((row >> 1) & 3);
+                rhv[j] = *reinterpret_cast<const uint4*>(rh + (chunk << 4));
+                rlv[j] = *reinterpret_cast<const uint4*>(rh + Cfg::OUT_PLANE_BYTES + (chunk << 4));
+              }
             }
           }
-        }
-        const bool rf = a.resid_first != 0;
-        if (a.act == CVB_ACT_SILU) {
+          float f[SUB];
+          {
+            uint32_t v[SUB];
+            tmem_ld_cols<SUB>(t_set + (uint32_t)(n_main * BLOCK_N + col), v);  // cross terms first (smallest magnitude)
+            tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < CW; ++j) {
-            const float t = f[j] + bias_s[col + j];
-            f[j] = rf ? silu_fast(t + rsum[j]) : silu_fast(t) + rsum[j];
+            for (int j = 0; j < SUB; ++j) f[j] = __uint_as_float(v[j]);
+            const float gain = a.rz_gain;
+            for (int r = 0; r < n_main; ++r) {
+              tmem_ld_cols<SUB>(t_set + (uint32_t)(r * BLOCK_N + col), v);
+              tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < SUB; ++j) f[j] = fmaf(__uint_as_float(v[j]), gain, f[j]);
+            }
           }
-        } else if (a.act == CVB_ACT_RELU) {
+          if (has_up) {
 #pragma unroll
-          for (int j = 0; j < CW; ++j) {
-            const float t = f[j] + bias_s[col + j];
-            f[j] = rf ? fmaxf(t + rsum[j], 0.0f) : fmaxf(t, 0.0f) + rsum[j];
+            for (int j = 0; j < SUB / 4; ++j) {
+              f[4 * j + 0] += upv[j].x;
+              f[4 * j + 1] += upv[j].y;
+              f[4 * j + 2] += upv[j].z;
+              f[4 * j + 3] += upv[j].w;
+            }
           }
-        } else {
+          float rsum[SUB];  // residual (hi + lo) of this thread's pixel, 0 when absent
 #pragma unroll
-          for (int j = 0; j < CW; ++j) f[j] = f[j] + bias_s[col + j] + rsum[j];
-        }
-        if constexpr (OUT_F32) {
-          // row = 32 fp32 = 128 B = 8 chunks of 16 B, 128B swizzle: chunk ^= row & 7; this warp owns chunks half*4 .. +3
-          uint8_t* rowp = out_stage + row * 128;
+          for (int j = 0; j < SUB; ++j) rsum[j] = 0.0f;
+          if (has_res) {
 #pragma unroll
-          for (int j = 0; j < CW / 4; ++j) {
-            const uint4 o = make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
-                                       __float_as_uint(f[4 * j + 3]));
-            *reinterpret_cast<uint4*>(rowp + (((half * (CW / 4) + j) ^ (row & 7)) << 4)) = o;
+            for (int j = 0; j < SUB / 8; ++j) {
+              const __half2* h2 = reinterpret_cast<const __half2*>(&rhv[j]);
+              const __half2* l2 = reinterpret_cast<const __half2*>(&rlv[j]);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 hf = __half22float2(h2[e]);
+                const float2 lf = __half22float2(l2[e]);
+                rsum[8 * j + 2 * e + 0] = hf.x + lf.x;
+                rsum[8 * j + 2 * e + 1] = hf.y + lf.y;
+              }
+            }
           }
-        } else {
-          uint8_t* rowh = out_stage + row * OUT_ROW_BYTES;
-          uint8_t* rowl = rowh + Cfg::OUT_PLANE_BYTES;
+          const bool rf = a.resid_first != 0;
+          if (a.act == CVB_ACT_SILU) {
 #pragma unroll
-          for (int j = 0; j < CW / 8; ++j) {
-            uint32_t hq[4], lq[4];
+            for (int j = 0; j < SUB; ++j) {
+              const float t = f[j] + bias_s[col + j];
+              f[j] = rf ? silu_fast(t + rsum[j]) : silu_fast(t) + rsum[j];
+            }
+          } else if (a.act == CVB_ACT_RELU) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) split_pair(f[8 * j + 2 * e], f[8 * j + 2 * e + 1], hq[e], lq[e]);
-            const int cj = half * (CW / 8) + j;  // 16-byte chunk (8 channels) inside the staged row
-            int chunk;
-            if constexpr (OUT_GROUP_CH == 64) chunk = cj ^ (row & 7);   // 128B swizzle
-            else chunk = cj ^ ((row >> 1) & 3);                         // 64B swizzle
-            *reinterpret_cast<uint4*>(rowh + (chunk << 4)) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
-            *reinterpret_cast<uint4*>(rowl + (chunk << 4)) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+            for (int j = 0; j < SUB; ++j) {
+              const float t = f[j] + bias_s[col + j];
+              f[j] = rf ? fmaxf(t + rsum[j], 0.0f) : fmaxf(t, 0.0f) + rsum[j];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < SUB; ++j) f[j] = f[j] + bias_s[col + j] + rsum[j];
+          }
+          if constexpr (OUT_F32) {
+            // row = 32 fp32 = 128 B = 8 chunks of 16 B, 128B swizzle: chunk ^= row & 7; this warp owns chunks half*4 .. +3
+            uint8_t* rowp = out_stage + row * 128;
+#pragma unroll
+            for (int j = 0; j < SUB / 4; ++j) {
+              const uint4 o = make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                                         __float_as_uint(f[4 * j + 3]));
+              *reinterpret_cast<uint4*>(rowp + (((half * (CW / 4) + sc * (SUB / 4) + j) ^ (row & 7)) << 4)) = o;
+            }
+          } else {
+            uint8_t* rowh = out_stage + row * OUT_ROW_BYTES;
+            uint8_t* rowl = rowh + Cfg::OUT_PLANE_BYTES;
+#pragma unroll
+            for (int j = 0; j < SUB / 8; ++j) {
+              uint32_t hq[4], lq[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) split_pair(f[8 * j + 2 * e], f[8 * j + 2 * e + 1], hq[e], lq[e]);
+              const int cj = half * (CW / 8) + sc * (SUB / 8) + j;  // 16-byte chunk (8 channels) inside the staged row
+              int chunk;
+              if constexpr (OUT_GROUP_CH == 64) chunk = cj ^ (row & 7);   // 128B swizzle
+              else chunk = cj ^ ((row >> 1) & 3);                         // 64B swizzle
+              *reinterpret_cast<uint4*>(rowh + (chunk << 4)) = make_uint4(hq[0], hq[1], hq[2], hq[3]);
+              *reinterpret_cast<uint4*>(rowl + (chunk << 4)) = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+            }
           }
         }
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
@@ -497,7 +513,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
   if (warp == 1) {
     tc_fence_after();
     __syncwarp();
-    tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    tmem_dealloc(tmem_base, (uint32_t)a.tmem_cols);
   }
 }
 
@@ -629,9 +645,20 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   const bool f32 = d->out_kind == CVB_OUT_F32;
   if (f32) CVB_REQUIRE(out.c_pitch % 4 == 0, "conv: fp32 output pitch must be a multiple of 4");
 
-  const int bk = (cin % 64 == 0) ? 64 : (cin % 32 == 0 ? 32 : 16);
   int bn = d->block_n;
   if (bn == 0) bn = cout <= 32 ? 32 : (cout <= 64 ? 64 : 128);
+  int bk = (cin % 64 == 0) ? 64 : (cin % 32 == 0 ? 32 : 16);
+  {
+    static const int bk_small = [] {
+      const char* e = getenv("CVB_BK_SMALLN");  // tuning knob: K chunk of the block_n <= 64 kernels for 64-channel inputs (default 32)
+      const int v = e ? atoi(e) : 0;
+      return (v == 16 || v == 32 || v == 64) ? v : 32;
+    }();
+    // 64-channel inputs into narrow tiles (1x1 convs and the row-window stems): half-size K chunks let two CTAs share an SM
+    // (see plan_smem below), which hides the epilogue latency these HBM-bound layers are limited by.  Multi-tap 3x3 layers
+    // keep 64-wide chunks: measured slower with twice the TMA operations.
+    if (bn <= 64 && cin == 64 && (d->kh * d->kw == 1 || win > 0)) bk = bk_small;
+  }
   KernelEntry ke;
   CVB_REQUIRE(lookup_kernel(bn, bk, f32, &ke), "conv: no kernel for block_n=%d block_k=%d", bn, bk);
 
@@ -794,28 +821,52 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   const int a_stage = 2 * kTileM * bk * 2;   // hi + lo activation tiles of one K chunk
   const int b_stage = 2 * bn * bk * 2;       // hi + lo weight tiles of one K chunk
   const int base = 1024 + ke.tail_bytes + (a.resid_tma ? ke.out_stage_bytes : 0);
-  int stages = 0;
-  a.b_resident = 0;
-  a.out_bufs = 1;
   const bool can_pin_n = (a.tiles_n == 1 || a.tiles_n == 2 || a.tiles_n == 4);
-  if (!d->no_resident && can_pin_n && (long long)k_iters * b_stage <= 65536) {
-    // small weight slab: keep it in smem for the whole kernel, stream only activations, double-buffer the output tile
-    const int st = (kSmemBudget - base - k_iters * b_stage - 2 * ke.out_stage_bytes) / a_stage;
-    if (st >= 3) {
-      stages = st;
-      a.b_resident = 1;
-      a.out_bufs = 2;
+  // ring depth / resident weights / staging buffers that fit `budget` bytes of dynamic shared memory (0 stages = no fit)
+  auto plan_smem = [&](int budget, int& resident, int& out_bufs) -> int {
+    resident = 0;
+    out_bufs = 1;
+    if (can_pin_n && !d->no_resident && (long long)k_iters * b_stage <= 64 * 1024) {
+      // the CTA's n-tile never changes and its whole weight slab fits: keep it resident, stream only activations
+      const int st = (budget - base - 2 * ke.out_stage_bytes - k_iters * b_stage) / a_stage;
+      if (st >= 3 || (st >= 2 && k_iters == 1)) {
+        resident = 1;
+        out_bufs = 2;
+        return st;
+      }
     }
-  }
-  if (stages == 0) {
-    const int st2 = (kSmemBudget - base - 2 * ke.out_stage_bytes) / (a_stage + b_stage);
+    const int st2 = (budget - base - 2 * ke.out_stage_bytes) / (a_stage + b_stage);
     if (st2 >= 3) {
-      stages = st2;
-      a.out_bufs = 2;
-    } else {
-      stages = (kSmemBudget - base - ke.out_stage_bytes) / (a_stage + b_stage);
+      out_bufs = 2;
+      return st2;
+    }
+    if (can_pin_n && !d->no_resident && (long long)k_iters * b_stage <= 64 * 1024) {
+      const int st = (budget - base - ke.out_stage_bytes - k_iters * b_stage) / a_stage;
+      if (st >= 3) {
+        resident = 1;
+        return st;
+      }
+    }
+    return (budget - base - ke.out_stage_bytes) / (a_stage + b_stage);
+  };
+  static const bool two_ctas_on = [] {
+    const char* e = getenv("CVB_CTAS_PER_SM");  // A/B knob: 1 = always one CTA per SM
+    return !(e && atoi(e) == 1);
+  }();
+  int stages = 0, ctas_per_sm = 1;
+  if (bn <= 64 && two_ctas_on) {
+    // small-N tiles are bound by epilogue latency, not by smem capacity: two co-resident CTAs (each <= half the SM's shared
+    // memory and <= 256 TMEM columns) overlap one tile's epilogue with the other's loads
+    int res, ob;
+    const int st = plan_smem(kSmemBudget2, res, ob);
+    if (st >= 3 || (st >= 2 && ob == 2)) {
+      stages = st;
+      a.b_resident = res;
+      a.out_bufs = ob;
+      ctas_per_sm = 2;
     }
   }
+  if (stages == 0) stages = plan_smem(kSmemBudget, a.b_resident, a.out_bufs);
   if (stages > 8) stages = 8;
   if (stages < 2) {
     delete p;
@@ -840,6 +891,14 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
     }
     a.n_main = n_main;
     a.nbuf = (2 * (n_main + 1) * bn <= 512) ? 2 : 1;
+    int cols = 32;
+    while (cols < a.nbuf * (n_main + 1) * bn) cols *= 2;
+    if (ctas_per_sm == 2 && cols > 256) {  // n_main = 3 at bn = 64: give up one accumulator buffer rather than the second CTA
+      a.nbuf = 1;
+      cols = 32;
+      while (cols < (n_main + 1) * bn) cols *= 2;
+    }
+    a.tmem_cols = ctas_per_sm == 2 ? cols : 512;
     static const double rz_c = [] {
       // measured on B200 (tools/precision_probe.py): the tensor core's fp32 adder rounds toward zero, so |sum| shrinks by
       // ~1.6e-8 per chained MMA for sign-random data (4e-8 if all products have one sign).  1.9e-8 centres the residual.
@@ -873,10 +932,18 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   const long long total = (long long)a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
   int sms = g_num_sms;
   if (d->sm_limit > 0 && d->sm_limit < sms) sms = d->sm_limit;
+  sms *= ctas_per_sm;
   p->grid = (int)(total < sms ? total : sms);
   if (a.b_resident && a.tiles_n > 1) {
     p->grid -= p->grid % a.tiles_n;  // every CTA keeps one n-tile (tile % tiles_n constant along its stride)
     if (p->grid < a.tiles_n) p->grid = a.tiles_n;
+  }
+  {
+    static const bool dbg = [] { const char* e = getenv("CVB_PLAN_DEBUG"); return e && atoi(e) != 0; }();
+    if (dbg)
+      fprintf(stderr, "[cvb plan] cin=%d cout=%d k=%dx%d s=%d out=%dx%dx%d bn=%d bk=%d stages=%d resident=%d out_bufs=%d ctas/sm=%d "
+              "tmem=%d n_main=%d nbuf=%d smem=%d grid=%d tiles=%lld resid_tma=%d\n", cin, cout, d->kh, d->kw, d->stride, out.B, Ho, Wo, bn, bk,
+              stages, a.b_resident, a.out_bufs, ctas_per_sm, a.tmem_cols, a.n_main, a.nbuf, p->smem, p->grid, total, a.resid_tma);
   }
   *out_plan = p;
   return CVB_OK;
