@@ -206,8 +206,8 @@ constexpr int kDecodeRows = 4;       // rows in flight per warp (all loads issue
 __global__ void __launch_bounds__(kDecodeThreads) yolo_decode_kernel(const float* __restrict__ raw, int ny, int nx, int pitch, int na,
                                                                      int no, const float* __restrict__ anchors_px, float stride,
                                                                      float* __restrict__ z, long long z_rows, long long z_off,
-                                                                     float* __restrict__ xperm, uint32_t* __restrict__ hist, float conf,
-                                                                     int multi_label) {
+                                                                     float* __restrict__ xperm, uint32_t* __restrict__ hist,
+                                                                     float* __restrict__ rowmax, float conf, int multi_label) {
   extern __shared__ uint32_t s_hist[];  // [kNmsBins] when hist != nullptr
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = kDecodeThreads / 32;
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kDecodeThreads) yolo_decode_kernel(const float
       const size_t orow = (size_t)a * npix + pix;
       float* zdst = z ? z + ((size_t)b * z_rows + z_off + orow) * no : nullptr;
       float* xdst = xperm ? xperm + ((size_t)b * na * npix + orow) * no : nullptr;
-      float obj = 0.0f, best = -1.0f;
+      float obj = 0.0f, best = -1.0f, rbest = 0.0f;
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
         const int c = k * 32 + lane;
@@ -270,21 +270,124 @@ __global__ void __launch_bounds__(kDecodeThreads) yolo_decode_kernel(const float
           if (obj > conf && c >= 5 && c < no && k < nchunk) {
             const float sc = __fmul_rn(o, obj);  // same fp32 product the NMS kernels recompute from z (yolov5.py:106)
             if (multi_label) {
-              if (sc > conf) atomicAdd(&s_hist[min(__float_as_uint(sc) >> 17, (uint32_t)(kNmsBins - 1))], 1u);
+              if (sc > conf) {
+                atomicAdd(&s_hist[min(__float_as_uint(sc) >> 17, (uint32_t)(kNmsBins - 1))], 1u);
+                rbest = fmaxf(rbest, sc);
+              }
             } else {
               best = fmaxf(best, sc);
             }
           }
         }
       }
-      if (hist != nullptr && !multi_label && obj > conf) {
+      if (hist != nullptr) {
+        if (!multi_label) rbest = best > conf ? best : 0.0f;
 #pragma unroll
-        for (int o2 = 16; o2 > 0; o2 >>= 1) best = fmaxf(best, __shfl_xor_sync(0xffffffffu, best, o2));
-        if (lane == 0 && best > conf) atomicAdd(&s_hist[min(__float_as_uint(best) >> 17, (uint32_t)(kNmsBins - 1))], 1u);
+        for (int o2 = 16; o2 > 0; o2 >>= 1) rbest = fmaxf(rbest, __shfl_xor_sync(0xffffffffu, rbest, o2));
+        if (lane == 0) {
+          rowmax[(size_t)b * z_rows + z_off + orow] = rbest;
+          if (!multi_label && rbest > conf) atomicAdd(&s_hist[min(__float_as_uint(rbest) >> 17, (uint32_t)(kNmsBins - 1))], 1u);
+        }
       }
     }
   }
   if (hist != nullptr) {
+    __syncthreads();
+    uint32_t* gh = hist + (size_t)b * kNmsBins;
+    for (int i = threadIdx.x; i < kNmsBins; i += kDecodeThreads) {
+      const uint32_t c = s_hist[i];
+      if (c) atomicAdd(&gh[i], c);
+    }
+  }
+}
+
+// Specialised decode for the hot configuration (64 <= no <= 96, decoded output only): one warp per (anchor, pixel) row, three
+// 32-lane chunks, kDecodeRows rows in flight, 32-bit offsets inside the CTA's pixel range, no per-chunk control flow.  Same
+// arithmetic as the generic kernel above (bit-identical z, histogram and rowmax).
+template <bool HIST, bool MULTI>
+__global__ void __launch_bounds__(kDecodeThreads) yolo_decode_fast_kernel(const float* __restrict__ raw, int ny, int nx, int pitch, int na,
+                                                                          int no, const float* __restrict__ anchors_px, float stride,
+                                                                          float* __restrict__ z, long long z_rows, long long z_off,
+                                                                          uint32_t* __restrict__ hist, float* __restrict__ rowmax,
+                                                                          float conf) {
+  extern __shared__ uint32_t s_hist[];  // [kNmsBins] when HIST
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NW = kDecodeThreads / 32;
+  constexpr int R = kDecodeRows;
+  const int b = blockIdx.y;
+  const int npix = ny * nx;
+  const int pix0 = blockIdx.x * kDecodePix;
+  const int cpix = min(npix, pix0 + kDecodePix) - pix0;
+  if (HIST) {
+    for (int i = threadIdx.x; i < kNmsBins; i += kDecodeThreads) s_hist[i] = 0;
+    __syncthreads();
+  }
+  const float* rbase = raw + ((size_t)b * npix + pix0) * pitch;
+  float* zb = z + ((size_t)b * z_rows + z_off) * no;        // row index inside the level: a * npix + pix
+  float* rmb = HIST ? rowmax + (size_t)b * z_rows + z_off : nullptr;
+  const int nrows = cpix * na;
+  const bool v2 = (64 + lane) < no;
+  const bool is_cls = lane >= 5;
+  for (int r0 = warp * R; r0 < nrows; r0 += NW * R) {
+    float v[R][3];
+    int av[R], pv[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int rr = min(r0 + i, nrows - 1);
+      const int a = rr / cpix;
+      const int p = rr - a * cpix;
+      av[i] = a;
+      pv[i] = p;
+      const float* src = rbase + (uint32_t)(p * pitch + a * no) + lane;
+      v[i][0] = __ldg(src);
+      v[i][1] = __ldg(src + 32);
+      v[i][2] = v2 ? __ldg(src + 64) : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const bool ok = (r0 + i) < nrows;  // tail rows are computed on clamped inputs and not stored (keeps the shuffles convergent)
+      const int a = av[i];
+      const int pix = pix0 + pv[i];
+      const int py = pix / nx, px = pix - py * nx;
+      const uint32_t orow = (uint32_t)(a * npix + pix);
+      float* dst = zb + (size_t)orow * no + lane;
+      const float y0 = sigmoid_fast(v[i][0]);
+      const float y1 = sigmoid_fast(v[i][1]);
+      const float y2 = sigmoid_fast(v[i][2]);
+      // reference: y = x.sigmoid(); xy = (y*2 - 0.5 + grid) * stride; wh = (y*2)**2 * anchor_grid   (yolov5_detect.py:50-53)
+      const float t2 = __fmul_rn(y0, 2.0f);
+      const float xy = __fmul_rn(__fadd_rn(__fsub_rn(t2, 0.5f), lane == 0 ? (float)px : (float)py), stride);
+      const float wh = __fmul_rn(__fmul_rn(t2, t2), __ldg(anchors_px + a * 2 + (lane & 1)));
+      const float o0 = lane < 2 ? xy : (lane < 4 ? wh : y0);
+      if (ok) {
+        dst[0] = o0;
+        dst[32] = y1;
+        if (v2) dst[64] = y2;
+      }
+      if (HIST) {
+        const float obj = __shfl_sync(0xffffffffu, o0, 4);
+        float rbest = 0.0f;
+        if (ok && obj > conf) {  // warp-uniform
+          // same fp32 product the NMS kernels recompute from z (yolov5.py:106)
+          const float s0 = is_cls ? __fmul_rn(o0, obj) : 0.0f;
+          const float s1 = __fmul_rn(y1, obj);
+          const float s2 = v2 ? __fmul_rn(y2, obj) : 0.0f;
+          if (MULTI) {
+            if (s0 > conf) atomicAdd(&s_hist[min(__float_as_uint(s0) >> 17, (uint32_t)(kNmsBins - 1))], 1u);
+            if (s1 > conf) atomicAdd(&s_hist[min(__float_as_uint(s1) >> 17, (uint32_t)(kNmsBins - 1))], 1u);
+            if (s2 > conf) atomicAdd(&s_hist[min(__float_as_uint(s2) >> 17, (uint32_t)(kNmsBins - 1))], 1u);
+          }
+          rbest = fmaxf(fmaxf(s0, s1), s2);
+          if (!(rbest > conf)) rbest = 0.0f;
+#pragma unroll
+          for (int o2 = 16; o2 > 0; o2 >>= 1) rbest = fmaxf(rbest, __shfl_xor_sync(0xffffffffu, rbest, o2));
+          if (!MULTI && lane == 0 && rbest > conf) atomicAdd(&s_hist[min(__float_as_uint(rbest) >> 17, (uint32_t)(kNmsBins - 1))], 1u);
+        }
+        if (ok && lane == 0) rmb[orow] = rbest;
+      }
+    }
+  }
+  if (HIST) {
     __syncthreads();
     uint32_t* gh = hist + (size_t)b * kNmsBins;
     for (int i = threadIdx.x; i < kNmsBins; i += kDecodeThreads) {
@@ -759,9 +862,30 @@ extern "C" int cvb_yolo_decode(const CvbView* raw, int32_t na, int32_t no, const
   }
   dim3 grid(ceil_div(raw->H * raw->W, kDecodePix), raw->B);
   CVB_REQUIRE(no <= 96, "yolo_decode: at most 91 classes supported (no=%d)", no);
-  yolo_decode_kernel<<<grid, kDecodeThreads, smem, as_stream(stream)>>>(static_cast<const float*>(raw->base), raw->H, raw->W, raw->c_pitch, na, no,
-                                                            anchors_px, stride, z, z_rows, z_off, xperm,
-                                                            static_cast<uint32_t*>(nms_workspace), conf_thres, multi_label);
+  uint32_t* hist = static_cast<uint32_t*>(nms_workspace);
+  float* rowmax = nms_workspace ? reinterpret_cast<float*>(static_cast<uint8_t*>(nms_workspace) + nms_ws_rowmax_offset(raw->B)) : nullptr;
+  const float* rawp = static_cast<const float*>(raw->base);
+  if (xperm == nullptr && no >= 64 && (long long)kDecodePix * raw->c_pitch + (long long)na * no < 0x7fffffffLL) {
+    static bool fast_attr_set = false;
+    if (!fast_attr_set) {
+      CVB_CHECK_CUDA(cudaFuncSetAttribute(yolo_decode_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsBins * (int)sizeof(uint32_t)));
+      CVB_CHECK_CUDA(cudaFuncSetAttribute(yolo_decode_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsBins * (int)sizeof(uint32_t)));
+      fast_attr_set = true;
+    }
+    cudaStream_t st = as_stream(stream);
+    if (!hist)
+      yolo_decode_fast_kernel<false, false><<<grid, kDecodeThreads, 0, st>>>(rawp, raw->H, raw->W, raw->c_pitch, na, no, anchors_px, stride, z, z_rows,
+                                                                             z_off, nullptr, nullptr, conf_thres);
+    else if (multi_label)
+      yolo_decode_fast_kernel<true, true><<<grid, kDecodeThreads, smem, st>>>(rawp, raw->H, raw->W, raw->c_pitch, na, no, anchors_px, stride, z, z_rows,
+                                                                              z_off, hist, rowmax, conf_thres);
+    else
+      yolo_decode_fast_kernel<true, false><<<grid, kDecodeThreads, smem, st>>>(rawp, raw->H, raw->W, raw->c_pitch, na, no, anchors_px, stride, z, z_rows,
+                                                                               z_off, hist, rowmax, conf_thres);
+  } else {
+    yolo_decode_kernel<<<grid, kDecodeThreads, smem, as_stream(stream)>>>(rawp, raw->H, raw->W, raw->c_pitch, na, no, anchors_px, stride, z, z_rows,
+                                                                          z_off, xperm, hist, rowmax, conf_thres, multi_label);
+  }
   CVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return CVB_OK;

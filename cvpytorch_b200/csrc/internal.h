@@ -37,5 +37,14 @@ static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // NMS score histogram (shared by nms.cu and the decode kernel): bin = float_bits(score) >> 17, per image
 constexpr int kNmsBins = 16384;
+constexpr int kNmsCap = 65536;   // candidate key capacity per image (phase B)
+constexpr int kNmsCapA = 4096;   // phase-A candidate capacity = one shared-memory sort chunk
+
+// NMS workspace layout (bytes): [hist B*kNmsBins u32][6 slots of B u32][keysB B*kNmsCap u64][keysA B*kNmsCapA u64][rowmax B*A f32]
+// rowmax[b][anchor] = best score (obj*cls, > conf) of the anchor row, 0 when it has no candidate: written by the pass that
+// builds the histogram (decode kernel or the NMS count pass) and lets the emit passes skip rows below the threshold bin.
+inline size_t nms_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline size_t nms_ws_head_bytes(int B) { return nms_align_up((size_t)B * kNmsBins * 4, 256) + 6 * nms_align_up((size_t)B * 4, 256); }
+inline size_t nms_ws_rowmax_offset(int B) { return nms_ws_head_bytes(B) + (size_t)B * (kNmsCap + kNmsCapA) * 8; }
 
 }  // namespace cvb

@@ -22,11 +22,11 @@
 namespace cvb {
 
 constexpr int kBins = kNmsBins;  // score_bits >> 17 for positive floats
-constexpr int kCap = 65536;    // candidate key capacity per image
+constexpr int kCap = kNmsCap;  // candidate key capacity per image
 constexpr int kChunk = 4096;   // keys sorted per CTA in shared memory
 constexpr int kGreedyThreads = 512;
 
-constexpr int kCapA = 4096;    // phase-A (early exit) candidate capacity = one shared-memory sort chunk
+constexpr int kCapA = kNmsCapA;  // phase-A (early exit) candidate capacity = one shared-memory sort chunk
 constexpr int kTargetA = 3072; // phase A takes the smallest set of top score bins holding >= this many candidates
 
 // Two-phase scheme: greedy NMS only needs candidates in score order until max_det boxes are kept, so phase A runs the
@@ -39,13 +39,14 @@ struct NmsWs {
   uint64_t* keys;   // [B][cap]
   uint32_t* done;   // [B]      set by phase A's greedy kernel
   uint32_t* total;  // [B]      number of candidates of the image (all bins)
+  float* rowmax;    // [B][A]   best candidate score of each anchor row (0: none), see internal.h
   int cap;          // kCapA or kCap
   int phase;        // 0 = A, 1 = B
 };
 
 __host__ __device__ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static size_t ws_head_bytes(int B) { return align_up((size_t)B * kBins * 4, 256) + 6 * align_up((size_t)B * 4, 256); }
+static size_t ws_head_bytes(int B) { return nms_ws_head_bytes(B); }
 
 static NmsWs carve_ws(void* ws, int B, int phase) {
   NmsWs w;
@@ -62,6 +63,7 @@ static NmsWs carve_ws(void* ws, int B, int phase) {
   p += 6 * slot;
   uint64_t* keysB = reinterpret_cast<uint64_t*>(p);
   uint64_t* keysA = keysB + (size_t)B * kCap;
+  w.rowmax = reinterpret_cast<float*>(static_cast<uint8_t*>(ws) + nms_ws_rowmax_offset(B));
   w.phase = phase;
   if (phase == 0) {
     w.cnt = cntA;
@@ -103,13 +105,28 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const float* __r
   }
   if (EMIT && ws.phase == 1 && ws.done[b]) return;  // phase A already produced this image's result
   const uint32_t tb = EMIT ? ws.tbin[b] : 0u;
+  float* rowmax = ws.rowmax + (size_t)b * A;
   constexpr int R = 4;  // rows in flight per warp: all loads of a batch are issued before the first use
   for (int base = row0 + warp * R; base < row1; base += (kScanThreads / 32) * R) {
     float obj[R];
+    if constexpr (EMIT) {
+      // rows whose best score falls below the threshold bin cannot emit anything: skip their 340-byte reads
+      float rm = 0.0f;
+      if (lane < R && base + lane < row1) rm = __ldg(rowmax + base + lane);
+      const uint32_t rb = __float_as_uint(rm);
+      const uint32_t live = __ballot_sync(0xffffffffu, rb != 0u && score_bin(rb) >= tb);
+      if (live == 0u) continue;
 #pragma unroll
-    for (int i = 0; i < R; ++i) {
-      const int anchor = min(base + i, row1 - 1);
-      obj[i] = __ldg(pred + ((size_t)b * A + anchor) * no + 4);
+      for (int i = 0; i < R; ++i) {
+        const int anchor = min(base + i, row1 - 1);
+        obj[i] = ((live >> i) & 1u) ? __ldg(pred + ((size_t)b * A + anchor) * no + 4) : 0.0f;  // 0 never passes obj > conf
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const int anchor = min(base + i, row1 - 1);
+        obj[i] = __ldg(pred + ((size_t)b * A + anchor) * no + 4);
+      }
     }
     if (multi_label && nc <= 96) {
       float v[R][3];
@@ -126,7 +143,12 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const float* __r
 #pragma unroll
       for (int i = 0; i < R; ++i) {
         const int anchor = base + i;
-        if (anchor >= row1 || !(obj[i] > conf)) continue;
+        if (anchor >= row1) continue;
+        if (!(obj[i] > conf)) {
+          if (!EMIT && lane == 0) rowmax[anchor] = 0.0f;
+          continue;
+        }
+        float rbest = 0.0f;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           const int c = k * 32 + lane;
@@ -138,8 +160,11 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const float* __r
             if (sc > conf) {
               bits = __float_as_uint(sc);
               const uint32_t bin = score_bin(bits);
-              if (EMIT) pass = bin >= tb;
-              else atomicAdd(&ws.hist[(size_t)b * kBins + bin], 1u);
+              if constexpr (EMIT) pass = bin >= tb;
+              else {
+                atomicAdd(&ws.hist[(size_t)b * kBins + bin], 1u);
+                rbest = fmaxf(rbest, sc);
+              }
             }
           }
           if (EMIT) {
@@ -155,15 +180,25 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const float* __r
             }
           }
         }
+        if (!EMIT) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) rbest = fmaxf(rbest, __shfl_xor_sync(0xffffffffu, rbest, o));
+          if (lane == 0) rowmax[anchor] = rbest;
+        }
       }
       continue;
     }
     for (int i = 0; i < R; ++i) {
       const int anchor = base + i;
-      if (anchor >= row1 || !(obj[i] > conf)) continue;
+      if (anchor >= row1) continue;
+      if (!(obj[i] > conf)) {
+        if (!EMIT && lane == 0) rowmax[anchor] = 0.0f;
+        continue;
+      }
       const float* r = pred + ((size_t)b * A + anchor) * no;
       const float ob = obj[i];
       if (multi_label) {
+        float rbest = 0.0f;
         for (int c0 = 0; c0 < nc; c0 += 32) {
           const int c = c0 + lane;
           bool pass = false;
@@ -173,8 +208,11 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const float* __r
             if (sc > conf) {
               bits = __float_as_uint(sc);
               const uint32_t bin = score_bin(bits);
-              if (EMIT) pass = bin >= tb;
-              else atomicAdd(&ws.hist[(size_t)b * kBins + bin], 1u);
+              if constexpr (EMIT) pass = bin >= tb;
+              else {
+                atomicAdd(&ws.hist[(size_t)b * kBins + bin], 1u);
+                rbest = fmaxf(rbest, sc);
+              }
             }
           }
           if (EMIT) {
@@ -189,6 +227,11 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const float* __r
               }
             }
           }
+        }
+        if (!EMIT) {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) rbest = fmaxf(rbest, __shfl_xor_sync(0xffffffffu, rbest, o));
+          if (lane == 0) rowmax[anchor] = rbest;
         }
       } else {
         // best class only: conf, j = x[:, 5:].max(1)  (first maximum wins ties)
@@ -210,10 +253,11 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const float* __r
             bi = oi;
           }
         }
+        if (!EMIT && lane == 0) rowmax[anchor] = best > conf ? best : 0.0f;
         if (lane == 0 && best > conf) {
           const uint32_t bits = __float_as_uint(best);
           const uint32_t bin = score_bin(bits);
-          if (EMIT) {
+          if constexpr (EMIT) {
             if (bin >= tb) {
               const uint32_t id = (uint32_t)anchor * (uint32_t)nc + (uint32_t)bi;
               stage[atomicAdd(&s_cnt, 1u)] = ((uint64_t)bits << 32) | (uint64_t)(0xFFFFFFFFu - id);
@@ -517,10 +561,9 @@ __global__ void __launch_bounds__(kGreedyThreads) nms_greedy_kernel(const float*
 using namespace cvb;
 
 extern "C" size_t cvb_nms_workspace_bytes(int32_t B, int32_t A, int32_t nc) {
-  (void)A;
   (void)nc;
-  if (B <= 0) return 0;
-  return ws_head_bytes(B) + (size_t)B * (kCap + kCapA) * 8;
+  if (B <= 0 || A <= 0) return 0;
+  return nms_ws_rowmax_offset(B) + nms_align_up((size_t)B * A * sizeof(float), 256);
 }
 
 extern "C" int cvb_nms_workspace_reset(void* workspace, size_t workspace_bytes, int32_t B, void* stream) {
