@@ -56,6 +56,7 @@ struct alignas(64) ConvKArgs {
   int a_fused;         // 1: one 5D box {K, TW, TH, NB, 2 planes} per stage instead of two
   int b_resident;      // 1: the whole weight slab of this CTA's n-tile stays in smem; the ring streams A only
   int tmem_cols;       // allocated TMEM columns: nbuf x (n_main + 1) accumulators of BLOCK_N columns, rounded to a power of two
+  int mma_pair;        // 1: A_hi x [B_hi | B_lo] as one MMA of N = 2 * BLOCK_N (needs n_main == 1 and BLOCK_N <= 128)
   int resid_tma;       // 1: the residual tile arrives by TMA (issued one group ahead by the epilogue), 0: per-thread loads
   int resid_first;     // 1: out = act(conv + bias + residual) (ResNet bottleneck); 0: out = act(conv + bias) + residual (Darknet)
   float rz_gain;       // 1 + (MMAs per hi*hi chain) * c: undoes the mean shrink of round-toward-zero accumulation
@@ -258,12 +259,27 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
           const uint64_t dbl = make_kmajor_desc<SWZ>(sbw + B_BYTES);
           const uint32_t d_main = d_base + (uint32_t)(r * BLOCK_N);
           const bool first_main = it < n_main;
+          if (a.mma_pair) {
+            // one accumulator chain (n_main == 1): the lo weight tile directly follows the hi tile in smem and the cross
+            // accumulator directly follows the main one in TMEM, so A_hi x [B_hi | B_lo] is ONE MMA of N = 2 * BLOCK_N --
+            // two MMAs and two A-operand reads per K step instead of three
+            if constexpr (2 * BLOCK_N <= 256) {
+              constexpr uint32_t IDESC2 = make_idesc_f16_f32(kTileM, 2 * BLOCK_N);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / 16; ++k) {
-            const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes per UMMA_K step, in 16-byte units
-            umma_f16(d_main, dah + koff, dbh + koff, IDESC, (first_main && k == 0) ? 0u : 1u);
-            umma_f16(d_cross, dah + koff, dbl + koff, IDESC, (it | k) != 0 ? 1u : 0u);
-            umma_f16(d_cross, dal + koff, dbh + koff, IDESC, 1u);
+              for (int k = 0; k < BLOCK_K / 16; ++k) {
+                const uint64_t koff = (uint64_t)(k * 2);
+                umma_f16(d_base, dah + koff, dbh + koff, IDESC2, (it | k) != 0 ? 1u : 0u);
+                umma_f16(d_cross, dal + koff, dbh + koff, IDESC, 1u);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / 16; ++k) {
+              const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes per UMMA_K step, in 16-byte units
+              umma_f16(d_main, dah + koff, dbh + koff, IDESC, (first_main && k == 0) ? 0u : 1u);
+              umma_f16(d_cross, dah + koff, dbl + koff, IDESC, (it | k) != 0 ? 1u : 0u);
+              umma_f16(d_cross, dal + koff, dbh + koff, IDESC, 1u);
+            }
           }
           umma_commit(&empty[stage]);  // frees this smem stage once the MMAs above have read it
           if (++stage == STAGES) {
@@ -895,6 +911,12 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
       return set_error(CVB_ERR_INVALID, "conv: block_n=%d leaves no room for the split accumulators", bn);
     }
     a.n_main = n_main;
+    static const bool pair_on = [] {
+      const char* e = getenv("CVB_MMA_PAIR");  // A/B knob: 0 = three MMAs per K step
+      return !(e && atoi(e) == 0);
+    }();
+    // (measured: a gain on every multi-tap layer and on 128-wide tiles, a loss on 1x1 layers with narrow tiles)
+    a.mma_pair = (pair_on && n_main == 1 && bn <= 128 && (bn == 128 || a.taps > 1)) ? 1 : 0;
     a.nbuf = (2 * (n_main + 1) * bn <= 512) ? 2 : 1;
     int cols = 32;
     while (cols < a.nbuf * (n_main + 1) * bn) cols *= 2;

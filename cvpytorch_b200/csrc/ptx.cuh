@@ -162,6 +162,21 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr) {
   d |= layout << 61;
   return d;
 }
+// Same, with an explicit stride byte offset (pitch between 8-row groups).  Used by the halo-tile 3x3 path: the rows of a
+// tap-shifted A tile are pixels of one halo image, 8 consecutive pixels per group, groups one image row (16 pixels) apart.
+// The hardware applies the swizzle XOR on absolute shared-memory address bits, so a start address shifted by whole rows
+// stays consistent with what TMA wrote (verified on B200 by tools/probe_halo_desc.cu).
+template <int SWIZZLE_BYTES>
+__device__ __forceinline__ uint64_t make_kmajor_desc_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  constexpr uint64_t layout = SWIZZLE_BYTES == 128 ? 2ull : (SWIZZLE_BYTES == 64 ? 4ull : 6ull);
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16: A=B=fp16 (format 0), D=fp32 (c_format 1), both K-major, M=128.
 //   bits [4,6) c_format  [7,10) a_format  [10,13) b_format  15 a_major  16 b_major  [17,23) N>>3  [24,29) M>>4
 __host__ __device__ constexpr uint32_t make_idesc_f16_f32(int m, int n) {

@@ -178,3 +178,16 @@ def test_sppf_pool(cuda):
     ref = torch.cat([xr, y1, y2, y3], 1)
     torch.cuda.synchronize()
     assert torch.equal(y, ref)  # max is exact on the hi+lo values
+
+
+def test_conv_3x3_shapes(cuda):
+    """more 3x3 / stride 1 shapes: borders, ragged maps, many K chunks (ring wrap-around), two N tiles, residual epilogue,
+    more tiles than SMs"""
+    assert _run_conv(32, 32, 3, 1, 1, 3, 16, 16) < TOL
+    assert _run_conv(64, 64, 3, 1, 1, 2, 24, 40) < TOL
+    assert _run_conv(256, 128, 3, 1, 1, 2, 32, 24, act='relu') < TOL
+    assert _run_conv(128, 256, 3, 1, 1, 2, 32, 32) < TOL
+    assert _run_conv(96, 64, 3, 1, 1, 1, 16, 24) < TOL
+    assert _run_conv(64, 64, 3, 1, 1, 4, 160, 160, residual=True) < TOL
+    assert _run_conv(32, 32, 3, 1, 1, 2, 160, 160, residual=True) < TOL
+    assert _run_conv(512, 64, 3, 1, 1, 1, 16, 16) < TOL   # chain of 288 MMAs: two main accumulators (three-MMA form)
