@@ -147,25 +147,42 @@ __global__ void sppf_pool_kernel(const __half* __restrict__ x, int H, int W, int
   const int pitches[3] = {p1, p2, p3};
   const long long planes[3] = {plane1, plane2, plane3};
   for (int r = 0; r < 3; ++r) {
-    // row pass: tmp[h][w] = max_{|d|<=2} cur[h][w+d]
-    for (int i = threadIdx.x; i < npix * 8; i += blockDim.x) {
-      const int c = i & 7, p = i >> 3, w = p % W, h = p / W;
-      float m = -CUDART_INF_F;
+    // row pass: tmp[h][w] = max_{|d|<=2} cur[h][w+d]; one thread per (pixel, 4-channel vector)
+    const float4* cur4 = reinterpret_cast<const float4*>(cur);
+    float4* tmp4 = reinterpret_cast<float4*>(tmp);
+    for (int i = threadIdx.x; i < npix * 2; i += blockDim.x) {
+      const int hf = i & 1, p = i >> 1, h = p / W, w = p - h * W;
+      float4 m = cur4[i];
+#pragma unroll
       for (int d = -2; d <= 2; ++d) {
         const int ww = w + d;
-        if (ww >= 0 && ww < W) m = fmaxf(m, cur[(h * W + ww) * 8 + c]);
+        if (d != 0 && ww >= 0 && ww < W) {
+          const float4 v = cur4[(p + d) * 2 + hf];
+          m.x = fmaxf(m.x, v.x);
+          m.y = fmaxf(m.y, v.y);
+          m.z = fmaxf(m.z, v.z);
+          m.w = fmaxf(m.w, v.w);
+        }
       }
-      tmp[i] = m;
+      tmp4[i] = m;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < npix * 8; i += blockDim.x) {
-      const int c = i & 7, p = i >> 3, w = p % W, h = p / W;
-      float m = -CUDART_INF_F;
+    float4* curw4 = reinterpret_cast<float4*>(cur);
+    for (int i = threadIdx.x; i < npix * 2; i += blockDim.x) {
+      const int hf = i & 1, p = i >> 1, h = p / W;
+      float4 m = tmp4[i];
+#pragma unroll
       for (int d = -2; d <= 2; ++d) {
         const int hh = h + d;
-        if (hh >= 0 && hh < H) m = fmaxf(m, tmp[(hh * W + w) * 8 + c]);
+        if (d != 0 && hh >= 0 && hh < H) {
+          const float4 v = tmp4[(p + d * W) * 2 + hf];
+          m.x = fmaxf(m.x, v.x);
+          m.y = fmaxf(m.y, v.y);
+          m.z = fmaxf(m.z, v.z);
+          m.w = fmaxf(m.w, v.w);
+        }
       }
-      cur[i] = m;
+      curw4[i] = m;
     }
     __syncthreads();
     for (int p = threadIdx.x; p < npix; p += blockDim.x) {

@@ -15,6 +15,7 @@
 // Pipeline: histogram of score bits -> per-image threshold bin (top max_nms) -> emit 64-bit keys
 // (score bits << 32 | ~candidate id) -> segmented bitonic sort (descending; shared-memory fused below 4096)
 // -> per-image greedy scan (warp-ballot compaction, 512x512 bit mask in shared memory, single-warp resolve).
+#include <cooperative_groups.h>
 #include <cuda_fp16.h>
 
 #include "internal.h"
@@ -85,6 +86,7 @@ static NmsWs carve_ws(void* ws, int B, int phase) {
 // reserves one contiguous range of the image's key array with a single global atomic and copies the keys out
 // coalesced -- the per-image counter sees ~A/64 atomics instead of one per candidate.
 constexpr int kRowsPerCta = 64;
+constexpr int kEmitSubs = 8;   // row blocks per CTA in the emit passes
 constexpr int kScanThreads = 256;
 
 __device__ __forceinline__ uint32_t score_bin(uint32_t bits) { return min(bits >> 17, (uint32_t)(kBins - 1)); }
@@ -97,16 +99,22 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const float* __r
   const int no = nc + 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
-  const int row0 = blockIdx.x * kRowsPerCta;
-  const int row1 = min(A, row0 + kRowsPerCta);
-  if (EMIT) {
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
-  }
   if (EMIT && ws.phase == 1 && ws.done[b]) return;  // phase A already produced this image's result
   const uint32_t tb = EMIT ? ws.tbin[b] : 0u;
   float* rowmax = ws.rowmax + (size_t)b * A;
   constexpr int R = 4;  // rows in flight per warp: all loads of a batch are issued before the first use
+  // EMIT CTAs walk kEmitSubs blocks of kRowsPerCta rows (most blocks have no row above the threshold bin and cost one
+  // rowmax read); the staging buffer is sized for one block and flushed after each
+  constexpr int SUBS = EMIT ? kEmitSubs : 1;
+  for (int sub = 0; sub < SUBS; ++sub) {
+  const int row0 = (blockIdx.x * SUBS + sub) * kRowsPerCta;
+  if (row0 >= A) break;
+  const int row1 = min(A, row0 + kRowsPerCta);
+  if (EMIT) {
+    __syncthreads();  // the previous block's keys have left the staging buffer
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+  }
   for (int base = row0 + warp * R; base < row1; base += (kScanThreads / 32) * R) {
     float obj[R];
     if constexpr (EMIT) {
@@ -272,14 +280,16 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const float* __r
   if (EMIT) {
     __syncthreads();
     const uint32_t n = s_cnt;
-    if (n == 0) return;
-    if (threadIdx.x == 0) s_base = atomicAdd(&ws.cnt[b], n);
-    __syncthreads();
-    const uint32_t base = s_base;
-    if (base + n > (uint32_t)ws.cap && ws.phase == 1 && status && threadIdx.x == 0) atomicExch(&status[0], 1);
-    uint64_t* keys = ws.keys + (size_t)b * ws.cap;
-    for (uint32_t i = threadIdx.x; i < n; i += kScanThreads)
-      if (base + i < (uint32_t)ws.cap) keys[base + i] = stage[i];
+    if (n != 0) {  // uniform
+      if (threadIdx.x == 0) s_base = atomicAdd(&ws.cnt[b], n);
+      __syncthreads();
+      const uint32_t base = s_base;
+      if (base + n > (uint32_t)ws.cap && ws.phase == 1 && status && threadIdx.x == 0) atomicExch(&status[0], 1);
+      uint64_t* keys = ws.keys + (size_t)b * ws.cap;
+      for (uint32_t i = threadIdx.x; i < n; i += kScanThreads)
+        if (base + i < (uint32_t)ws.cap) keys[base + i] = stage[i];
+    }
+  }
   }
 }
 
@@ -407,6 +417,91 @@ __device__ __forceinline__ bool iou_gt(const float4& a, float aa, const float4& 
   const float inter = __fmul_rn(w, h);
   const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(aa, ab), inter));
   return (double)ovr > thr;
+}
+
+// Phase B in ONE cooperative launch: the whole segmented bitonic sort (local sort, global steps, local merges) with grid-wide
+// barriers between steps.  When no image needs phase B (the common case: phase A already kept max_det boxes everywhere) every
+// CTA sees that from the `done` flags and returns before the first barrier, so the idle cost is one small launch instead of
+// fifteen.  Same compare-exchange network, hence the same (unique-key) result as the separate kernels above.
+__global__ void __launch_bounds__(1024) bitonic_full_sort_kernel(NmsWs ws, int B) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ uint64_t s[kChunk];
+  __shared__ int s_any;
+  if (threadIdx.x == 0) s_any = 0;
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    uint32_t n;
+    seg_npad(ws, b, &n);
+    if (n > 1) s_any = 1;
+  }
+  __syncthreads();
+  if (!s_any) return;  // identical decision in every CTA: nobody reaches a grid barrier
+  constexpr int kChunks = kCap / kChunk;
+  // ---- full sort of every 4096-key chunk
+  for (int w = blockIdx.x; w < kChunks * B; w += gridDim.x) {
+    const int b = w / kChunks;
+    const uint32_t start = (uint32_t)(w % kChunks) * kChunk;
+    uint32_t n;
+    const uint32_t npad = seg_npad(ws, b, &n);
+    if (start >= npad) continue;  // uniform per work item
+    uint64_t* keys = ws.keys + (size_t)b * ws.cap;
+    __syncthreads();
+    for (int i = threadIdx.x; i < kChunk; i += blockDim.x) s[i] = (start + i < n) ? keys[start + i] : 0ull;
+    for (int k = 2; k <= kChunk; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < kChunk / 2; t += blockDim.x) {
+          const int i = 2 * j * (t / j) + (t % j);
+          cmpswap(s, i, i + j, ((start + i) & k) == 0);
+        }
+      }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kChunk; i += blockDim.x) keys[start + i] = s[i];
+  }
+  grid.sync();
+  for (uint32_t k = 2 * kChunk; k <= (uint32_t)kCap; k <<= 1) {
+    for (uint32_t j = k >> 1; j >= (uint32_t)kChunk; j >>= 1) {
+      const uint32_t per = kCap / 2;
+      for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < per * (uint32_t)B; e += gridDim.x * blockDim.x) {
+        const int b = (int)(e / per);
+        const uint32_t t = e - (uint32_t)b * per;
+        uint32_t n;
+        const uint32_t npad = seg_npad(ws, b, &n);
+        if (k > npad) continue;
+        const uint32_t i = 2 * j * (t / j) + (t % j);
+        if (i >= npad) continue;
+        uint64_t* keys = ws.keys + (size_t)b * ws.cap;
+        const uint64_t x = keys[i], y = keys[i + j];
+        const bool desc = (i & k) == 0;
+        if (desc ? (x < y) : (x > y)) {
+          keys[i] = y;
+          keys[i + j] = x;
+        }
+      }
+      grid.sync();
+    }
+    for (int w = blockIdx.x; w < kChunks * B; w += gridDim.x) {
+      const int b = w / kChunks;
+      const uint32_t start = (uint32_t)(w % kChunks) * kChunk;
+      uint32_t n;
+      const uint32_t npad = seg_npad(ws, b, &n);
+      if (k > npad || start >= npad) continue;
+      uint64_t* keys = ws.keys + (size_t)b * ws.cap;
+      __syncthreads();
+      for (int i = threadIdx.x; i < kChunk; i += blockDim.x) s[i] = keys[start + i];
+      for (int j = kChunk >> 1; j > 0; j >>= 1) {
+        __syncthreads();
+        for (int t = threadIdx.x; t < kChunk / 2; t += blockDim.x) {
+          const int i = 2 * j * (t / j) + (t % j);
+          cmpswap(s, i, i + j, ((start + i) & k) == 0);
+        }
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < kChunk; i += blockDim.x) keys[start + i] = s[i];
+    }
+    grid.sync();
+  }
 }
 
 struct GreedySmem {
@@ -588,6 +683,7 @@ extern "C" int cvb_yolo_nms(const float* prediction, const CvbNmsParams* p, floa
   CVB_CHECK_CUDA(cudaMemsetAsync(det_idx, 0xFF, (size_t)p->B * p->max_det * sizeof(int32_t), st));
 
   dim3 sgrid(ceil_div(p->A, kRowsPerCta), p->B);
+  dim3 egrid(ceil_div(p->A, kRowsPerCta * kEmitSubs), p->B);
   const size_t stage_bytes = (size_t)kRowsPerCta * p->nc * sizeof(uint64_t);
   CVB_REQUIRE(stage_bytes <= 160 * 1024, "nms: too many classes (%d) for the shared-memory candidate stage", p->nc);
   const size_t gsmem = sizeof(GreedySmem) + (size_t)p->max_det * (sizeof(float4) + sizeof(float));
@@ -605,7 +701,7 @@ extern "C" int cvb_yolo_nms(const float* prediction, const CvbNmsParams* p, floa
   // ---- phase A: the top ~3k candidates of every image (one shared-memory sort chunk), early exit at max_det
   const int targetA = p->max_nms < kTargetA ? p->max_nms : kTargetA;
   nms_threshold_kernel<<<p->B, 256, 0, st>>>(wsA, targetA);
-  nms_scan_kernel<true><<<sgrid, kScanThreads, stage_bytes, st>>>(prediction, p->B, p->A, p->nc, p->conf_thres, p->multi_label, wsA, status);
+  nms_scan_kernel<true><<<egrid, kScanThreads, stage_bytes, st>>>(prediction, p->B, p->A, p->nc, p->conf_thres, p->multi_label, wsA, status);
   bitonic_local_sort_kernel<<<dim3(1, p->B), 1024, 0, st>>>(wsA);
   nms_greedy_kernel<<<p->B, kGreedyThreads, gsmem, st>>>(prediction, p->A, p->nc, wsA, p->iou_thres, p->max_nms, p->max_det, p->max_wh, det,
                                                          det_idx, det_count);
@@ -613,18 +709,21 @@ extern "C" int cvb_yolo_nms(const float* prediction, const CvbNmsParams* p, floa
   count_launch(4);
   // ---- phase B: full top-max_nms path for the images phase A could not finish (every kernel returns at once otherwise)
   nms_threshold_kernel<<<p->B, 256, 0, st>>>(wsB, p->max_nms);
-  nms_scan_kernel<true><<<sgrid, kScanThreads, stage_bytes, st>>>(prediction, p->B, p->A, p->nc, p->conf_thres, p->multi_label, wsB, status);
+  nms_scan_kernel<true><<<egrid, kScanThreads, stage_bytes, st>>>(prediction, p->B, p->A, p->nc, p->conf_thres, p->multi_label, wsB, status);
   count_launch(2);
-  dim3 lgrid(kCap / kChunk, p->B);
-  bitonic_local_sort_kernel<<<lgrid, 1024, 0, st>>>(wsB);
-  count_launch();
-  for (uint32_t k = 2 * kChunk; k <= (uint32_t)kCap; k <<= 1) {
-    for (uint32_t j = k >> 1; j >= (uint32_t)kChunk; j >>= 1) {
-      dim3 ggrid(kCap / 2 / 256, p->B);
-      bitonic_global_step_kernel<<<ggrid, 256, 0, st>>>(wsB, k, j);
-      count_launch();
+  {
+    static int coop_grid = 0;
+    if (coop_grid == 0) {
+      int dev = 0, sms = 0, per_sm = 0;
+      CVB_CHECK_CUDA(cudaGetDevice(&dev));
+      CVB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+      CVB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bitonic_full_sort_kernel, 1024, 0));
+      CVB_REQUIRE(sms > 0 && per_sm > 0, "nms: cooperative sort kernel cannot be resident");
+      coop_grid = sms;  // one CTA per SM: co-residency guaranteed (required by the grid barriers)
     }
-    bitonic_local_merge_kernel<<<lgrid, 1024, 0, st>>>(wsB, k);
+    int Bn = p->B;
+    void* cargs[2] = {&wsB, &Bn};
+    CVB_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(bitonic_full_sort_kernel), dim3(coop_grid), dim3(1024), cargs, 0, st));
     count_launch();
   }
   nms_greedy_kernel<<<p->B, kGreedyThreads, gsmem, st>>>(prediction, p->A, p->nc, wsB, p->iou_thres, p->max_nms, p->max_det, p->max_wh, det,
