@@ -291,11 +291,31 @@ def run_b200_arm(args):
         roof = None
         if conv_ms:
             ach = ALG_GFLOP_PER_IMG * B / conv_ms  # GFLOP / ms == TFLOP/s
+            # DRAM bytes of the conv launches of one bs64 step, from the committed ncu launch list (tools/launch_summary.py)
+            traffic = None
+            try:
+                tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01', 'conv_traffic.json')))
+                if int(tj.get('batch', 0)) == B:
+                    traffic = int(tj['conv_dram_bytes_per_step'])
+            except Exception:
+                pass
+            # per-layer conv roofline: sum_i max(3 * flops_i / P_tensor, bytes_i / BW_hbm) with the stored 4 B/element
+            hbm = float(peaks.get('hbm_gbs', 6500.0))
+            bound_ms = 0.0
+            for (_n, cin, cout, k, s_, Ho, Wo) in g.layer_log:
+                fl = 2.0 * B * Ho * Wo * cout * cin * k * k
+                by = 4.0 * (B * (Ho * s_) * (Wo * s_) * cin + B * Ho * Wo * cout) + 4.0 * cout * cin * k * k
+                bound_ms += max(3 * fl / (peak_tf * 1e12), by / (hbm * 1e9)) * 1e3
             roof = {'bound': 'tensor', 'achieved': round(ach, 2), 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': round(ach / peak_tf, 4),
-                    'traffic': None, 'kernel': 'conv_tc_kernel<*> (all %d fused conv launches of one step)' % g.n_convs,
+                    'traffic': traffic, 'kernel': 'conv_tc_kernel<*> (all %d fused conv launches of one step)' % g.n_convs,
                     'conv_ms_per_step': round(conv_ms, 4), 'peak_source': peak_src,
-                    'note': 'algorithmic FLOPs 2*M*N*K of the fp32 reference graph (1051.75 GFLOP/bs64); the kernel issues 3 fp16 MMAs per product '
-                            '(hi/lo split, fp32-equivalent accuracy), so frac <= 1/3 by construction; per-layer numbers in profiles/'}
+                    'algorithmic_bytes_per_step': int(7.80e9 * B / 64),
+                    'per_layer_roofline': {'bound_ms': round(bound_ms, 4), 'frac': round(bound_ms / conv_ms, 4),
+                                           'definition': 'sum over the conv layers of max(3*flops/P_tensor, bytes/BW_hbm): three fp16 MMA products per '
+                                                         'fp32 product, activations stored as fp16 hi+lo (4 B/element); P = %.1f TF/s, BW = %.1f GB/s' % (peak_tf, hbm)},
+                    'note': 'algorithmic FLOPs 2*M*N*K of the fp32 reference graph (1051.75 GFLOP/bs64); the kernel issues 3 fp16 MMA products per fp32 '
+                            'product (hi/lo split, fp32-equivalent accuracy), so frac <= 1/3 by construction; traffic = dram read+write of the conv '
+                            'launches of one step (ncu, profiles/r01); per-layer numbers in profiles/'}
         cpu_v, cores, spt, sample = cpu_reference_throughput(args.cpu_steps, 1) if args.cpu_steps > 0 else (None, 0, 0, 'skipped')
         line = {'metric': METRIC, 'value': round(value, 2), 'unit': 'images/sec', 'n_gpus': world, 'steps': K, 'warmup': W,
                 'ms_per_step': round(ms_per_step, 4), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,

@@ -80,133 +80,153 @@ static NmsWs carve_ws(void* ws, int B, int phase) {
   return w;
 }
 
-// ------------------------------------------------------------------ pass 1/2: scan predictions
-// Grid (ceil(A / kRowsPerCta), B); each warp walks rows of ONE image.  COUNT pass: histogram of score bits (spread
-// global atomics).  EMIT pass: candidates are staged in shared memory (warp-aggregated smem atomics), then the CTA
-// reserves one contiguous range of the image's key array with a single global atomic and copies the keys out
-// coalesced -- the per-image counter sees ~A/64 atomics instead of one per candidate.
+// ------------------------------------------------------------------ counting pass (only when the decode kernel did not build the histogram)
+// Grid (ceil(A / kRowsPerCta), B); each warp walks rows of ONE image: histogram of score bits (spread global atomics) and the
+// per-row best score (rowmax) that lets the emit passes skip rows.
 constexpr int kRowsPerCta = 64;
-constexpr int kEmitSubs = 8;   // row blocks per CTA in the emit passes
 constexpr int kScanThreads = 256;
 
 __device__ __forceinline__ uint32_t score_bin(uint32_t bits) { return min(bits >> 17, (uint32_t)(kBins - 1)); }
 
-template <bool EMIT>
-__global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const float* __restrict__ pred, int B, int A, int nc, float conf,
-                                                                int multi_label, NmsWs ws, int* __restrict__ status) {
-  extern __shared__ uint64_t stage[];  // EMIT: [kRowsPerCta * nc] worst case
-  __shared__ uint32_t s_cnt, s_base;
+__global__ void __launch_bounds__(kScanThreads) nms_count_kernel(const float* __restrict__ pred, int A, int nc, float conf, int multi_label,
+                                                                 NmsWs ws) {
   const int no = nc + 5;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.y;
-  if (EMIT && ws.phase == 1 && ws.done[b]) return;  // phase A already produced this image's result
-  const uint32_t tb = EMIT ? ws.tbin[b] : 0u;
-  float* rowmax = ws.rowmax + (size_t)b * A;
-  constexpr int R = 4;  // rows in flight per warp: all loads of a batch are issued before the first use
-  // EMIT CTAs walk kEmitSubs blocks of kRowsPerCta rows (most blocks have no row above the threshold bin and cost one
-  // rowmax read); the staging buffer is sized for one block and flushed after each
-  constexpr int SUBS = EMIT ? kEmitSubs : 1;
-  for (int sub = 0; sub < SUBS; ++sub) {
-  const int row0 = (blockIdx.x * SUBS + sub) * kRowsPerCta;
-  if (row0 >= A) break;
+  const int row0 = blockIdx.x * kRowsPerCta;
   const int row1 = min(A, row0 + kRowsPerCta);
-  if (EMIT) {
-    __syncthreads();  // the previous block's keys have left the staging buffer
-    if (threadIdx.x == 0) s_cnt = 0;
-    __syncthreads();
-  }
+  float* rowmax = ws.rowmax + (size_t)b * A;
+  uint32_t* hist = ws.hist + (size_t)b * kBins;
+  constexpr int R = 4;  // rows in flight per warp: all loads of a batch are issued before the first use
   for (int base = row0 + warp * R; base < row1; base += (kScanThreads / 32) * R) {
     float obj[R];
-    if constexpr (EMIT) {
-      // rows whose best score falls below the threshold bin cannot emit anything: skip their 340-byte reads
-      float rm = 0.0f;
-      if (lane < R && base + lane < row1) rm = __ldg(rowmax + base + lane);
-      const uint32_t rb = __float_as_uint(rm);
-      const uint32_t live = __ballot_sync(0xffffffffu, rb != 0u && score_bin(rb) >= tb);
-      if (live == 0u) continue;
 #pragma unroll
-      for (int i = 0; i < R; ++i) {
-        const int anchor = min(base + i, row1 - 1);
-        obj[i] = ((live >> i) & 1u) ? __ldg(pred + ((size_t)b * A + anchor) * no + 4) : 0.0f;  // 0 never passes obj > conf
+    for (int i = 0; i < R; ++i) {
+      const int anchor = min(base + i, row1 - 1);
+      obj[i] = __ldg(pred + ((size_t)b * A + anchor) * no + 4);
+    }
+    for (int i = 0; i < R; ++i) {
+      const int anchor = base + i;
+      if (anchor >= row1) continue;
+      if (!(obj[i] > conf)) {
+        if (lane == 0) rowmax[anchor] = 0.0f;
+        continue;
       }
-    } else {
+      const float* r = pred + ((size_t)b * A + anchor) * no;
+      const float ob = obj[i];
+      float rbest = 0.0f;
+      if (multi_label) {
+        for (int c = lane; c < nc; c += 32) {
+          const float sc = __fmul_rn(__ldg(r + 5 + c), ob);
+          if (sc > conf) {
+            atomicAdd(&hist[score_bin(__float_as_uint(sc))], 1u);
+            rbest = fmaxf(rbest, sc);
+          }
+        }
+      } else {
+        // best class only: conf, j = x[:, 5:].max(1)
+        for (int c = lane; c < nc; c += 32) rbest = fmaxf(rbest, __fmul_rn(__ldg(r + 5 + c), ob));
+      }
 #pragma unroll
-      for (int i = 0; i < R; ++i) {
-        const int anchor = min(base + i, row1 - 1);
-        obj[i] = __ldg(pred + ((size_t)b * A + anchor) * no + 4);
+      for (int o = 16; o > 0; o >>= 1) rbest = fmaxf(rbest, __shfl_xor_sync(0xffffffffu, rbest, o));
+      if (!(rbest > conf)) rbest = 0.0f;
+      if (lane == 0) {
+        rowmax[anchor] = rbest;
+        if (!multi_label && rbest > conf) atomicAdd(&hist[score_bin(__float_as_uint(rbest))], 1u);
       }
     }
+  }
+}
+
+// ------------------------------------------------------------------ emit pass (both phases)
+// Grid (ceil(A / kEmitRows), B).  Step 1: one coalesced read of the CTA's rowmax slice builds the list of live rows (best score
+// in or above the threshold bin) in shared memory -- in phase A that is a few percent of the rows, so almost nothing of the
+// 548 MB prediction tensor is touched.  Step 2: the warps walk the live rows in batches of kRowsPerCta (the staging buffer's
+// worst case), recompute obj*cls exactly as the counting pass did, stage the keys and copy each batch out with one global
+// atomic.  Key order inside the image's array is irrelevant (unique keys, sorted next).
+constexpr int kEmitRows = 512;
+
+__global__ void __launch_bounds__(kScanThreads) nms_emit_kernel(const float* __restrict__ pred, int A, int nc, float conf, int multi_label,
+                                                                NmsWs ws, int* __restrict__ status) {
+  extern __shared__ uint64_t stage[];  // [kRowsPerCta * nc] worst case of one batch
+  __shared__ uint32_t s_cnt, s_base, s_nlive;
+  __shared__ int s_live[kEmitRows];
+  const int no = nc + 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  if (ws.phase == 1 && ws.done[b]) return;  // phase A already produced this image's result
+  const uint32_t tb = ws.tbin[b];
+  const float* rowmax = ws.rowmax + (size_t)b * A;
+  const int row0 = blockIdx.x * kEmitRows;
+  if (threadIdx.x == 0) s_nlive = 0;
+  __syncthreads();
+  for (int r = threadIdx.x; r < kEmitRows; r += kScanThreads) {
+    const int row = row0 + r;
+    if (row < A) {
+      const uint32_t rb = __float_as_uint(__ldg(rowmax + row));
+      if (rb != 0u && score_bin(rb) >= tb) s_live[atomicAdd(&s_nlive, 1u)] = row;
+    }
+  }
+  __syncthreads();
+  const int nlive = (int)s_nlive;
+  for (int batch0 = 0; batch0 < nlive; batch0 += kRowsPerCta) {  // uniform trip count
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const int batch1 = min(nlive, batch0 + kRowsPerCta);
     if (multi_label && nc <= 96) {
-      float v[R][3];
+      // hot configuration: R live rows per warp in flight, objectness and the three class chunks of every row requested
+      // together (a live row always passes obj > conf), so a CTA pays about one DRAM latency per batch
+      constexpr int R = 4, NW = kScanThreads / 32;
+      for (int l0 = batch0 + warp; l0 < batch1; l0 += NW * R) {
+        float v[R][3], ob[R];
+        int an[R];
 #pragma unroll
-      for (int i = 0; i < R; ++i) {
-        const int anchor = min(base + i, row1 - 1);
-        const float* r = pred + ((size_t)b * A + anchor) * no + 5;
+        for (int i = 0; i < R; ++i) {
+          const int li = l0 + i * NW;
+          an[i] = s_live[min(li, batch1 - 1)];
+          const float* r = pred + ((size_t)b * A + an[i]) * no;
+          ob[i] = __ldg(r + 4);
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int c = k * 32 + lane;
-          v[i][k] = (obj[i] > conf && c < nc) ? __ldg(r + c) : 0.0f;
+          for (int k = 0; k < 3; ++k) {
+            const int c = k * 32 + lane;
+            v[i][k] = (c < nc) ? __ldg(r + 5 + c) : 0.0f;
+          }
         }
-      }
 #pragma unroll
-      for (int i = 0; i < R; ++i) {
-        const int anchor = base + i;
-        if (anchor >= row1) continue;
-        if (!(obj[i] > conf)) {
-          if (!EMIT && lane == 0) rowmax[anchor] = 0.0f;
-          continue;
-        }
-        float rbest = 0.0f;
+        for (int i = 0; i < R; ++i) {
+          if (l0 + i * NW >= batch1 || !(ob[i] > conf)) continue;  // warp-uniform
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int c = k * 32 + lane;
-          if (k * 32 >= nc) break;
-          bool pass = false;
-          uint32_t bits = 0;
-          if (c < nc) {
-            const float sc = __fmul_rn(v[i][k], obj[i]);
-            if (sc > conf) {
-              bits = __float_as_uint(sc);
-              const uint32_t bin = score_bin(bits);
-              if constexpr (EMIT) pass = bin >= tb;
-              else {
-                atomicAdd(&ws.hist[(size_t)b * kBins + bin], 1u);
-                rbest = fmaxf(rbest, sc);
+          for (int k = 0; k < 3; ++k) {
+            const int c = k * 32 + lane;
+            bool pass = false;
+            uint32_t bits = 0;
+            if (c < nc) {
+              const float sc = __fmul_rn(v[i][k], ob[i]);
+              if (sc > conf) {
+                bits = __float_as_uint(sc);
+                pass = score_bin(bits) >= tb;
               }
             }
-          }
-          if (EMIT) {
             const uint32_t m = __ballot_sync(0xffffffffu, pass);
             if (m) {
               uint32_t sb = 0;
               if (lane == 0) sb = atomicAdd(&s_cnt, (uint32_t)__popc(m));
               sb = __shfl_sync(0xffffffffu, sb, 0);
               if (pass) {
-                const uint32_t id = (uint32_t)anchor * (uint32_t)nc + (uint32_t)c;
+                const uint32_t id = (uint32_t)an[i] * (uint32_t)nc + (uint32_t)c;
                 stage[sb + __popc(m & ((1u << lane) - 1))] = ((uint64_t)bits << 32) | (uint64_t)(0xFFFFFFFFu - id);
               }
             }
           }
         }
-        if (!EMIT) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) rbest = fmaxf(rbest, __shfl_xor_sync(0xffffffffu, rbest, o));
-          if (lane == 0) rowmax[anchor] = rbest;
-        }
       }
-      continue;
-    }
-    for (int i = 0; i < R; ++i) {
-      const int anchor = base + i;
-      if (anchor >= row1) continue;
-      if (!(obj[i] > conf)) {
-        if (!EMIT && lane == 0) rowmax[anchor] = 0.0f;
-        continue;
-      }
+    } else
+    for (int li = batch0 + warp; li < batch1; li += kScanThreads / 32) {
+      const int anchor = s_live[li];
       const float* r = pred + ((size_t)b * A + anchor) * no;
-      const float ob = obj[i];
+      const float ob = __ldg(r + 4);
+      if (!(ob > conf)) continue;  // cannot happen for a live row; kept for symmetry with the counting pass
       if (multi_label) {
-        float rbest = 0.0f;
         for (int c0 = 0; c0 < nc; c0 += 32) {
           const int c = c0 + lane;
           bool pass = false;
@@ -215,31 +235,19 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const float* __r
             const float sc = __fmul_rn(__ldg(r + 5 + c), ob);
             if (sc > conf) {
               bits = __float_as_uint(sc);
-              const uint32_t bin = score_bin(bits);
-              if constexpr (EMIT) pass = bin >= tb;
-              else {
-                atomicAdd(&ws.hist[(size_t)b * kBins + bin], 1u);
-                rbest = fmaxf(rbest, sc);
-              }
+              pass = score_bin(bits) >= tb;
             }
           }
-          if (EMIT) {
-            const uint32_t m = __ballot_sync(0xffffffffu, pass);
-            if (m) {
-              uint32_t sb = 0;
-              if (lane == 0) sb = atomicAdd(&s_cnt, (uint32_t)__popc(m));
-              sb = __shfl_sync(0xffffffffu, sb, 0);
-              if (pass) {
-                const uint32_t id = (uint32_t)anchor * (uint32_t)nc + (uint32_t)c;
-                stage[sb + __popc(m & ((1u << lane) - 1))] = ((uint64_t)bits << 32) | (uint64_t)(0xFFFFFFFFu - id);
-              }
+          const uint32_t m = __ballot_sync(0xffffffffu, pass);
+          if (m) {
+            uint32_t sb = 0;
+            if (lane == 0) sb = atomicAdd(&s_cnt, (uint32_t)__popc(m));
+            sb = __shfl_sync(0xffffffffu, sb, 0);
+            if (pass) {
+              const uint32_t id = (uint32_t)anchor * (uint32_t)nc + (uint32_t)c;
+              stage[sb + __popc(m & ((1u << lane) - 1))] = ((uint64_t)bits << 32) | (uint64_t)(0xFFFFFFFFu - id);
             }
           }
-        }
-        if (!EMIT) {
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) rbest = fmaxf(rbest, __shfl_xor_sync(0xffffffffu, rbest, o));
-          if (lane == 0) rowmax[anchor] = rbest;
         }
       } else {
         // best class only: conf, j = x[:, 5:].max(1)  (first maximum wins ties)
@@ -261,23 +269,15 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const float* __r
             bi = oi;
           }
         }
-        if (!EMIT && lane == 0) rowmax[anchor] = best > conf ? best : 0.0f;
         if (lane == 0 && best > conf) {
           const uint32_t bits = __float_as_uint(best);
-          const uint32_t bin = score_bin(bits);
-          if constexpr (EMIT) {
-            if (bin >= tb) {
-              const uint32_t id = (uint32_t)anchor * (uint32_t)nc + (uint32_t)bi;
-              stage[atomicAdd(&s_cnt, 1u)] = ((uint64_t)bits << 32) | (uint64_t)(0xFFFFFFFFu - id);
-            }
-          } else {
-            atomicAdd(&ws.hist[(size_t)b * kBins + bin], 1u);
+          if (score_bin(bits) >= tb) {
+            const uint32_t id = (uint32_t)anchor * (uint32_t)nc + (uint32_t)bi;
+            stage[atomicAdd(&s_cnt, 1u)] = ((uint64_t)bits << 32) | (uint64_t)(0xFFFFFFFFu - id);
           }
         }
       }
     }
-  }
-  if (EMIT) {
     __syncthreads();
     const uint32_t n = s_cnt;
     if (n != 0) {  // uniform
@@ -289,41 +289,56 @@ __global__ void __launch_bounds__(kScanThreads) nms_scan_kernel(const float* __r
       for (uint32_t i = threadIdx.x; i < n; i += kScanThreads)
         if (base + i < (uint32_t)ws.cap) keys[base + i] = stage[i];
     }
-  }
+    __syncthreads();
   }
 }
 
 // ------------------------------------------------------------------ threshold bin: smallest set of top bins holding >= max_nms
-__global__ void nms_threshold_kernel(NmsWs ws, int target) {
-  __shared__ uint32_t part[256];
+__global__ void __launch_bounds__(256) nms_threshold_kernel(NmsWs ws, int target) {
+  __shared__ uint32_t seg[kBins / 32];  // sums of 32-bin segments (coalesced reads, one warp reduction each)
   const int b = blockIdx.x;
   const uint32_t* h = ws.hist + (size_t)b * kBins;
-  constexpr int per = kBins / 256;
-  const int t = threadIdx.x;
-  const int hi_bin = kBins - 1 - t * per;  // this thread walks bins hi_bin, hi_bin-1, ... (top-down)
-  uint32_t s = 0;
-  for (int i = 0; i < per; ++i) s += h[hi_bin - i];
-  part[t] = s;
-  __syncthreads();
-  if (t == 0) {
-    uint32_t run = 0;
-    for (int i = 0; i < 256; ++i) {
-      const uint32_t v = part[i];
-      part[i] = run;  // exclusive prefix (count in all higher bins)
-      run += v;
-    }
-    ws.tbin[b] = 0;  // default: everything
-    ws.total[b] = run;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int sgi = warp; sgi < kBins / 32; sgi += 8) {
+    uint32_t v = h[sgi * 32 + lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) seg[sgi] = v;
   }
   __syncthreads();
-  uint32_t run = part[t];
-  if (run < (uint32_t)target) {
-    for (int i = 0; i < per; ++i) {
-      run += h[hi_bin - i];
-      if (run >= (uint32_t)target) {
-        ws.tbin[b] = (uint32_t)(hi_bin - i);  // exactly one thread crosses the threshold
+  if (warp != 0) return;
+  // top-down scan: lane l owns the kPer consecutive segments just below those of lane l-1
+  constexpr int kPer = kBins / 32 / 32;
+  const int top = kBins / 32 - 1 - lane * kPer;
+  uint32_t part = 0;
+  for (int i = 0; i < kPer; ++i) part += seg[top - i];
+  uint32_t incl = part;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  if (lane == 0) {
+    ws.tbin[b] = 0;  // default: everything
+    ws.total[b] = total;
+  }
+  __syncwarp();
+  uint32_t run = incl - part;  // candidates in all higher segments
+  if (run < (uint32_t)target && incl >= (uint32_t)target) {  // exactly one lane crosses the target
+    for (int i = 0; i < kPer; ++i) {
+      const int sgi = top - i;
+      if (run + seg[sgi] >= (uint32_t)target) {
+        for (int j = 31; j >= 0; --j) {
+          run += h[sgi * 32 + j];
+          if (run >= (uint32_t)target) {
+            ws.tbin[b] = (uint32_t)(sgi * 32 + j);
+            break;
+          }
+        }
         break;
       }
+      run += seg[sgi];
     }
   }
 }
@@ -683,25 +698,25 @@ extern "C" int cvb_yolo_nms(const float* prediction, const CvbNmsParams* p, floa
   CVB_CHECK_CUDA(cudaMemsetAsync(det_idx, 0xFF, (size_t)p->B * p->max_det * sizeof(int32_t), st));
 
   dim3 sgrid(ceil_div(p->A, kRowsPerCta), p->B);
-  dim3 egrid(ceil_div(p->A, kRowsPerCta * kEmitSubs), p->B);
+  dim3 egrid(ceil_div(p->A, kEmitRows), p->B);
   const size_t stage_bytes = (size_t)kRowsPerCta * p->nc * sizeof(uint64_t);
   CVB_REQUIRE(stage_bytes <= 160 * 1024, "nms: too many classes (%d) for the shared-memory candidate stage", p->nc);
   const size_t gsmem = sizeof(GreedySmem) + (size_t)p->max_det * (sizeof(float4) + sizeof(float));
   CVB_REQUIRE(gsmem <= 200 * 1024, "nms: max_det too large");
   static bool attr_set = false;
   if (!attr_set) {
-    CVB_CHECK_CUDA(cudaFuncSetAttribute(nms_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CVB_CHECK_CUDA(cudaFuncSetAttribute(nms_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     CVB_CHECK_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
   if (!p->hist_ready) {
-    nms_scan_kernel<false><<<sgrid, kScanThreads, 0, st>>>(prediction, p->B, p->A, p->nc, p->conf_thres, p->multi_label, wsB, status);
+    nms_count_kernel<<<sgrid, kScanThreads, 0, st>>>(prediction, p->A, p->nc, p->conf_thres, p->multi_label, wsB);
     count_launch();
   }
   // ---- phase A: the top ~3k candidates of every image (one shared-memory sort chunk), early exit at max_det
   const int targetA = p->max_nms < kTargetA ? p->max_nms : kTargetA;
   nms_threshold_kernel<<<p->B, 256, 0, st>>>(wsA, targetA);
-  nms_scan_kernel<true><<<egrid, kScanThreads, stage_bytes, st>>>(prediction, p->B, p->A, p->nc, p->conf_thres, p->multi_label, wsA, status);
+  nms_emit_kernel<<<egrid, kScanThreads, stage_bytes, st>>>(prediction, p->A, p->nc, p->conf_thres, p->multi_label, wsA, status);
   bitonic_local_sort_kernel<<<dim3(1, p->B), 1024, 0, st>>>(wsA);
   nms_greedy_kernel<<<p->B, kGreedyThreads, gsmem, st>>>(prediction, p->A, p->nc, wsA, p->iou_thres, p->max_nms, p->max_det, p->max_wh, det,
                                                          det_idx, det_count);
@@ -709,7 +724,7 @@ extern "C" int cvb_yolo_nms(const float* prediction, const CvbNmsParams* p, floa
   count_launch(4);
   // ---- phase B: full top-max_nms path for the images phase A could not finish (every kernel returns at once otherwise)
   nms_threshold_kernel<<<p->B, 256, 0, st>>>(wsB, p->max_nms);
-  nms_scan_kernel<true><<<egrid, kScanThreads, stage_bytes, st>>>(prediction, p->B, p->A, p->nc, p->conf_thres, p->multi_label, wsB, status);
+  nms_emit_kernel<<<egrid, kScanThreads, stage_bytes, st>>>(prediction, p->A, p->nc, p->conf_thres, p->multi_label, wsB, status);
   count_launch(2);
   {
     static int coop_grid = 0;

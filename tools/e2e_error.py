@@ -12,4 +12,4 @@ m.predict(x); e128 = rel(m._graph_for(x)['z'], g['z'])
 g = np.load(os.path.join(ROOT, 'tests/golden/yolov5s_fwd640.npz'))
 torch.manual_seed(1029); x = torch.randn(1, 3, 640, 640).cuda()
 m.predict(x); e640 = rel(m._graph_for(x)['z'][0, ::16], g['z_sub'])
-print(f'CVB_MAX_CHAIN={os.environ.get("CVB_MAX_CHAIN", "48(default)")}: decoded z rel err vs reference golden: 128x128 {e128:.2e}, 640x640 {e640:.2e}')
+print(f'CVB_MAX_CHAIN={os.environ.get("CVB_MAX_CHAIN", "160(default)")}: decoded z rel err vs reference golden: 128x128 {e128:.2e}, 640x640 {e640:.2e}')

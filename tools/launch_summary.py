@@ -1,6 +1,6 @@
 """Summarise an `ncu --csv` launch list (gpu__time_duration + dram bytes): per-kernel totals of ONE step of bench.py.
-Usage: python tools/launch_summary.py <csv> [first_kernel_substring=stem_s2d]"""
-import csv, collections, sys
+Usage: python tools/launch_summary.py <csv> [first_kernel_substring=stem_s2d] [out.json batch]"""
+import csv, collections, json, sys
 path = sys.argv[1]
 anchor = sys.argv[2] if len(sys.argv) > 2 else 'stem_s2d'
 with open(path) as f:
@@ -30,3 +30,9 @@ for n, a in agg.items():
     tot += a[1]
     if 'conv_tc' in n: conv_b += a[2] + a[3]; conv_t += a[1]
 print(f'total {tot:.1f} us; conv_tc: {conv_t:.1f} us, DRAM traffic {conv_b / 1e9:.3f} GB per step')
+if len(sys.argv) > 4:
+    json.dump({'batch': int(sys.argv[4]), 'conv_dram_bytes_per_step': int(conv_b), 'conv_us_per_step_under_ncu': round(conv_t, 1),
+               'step_us_under_ncu': round(tot, 1), 'kernels': {n: {'launches': a[0], 'us': round(a[1], 1), 'dram_read_MB': round(a[2] / 1e6, 1),
+                                                                    'dram_write_MB': round(a[3] / 1e6, 1)} for n, a in agg.items()},
+               'source': path.split('/')[-1], 'how': 'ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none; one step of bench.py'},
+              open(sys.argv[3], 'w'), indent=1)

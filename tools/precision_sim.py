@@ -1,3 +1,12 @@
+"""Test-infrastructure tool (not on the product path): simulates cheaper operand formats on the CPU oracle to show why the
+conv kernel keeps fp16 (hi, lo) pairs for BOTH operands.  Rounds conv inputs and/or weights of every layer of the calibrated
+YOLOv5-s oracle to fp16 / bf16 and reports the end-to-end error at 1x3x640x640 against the fp32 oracle:
+  fp16     activations and weights rounded to fp16 (what a single tensor-core pass computes)  -> logits 1.4e-2
+  a16w32   only activations rounded                                                          -> 1.2e-2
+  a32w16   only weights rounded                                                              -> 9.8e-3
+  bf16     both rounded to bf16                                                              -> 1.4e-1
+All are 10-100x outside the 1e-3 budget of BASELINE.json (the calibrated random network amplifies per-layer rounding ~28x),
+whereas the three-product fp16 split measures 2e-5 on the GPU (profiles/r01/e2e_error_vs_reference_golden.txt)."""
 import sys, os
 sys.path.insert(0, '/root/repo')
 import torch, numpy as np, torch.nn.functional as F
