@@ -111,7 +111,6 @@ struct ConvCfg {
   static constexpr int OUT_PLANE_BYTES = kTileM * OUT_ROW_BYTES;
   static constexpr int OUT_STAGE_BYTES = OUT_PLANE_BYTES * (OUT_F32 ? 1 : 2);
   static constexpr int TAIL_BYTES = BLOCK_N * 4 + 64 * 8 + 16;  // bias + barriers + tmem slot
-  static constexpr int smem_bytes(int stages) { return 1024 + stages * STAGE_BYTES + OUT_STAGE_BYTES + TAIL_BYTES; }
 };
 
 template <int BLOCK_N, int BLOCK_K, bool OUT_F32>
@@ -125,8 +124,14 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
   constexpr int OUT_ROW_BYTES = Cfg::OUT_ROW_BYTES;
   constexpr uint32_t IDESC = make_idesc_f16_f32(kTileM, BLOCK_N);
 
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // the kernel has no static shared memory, so the dynamic window starts at offset 0 of the CTA's (1024-byte aligned)
+  // allocation; checked once instead of spending 1 KB of slack (which is what lets some two-CTA plans fit in 113 KB)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0u) {
+    printf("conv_tc_kernel: dynamic shared memory is not 1024-byte aligned\n");
+    __trap();
+  }
   const int STAGES = a.stages;
   const int stage_bytes = a.b_resident ? 2 * A_BYTES : STAGE_BYTES;
   uint8_t* stage_base = smem;
@@ -667,7 +672,16 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   if (f32) CVB_REQUIRE(out.c_pitch % 4 == 0, "conv: fp32 output pitch must be a multiple of 4");
 
   int bn = d->block_n;
-  if (bn == 0) bn = cout <= 32 ? 32 : (cout <= 64 ? 64 : 128);
+  if (bn == 0) {
+    bn = cout <= 32 ? 32 : (cout <= 64 ? 64 : 128);
+    static const int split128 = [] {
+      // 128-wide 1x1 layers with cin <= 128 run as two pinned 64-wide n-tiles so that two CTAs share an SM (measured +3-10 % on
+      // those layers; the activation tile is read twice, from L2).  CVB_SPLIT_N128=0 restores one 128-wide tile per CTA.
+      const char* e = getenv("CVB_SPLIT_N128");
+      return e ? atoi(e) : 1;
+    }();
+    if (split128 && !f32 && d->kh * d->kw == 1 && cout == 128 && cin <= 128 && cin % 64 == 0) bn = 64;
+  }
   int bk = (cin % 64 == 0) ? 64 : (cin % 32 == 0 ? 32 : 16);
   {
     static const int bk_small = [] {
@@ -678,7 +692,7 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
     // 64-channel inputs into narrow tiles (1x1 convs and the row-window stems): half-size K chunks let two CTAs share an SM
     // (see plan_smem below), which hides the epilogue latency these HBM-bound layers are limited by.  Multi-tap 3x3 layers
     // keep 64-wide chunks: measured slower with twice the TMA operations.
-    if (bn <= 64 && cin == 64 && (d->kh * d->kw == 1 || win > 0)) bk = bk_small;
+    if (bn <= 64 && (cin == 64 || (cin == 128 && cout > 64)) && (d->kh * d->kw == 1 || win > 0)) bk = bk_small;
   }
   KernelEntry ke;
   CVB_REQUIRE(lookup_kernel(bn, bk, f32, &ke), "conv: no kernel for block_n=%d block_k=%d", bn, bk);
@@ -841,7 +855,7 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   const int k_iters = a.taps * a.chunks;
   const int a_stage = 2 * kTileM * bk * 2;   // hi + lo activation tiles of one K chunk
   const int b_stage = 2 * bn * bk * 2;       // hi + lo weight tiles of one K chunk
-  const int base = 1024 + ke.tail_bytes + (a.resid_tma ? ke.out_stage_bytes : 0);
+  const int base = ke.tail_bytes + (a.resid_tma ? ke.out_stage_bytes : 0);
   const bool can_pin_n = (a.tiles_n == 1 || a.tiles_n == 2 || a.tiles_n == 4);
   // ring depth / resident weights / staging buffers that fit `budget` bytes of dynamic shared memory (0 stages = no fit)
   auto plan_smem = [&](int budget, int& resident, int& out_bufs) -> int {
