@@ -43,6 +43,7 @@ SYMBOLS = {
     'cvb_split_to_nchw': (c_int32, [POINTER(CvbView), c_void_p, c_void_p]),
     'cvb_f32nhwc_to_nchw': (c_int32, [POINTER(CvbView), c_void_p, c_void_p]),
     'cvb_stem_s2d': (c_int32, [c_void_p, c_int32, c_int32, c_int32, POINTER(CvbView), c_int32, c_void_p]),
+    'cvb_stem_s2d_u8': (c_int32, [c_void_p, c_int32, c_int32, c_int32, POINTER(c_float), POINTER(c_float), c_int32, POINTER(CvbView), c_int32, c_void_p]),
     'cvb_maxpool3x3s2': (c_int32, [POINTER(CvbView), POINTER(CvbView), c_void_p]),
     'cvb_split_to_f32nhwc': (c_int32, [POINTER(CvbView), POINTER(CvbView), c_void_p]),
     'cvb_groupnorm_workspace_bytes': (c_size_t, [c_int32, c_int32]),

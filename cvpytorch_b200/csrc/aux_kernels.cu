@@ -118,6 +118,94 @@ __global__ void stem_s2d_kernel(const float* __restrict__ src, int B, int H, int
   }
 }
 
+// Same output, fed by the camera-side format: uint8 HWC frames.  ToTensor (src/data/transforms/det_transforms.py:85-99: HWC->CHW,
+// channel reversal BGR->RGB, float32 / 255) and Normalize (:102-109, torchvision F.normalize: (x - mean) / std in fp32) are
+// applied while the 2x2x3 patch is in registers, with the reference's operation order and IEEE division, so the result is
+// bit-identical to stem_s2d_kernel on the tensor the reference's transforms would have produced.  One thread per output pixel:
+// reads 2 rows x 6 contiguous bytes.
+// A 256-entry table per output channel (built per CTA with exactly those operations) replaces 24 IEEE divisions per thread.
+// PAIR: one thread converts two horizontally adjacent output pixels = 12 contiguous source bytes per row (three aligned 32-bit
+// loads; needs W % 4 == 0); otherwise one output pixel per thread with 16-bit loads.
+template <bool PAIR>
+__global__ void __launch_bounds__(256) stem_s2d_u8_kernel(const uint8_t* __restrict__ src, int B, int H, int W, float m0, float m1, float m2,
+                                                          float s0, float s1, float s2, int reverse, __half* __restrict__ dst, int pitch,
+                                                          long long plane, int Wd, int col_off) {
+  __shared__ float lut[3][256];  // lut[c][byte] for OUTPUT channel c
+  {
+    const float mean[3] = {m0, m1, m2}, stdv[3] = {s0, s1, s2};
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+      const int c = i >> 8;
+      lut[c][i & 255] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(i & 255), 255.0f), mean[c]), stdv[c]);
+    }
+  }
+  __syncthreads();
+  const int W2 = W >> 1, H2 = H >> 1;
+  constexpr int PX = PAIR ? 2 : 1;
+  const int Wt = W2 / PX;
+  const long long n = (long long)B * H2 * Wt;
+  const int cmap0 = reverse ? 2 : 0, cmap2 = reverse ? 0 : 2;  // output channel of source channels 0 and 2 (1 stays 1)
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int wt = (int)(i % Wt);
+    const long long t = i / Wt;
+    const int h2 = (int)(t % H2);
+    const int b = (int)(t / H2);
+    const int w2 = wt * PX;
+    uint8_t px[2][6 * PX];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const uint8_t* p = src + (((size_t)b * H + (2 * h2 + dy)) * W + 2 * w2) * 3;
+      if constexpr (PAIR) {
+        const uint32_t* p4 = reinterpret_cast<const uint32_t*>(p);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const uint32_t a = __ldg(p4 + k);
+          px[dy][4 * k + 0] = (uint8_t)(a & 0xFF);
+          px[dy][4 * k + 1] = (uint8_t)((a >> 8) & 0xFF);
+          px[dy][4 * k + 2] = (uint8_t)((a >> 16) & 0xFF);
+          px[dy][4 * k + 3] = (uint8_t)(a >> 24);
+        }
+      } else {
+        const uint16_t* p2 = reinterpret_cast<const uint16_t*>(p);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const uint32_t a = __ldg(p2 + k);
+          px[dy][2 * k + 0] = (uint8_t)(a & 0xFF);
+          px[dy][2 * k + 1] = (uint8_t)(a >> 8);
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < PX; ++q) {
+      float v[16];
+#pragma unroll
+      for (int k = 12; k < 16; ++k) v[k] = 0.0f;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const uint8_t* s3 = &px[dy][(q * 2 + dx) * 3];
+          v[(dy * 2 + dx) * 3 + cmap0] = lut[cmap0][s3[0]];
+          v[(dy * 2 + dx) * 3 + 1] = lut[1][s3[1]];
+          v[(dy * 2 + dx) * 3 + cmap2] = lut[cmap2][s3[2]];
+        }
+      uint32_t hq[8], lq[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        __half h0, l0, h1, l1;
+        split_f32(v[2 * k], &h0, &l0);
+        split_f32(v[2 * k + 1], &h1, &l1);
+        hq[k] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        lq[k] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      }
+      __half* o = dst + (((size_t)b * H2 + h2) * Wd + (w2 + q + col_off)) * pitch;
+      reinterpret_cast<uint4*>(o)[0] = make_uint4(hq[0], hq[1], hq[2], hq[3]);
+      reinterpret_cast<uint4*>(o)[1] = make_uint4(hq[4], hq[5], hq[6], hq[7]);
+      reinterpret_cast<uint4*>(o + plane)[0] = make_uint4(lq[0], lq[1], lq[2], lq[3]);
+      reinterpret_cast<uint4*>(o + plane)[1] = make_uint4(lq[4], lq[5], lq[6], lq[7]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ SPPF: three chained 5x5/s1/p2 max pools
 // One CTA per (image, 8-channel slice): the whole HxW map of the slice lives in shared memory as fp32;
 // each pool is a separable row-max / column-max pass.  y2 == 9x9 pool, y3 == 13x13 pool of x.
@@ -829,6 +917,33 @@ extern "C" int cvb_stem_s2d(const float* src, int32_t B, int32_t H, int32_t W, c
   if (grid > 148 * 32) grid = 148 * 32;
   stem_s2d_kernel<<<(int)grid, block, 0, as_stream(stream)>>>(src, B, H, W, static_cast<__half*>(dst->base), dst->c_pitch,
                                                              dst->plane_stride / 2, dst->W, pad_left);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}
+
+extern "C" int cvb_stem_s2d_u8(const uint8_t* src, int32_t B, int32_t H, int32_t W, const float* mean, const float* std, int32_t reverse_channels,
+                               const CvbView* dst, int32_t pad_left, void* stream) {
+  int rc = check_split_view(dst, "stem_s2d_u8");
+  if (rc) return rc;
+  CVB_REQUIRE(src && mean && std && H % 2 == 0 && W % 2 == 0, "stem_s2d_u8: null argument or odd H/W");
+  CVB_REQUIRE(std[0] != 0.0f && std[1] != 0.0f && std[2] != 0.0f, "stem_s2d_u8: zero std");
+  CVB_REQUIRE(dst->B == B && dst->H == H / 2 && dst->W >= W / 2 + pad_left && pad_left >= 0 && dst->C == 16 && dst->c_pitch == 16,
+              "stem_s2d_u8: dst must be [B,H/2,>=W/2+pad_left,16]");
+  CVB_REQUIRE((reinterpret_cast<uintptr_t>(src) & 1) == 0 && (reinterpret_cast<uintptr_t>(dst->base) & 15) == 0 && dst->plane_stride % 16 == 0,
+              "stem_s2d_u8: alignment");
+  const bool pair = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(src) & 3) == 0;
+  const long long n = (long long)B * (H / 2) * (W / 2) / (pair ? 2 : 1);
+  const int block = 256;
+  long long grid = (n + block - 1) / block;
+  if (grid > 148 * 16) grid = 148 * 16;
+  __half* dp = static_cast<__half*>(dst->base);
+  if (pair)
+    stem_s2d_u8_kernel<true><<<(int)grid, block, 0, as_stream(stream)>>>(src, B, H, W, mean[0], mean[1], mean[2], std[0], std[1], std[2],
+                                                                        reverse_channels, dp, dst->c_pitch, dst->plane_stride / 2, dst->W, pad_left);
+  else
+    stem_s2d_u8_kernel<false><<<(int)grid, block, 0, as_stream(stream)>>>(src, B, H, W, mean[0], mean[1], mean[2], std[0], std[1], std[2],
+                                                                         reverse_channels, dp, dst->c_pitch, dst->plane_stride / 2, dst->W, pad_left);
   CVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return CVB_OK;

@@ -88,11 +88,12 @@ class YOLOv5CSPDarknet(_GraphCache):
                 m.eps = 1e-3
                 m.momentum = 0.03
 
-    def emit(self, g, img_nchw_getter, H, W, name='backbone'):
-        """img_nchw_getter() -> contiguous fp32 CUDA tensor [B,3,H,W] at run time.  Returns list of Val."""
+    def emit(self, g, img_nchw_getter, H, W, name='backbone', u8_norm=None):
+        """img_nchw_getter() -> contiguous fp32 CUDA tensor [B,3,H,W] at run time (or uint8 [B,H,W,3] frames when the graph was
+        built with ``u8_norm`` = ToTensor/Normalize constants, see ops.stem_s2d).  Returns list of Val."""
         # space-to-depth input in the zero-padded "row window" layout: one 128-byte K chunk = 4 adjacent s2d pixels
         x0 = g.new_act(H // 2, W // 2 + 3, 16)
-        g.fn(lambda: ops.stem_s2d(img_nchw_getter(), x0.view()))
+        g.fn(lambda: ops.stem_s2d(img_nchw_getter(), x0.view(), norm=u8_norm))
         w, b = folded(self.stem.conv, self.stem.bn)
         x = g.conv(x0, ops.stem_weights_to_s2d(w), b, 3, 1, 1, 'silu', name=name + '.stem', w_window=4)
         outs = []
@@ -326,10 +327,13 @@ class YOLOv5(_GraphCache):
                 m.momentum = 0.03
 
     # ------------------------------------------------------------------ fused graph
-    def build_graph(self, B, H, W, device, want_raw=False):
+    # ToTensor + Normalize of conf/coco_yolov5_s.yml:58-59 (det_transforms.py:85-109), used only by the uint8-frame entry points
+    input_norm = dict(mean=(0.406, 0.456, 0.485), std=(0.225, 0.224, 0.229), reverse_channels=True)
+
+    def build_graph(self, B, H, W, device, want_raw=False, u8_input=False):
         g = GraphBuilder(B, device)
         holder = {}
-        feats = self.backbone.emit(g, lambda: holder['x'], H, W)
+        feats = self.backbone.emit(g, lambda: holder['x'], H, W, u8_norm=dict(self.input_norm) if u8_input else None)
         feats = self.neck.emit(g, feats)
         conf, iou = self.conf_thres, self.iou_thres
         ws = ops.NmsWorkspace(B, self.detect.num_candidates(feats), self.num_classes, max_det=self.max_det, device=device)
@@ -338,11 +342,25 @@ class YOLOv5(_GraphCache):
         return dict(g=g, holder=holder, z=z, raws=raws, ws=ws)
 
     def _graph_for(self, imgs, want_raw=False):
-        B, _, H, W = imgs.shape
-        key = (B, H, W, imgs.device.index, want_raw)
+        u8 = imgs.dtype == torch.uint8
+        B, H, W = (imgs.shape[0], imgs.shape[1], imgs.shape[2]) if u8 else (imgs.shape[0], imgs.shape[2], imgs.shape[3])
+        key = (B, H, W, imgs.device.index, want_raw, u8)
         if key not in self._graphs:
-            self._graphs[key] = self.build_graph(B, H, W, imgs.device, want_raw)
+            self._graphs[key] = self.build_graph(B, H, W, imgs.device, want_raw, u8_input=u8)
         return self._graphs[key]
+
+    def predict_frames(self, frames_u8):
+        """Device-only inference on camera frames: uint8 CUDA tensor [B,H,W,3] (BGR, already letterboxed to the network size).
+        The reference's ToTensor + Normalize run inside the stem loader (``input_norm``); results equal ``predict`` on the
+        tensor those transforms would have produced."""
+        if self.training:
+            raise RuntimeError('inference only: call .eval() first')
+        if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[3] != 3 or not frames_u8.is_cuda:
+            raise ValueError('predict_frames expects a uint8 CUDA tensor [B,H,W,3]')
+        G = self._graph_for(frames_u8)
+        G['holder']['x'] = frames_u8.contiguous()
+        G['g'].run()
+        return G['ws'].det, G['ws'].det_idx, G['ws'].det_count
 
     def predict(self, imgs):
         """Device-only inference: returns (det [B,300,6], det_idx [B,300], det_count [B]) device tensors, no host sync."""

@@ -194,10 +194,23 @@ def f32nhwc_to_nchw(src_view, out=None):
     return out
 
 
-def stem_s2d(x, dst_view, pad_left=None):
-    """pad_left=None: 0 for a plain [B,H/2,W/2,16] target, 1 for the padded row-window layout (W/2+3 columns)."""
+def stem_s2d(x, dst_view, pad_left=None, norm=None):
+    """x: fp32 NCHW [B,3,H,W] (the reference's model input), or uint8 NHWC [B,H,W,3] camera frames with
+    ``norm = dict(mean=(..3), std=(..3), reverse_channels=bool)`` = the reference's ToTensor + Normalize fused into the loader.
+    pad_left=None: 0 for a plain [B,H/2,W/2,16] target, 1 for the padded row-window layout (W/2+3 columns)."""
     _require_cuda(x, 'stem_s2d')
-    assert x.dtype == torch.float32 and x.is_contiguous()
+    assert x.is_contiguous()
+    if x.dtype == torch.uint8:
+        B, H, W, C = x.shape
+        assert C == 3 and norm is not None, 'uint8 frames need [B,H,W,3] and normalisation constants'
+        if pad_left is None:
+            pad_left = 0 if dst_view.W == W // 2 else 1
+        mean = (ctypes.c_float * 3)(*[float(v) for v in norm['mean']])
+        std = (ctypes.c_float * 3)(*[float(v) for v in norm['std']])
+        _lib.check(_lib.lib().cvb_stem_s2d_u8(x.data_ptr(), B, H, W, mean, std, 1 if norm.get('reverse_channels', True) else 0,
+                                              byref(dst_view), pad_left, _stream()), 'cvb_stem_s2d_u8')
+        return
+    assert x.dtype == torch.float32
     B, C, H, W = x.shape
     assert C == 3
     if pad_left is None:

@@ -10,15 +10,21 @@ from . import dist as cdist
 
 
 class InferencePipeline:
-    def __init__(self, model, batch, height, width, device, depth=2, gather_group=None, use_cuda_graph=True):
+    def __init__(self, model, batch, height, width, device, depth=2, gather_group=None, use_cuda_graph=True, uint8_frames=False):
+        """uint8_frames=False: submit() takes the reference's model input, pinned fp32 [B,3,H,W] (already normalised).
+        uint8_frames=True: submit() takes pinned uint8 [B,H,W,3] camera frames; ToTensor + Normalize run in the stem loader and the
+        host->device copy is 4x smaller."""
         self.model = model
         self.device = device
         self.depth = depth
         self.group = gather_group
-        self.G = model.build_graph(batch, height, width, device)
+        self.G = model.build_graph(batch, height, width, device, u8_input=True) if uint8_frames else model.build_graph(batch, height, width, device)
         self.g = self.G['g']
         self.ws = self.G['ws']
-        self.x_dev = [torch.empty((batch, 3, height, width), dtype=torch.float32, device=device) for _ in range(depth)]
+        if uint8_frames:
+            self.x_dev = [torch.empty((batch, height, width, 3), dtype=torch.uint8, device=device) for _ in range(depth)]
+        else:
+            self.x_dev = [torch.empty((batch, 3, height, width), dtype=torch.float32, device=device) for _ in range(depth)]
         self.copy_stream = torch.cuda.Stream(device)
         self.out_stream = torch.cuda.Stream(device)
         self.compute_stream = torch.cuda.Stream(device)
@@ -34,7 +40,7 @@ class InferencePipeline:
         self.res_host = [torch.empty((world * batch, M * 7 + 1), dtype=torch.float32).pin_memory() for _ in range(depth)]
         self.graphs = [None] * depth
         self.n_submitted = 0
-        self.h2d_bytes = self.x_dev[0].numel() * 4
+        self.h2d_bytes = self.x_dev[0].numel() * self.x_dev[0].element_size()
         self.d2h_bytes = self.res_host[0].numel() * 4
         if use_cuda_graph:
             with torch.cuda.stream(self.compute_stream):

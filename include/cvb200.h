@@ -115,6 +115,17 @@ int cvb_f32nhwc_to_nchw(const CvbView* src, float* dst, void* stream);
 int cvb_stem_s2d(const float* src, int32_t B, int32_t H, int32_t W, const CvbView* dst, int32_t pad_left, void* stream);
 
 /*
+ * Same output from the camera-side format: uint8 HWC frames [B,H,W,3].  Fuses the reference's input
+ * transforms into the stem loader: ToTensor (src/data/transforms/det_transforms.py:85-99: HWC->CHW, channel reversal BGR->RGB when
+ * reverse_channels != 0, float32 / 255) and Normalize (:102-109 = torchvision F.normalize, (x - mean[c]) / std[c] in fp32, mean/std
+ * indexed by the OUTPUT channel; conf/coco_yolov5_s.yml:59 mean [0.406,0.456,0.485] std [0.225,0.224,0.229]).  Same operation order
+ * and IEEE division as the reference, so dst is bit-identical to cvb_stem_s2d on the tensor those transforms would have produced;
+ * the fp32 NCHW image never exists and the host->device copy shrinks 4x.  mean/std: host pointers to 3 floats.
+ */
+int cvb_stem_s2d_u8(const uint8_t* src, int32_t B, int32_t H, int32_t W, const float* mean, const float* std, int32_t reverse_channels,
+                    const CvbView* dst, int32_t pad_left, void* stream);
+
+/*
  * ResNet stem max pool 3x3 / stride 2 / pad 1 on a split16 tensor.
  * replaces: nn.MaxPool2d(3, 2, 1) of torchvision.models.resnet (src/models/backbones/seg/resnet.py:80-83).
  */

@@ -119,6 +119,19 @@ def forward(x, sd):
     with torch.no_grad():
         return detect(neck(backbone(x, sd), sd), sd)
 
+def input_transform(frames_u8_hwc, mean, std, reverse_channels=True):
+    """ToTensor + Normalize of the reference (src/data/transforms/det_transforms.py:85-99 and :102-109): HWC -> CHW, channel
+    reversal (BGR -> RGB), float32 / 255, then torchvision F.normalize = (x - mean[c]) / std[c] in fp32.
+    frames: uint8 [B,H,W,3] (numpy or torch) -> float32 torch tensor [B,3,H,W].  Pinned by tests/golden/input_transform.npz."""
+    f = torch.as_tensor(frames_u8_hwc)
+    x = f.permute(0, 3, 1, 2)
+    if reverse_channels:
+        x = x.flip(1)
+    x = x.contiguous().to(torch.float32).div_(255.0)
+    m = torch.as_tensor(mean, dtype=torch.float32).view(1, 3, 1, 1)
+    sd = torch.as_tensor(std, dtype=torch.float32).view(1, 3, 1, 1)
+    return x.sub_(m).div_(sd)
+
 
 def rel_err(a, b):
     """Parity metric of SURVEY.md §8(d): max|a-b| / (max|b| + 1e-12)."""

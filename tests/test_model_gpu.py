@@ -152,3 +152,42 @@ def test_inference_pipeline_matches_predict(model):
         dd, ii, cc = model.predict(xh.cuda())
         torch.cuda.synchronize()
         assert torch.equal(cc.cpu(), c) and torch.equal(dd.cpu(), d) and torch.equal(ii.cpu(), ix)
+
+
+def test_uint8_frames_stem_bit_identical_and_model_equal(cuda):
+    """uint8 HWC frames with ToTensor + Normalize fused into the stem loader.  The space-to-depth tensor must
+    be bit-identical to the fp32 path fed with the reference's transformed tensor (golden fixture from the reference's own
+    classes), and model-level detections must be identical."""
+    import os
+    import numpy as np
+    from cvpytorch_b200 import ops, synth
+    from oracle import yolov5_oracle as YO
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'input_transform.npz'))
+    frames = torch.from_numpy(g['frames']).cuda()
+    ref = torch.from_numpy(g['tensor']).cuda()
+    norm = dict(mean=g['mean'].tolist(), std=g['std'].tolist(), reverse_channels=True)
+    B, H, W = frames.shape[0], frames.shape[1], frames.shape[2]
+    for padded in (False, True):
+        Wd = W // 2 + (3 if padded else 0)
+        a, b = ops.SplitTensor(B, H // 2, Wd, 16), ops.SplitTensor(B, H // 2, Wd, 16)
+        ops.stem_s2d(ref, a.view())
+        ops.stem_s2d(frames, b.view(), norm=norm)
+        torch.cuda.synchronize()
+        assert torch.equal(a.data, b.data)
+    # W % 4 != 0 takes the one-pixel-per-thread kernel; reference tensor from the (fixture-pinned) oracle restatement
+    fr46 = g['frames'][:, :, :46].copy()
+    x46 = YO.input_transform(fr46, norm['mean'], norm['std'], True).cuda()
+    a, b = ops.SplitTensor(B, H // 2, 23, 16), ops.SplitTensor(B, H // 2, 23, 16)
+    ops.stem_s2d(x46, a.view())
+    ops.stem_s2d(torch.from_numpy(fr46).cuda(), b.view(), norm=norm)
+    torch.cuda.synchronize()
+    assert torch.equal(a.data, b.data)
+    # model level: random frames at 128x128
+    m = synth.build_yolov5s(True)
+    rng = np.random.default_rng(5)
+    fr = torch.from_numpy(rng.integers(0, 256, size=(2, 128, 128, 3), dtype=np.uint8))
+    x = YO.input_transform(fr, m.input_norm['mean'], m.input_norm['std'], True)
+    d0, i0, c0 = [t.clone() for t in m.predict(x.cuda())]
+    d1, i1, c1 = m.predict_frames(fr.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(c0, c1) and torch.equal(i0, i1) and torch.equal(d0, d1)
