@@ -191,3 +191,56 @@ def test_uint8_frames_stem_bit_identical_and_model_equal(cuda):
     d1, i1, c1 = m.predict_frames(fr.cuda())
     torch.cuda.synchronize()
     assert torch.equal(c0, c1) and torch.equal(i0, i1) and torch.equal(d0, d1)
+
+
+def test_full_size_bs64_properties(model):
+    """BASELINE.json configs[1] at full size (64 x 3 x 640 x 640), through properties that need no oracle run:
+    (1) determinism: two passes are bit-identical; (2) images are independent: image i of the batch equals the same image run
+    alone (different tile boxes, same arithmetic); (3) NMS invariants on every image: scores non-increasing, counts <= 300,
+    kept boxes of one class have IoU <= thr (torchvision's float IoU compared in double), kept ids unique and consistent
+    with the decoded tensor; (4) batch permutation permutes the outputs."""
+    torch.manual_seed(1029)
+    x = torch.randn(64, 3, 640, 640).cuda()
+    det, idx, cnt = [t.clone() for t in model.predict(x)]
+    z = model._graph_for(x)['z']
+    det2, idx2, cnt2 = model.predict(x)
+    torch.cuda.synchronize()
+    assert torch.equal(det, det2) and torch.equal(idx, idx2) and torch.equal(cnt, cnt2)
+    # (3) invariants, checked on the host for all 64 images
+    d, ix, c = det.cpu().double(), idx.cpu().long(), cnt.cpu().long()
+    zc = z.cpu()
+    nc = zc.shape[2] - 5
+    for b in range(64):
+        k = int(c[b])
+        assert 0 < k <= 300
+        s = d[b, :k, 4]
+        assert bool((s[:-1] >= s[1:]).all())
+        ids = ix[b, :k]
+        assert ids.unique().numel() == k
+        anchor, cls = ids // nc, ids % nc
+        assert torch.equal(cls.double(), d[b, :k, 5])
+        # score and box recomputed from the decoded tensor exactly as yolov5.py:106,52-59 does
+        row = zc[b, anchor]
+        assert torch.equal((row[:, 5:].gather(1, cls[:, None])[:, 0] * row[:, 4]).double(), s)
+        box = torch.stack([row[:, 0] - row[:, 2] / 2, row[:, 1] - row[:, 3] / 2, row[:, 0] + row[:, 2] / 2, row[:, 1] + row[:, 3] / 2], 1)
+        assert torch.equal(box.double(), d[b, :k, :4])
+        if b % 16 == 0:  # pairwise IoU of same-class kept boxes (float32 arithmetic like torchvision, compared in double)
+            bo = box + (cls.float() * 4096.0)[:, None]
+            area = (bo[:, 2] - bo[:, 0]) * (bo[:, 3] - bo[:, 1])
+            lt = torch.max(bo[:, None, :2], bo[None, :, :2])
+            rb = torch.min(bo[:, None, 2:], bo[None, :, 2:])
+            wh = (rb - lt).clamp(min=0)
+            inter = wh[..., 0] * wh[..., 1]
+            iou = inter / (area[:, None] + area[None, :] - inter)
+            iou = torch.nan_to_num(iou, nan=0.0)  # 0/0 for degenerate boxes: NaN > thr is false in torchvision, nothing is suppressed
+            iou.fill_diagonal_(0)
+            assert float(iou.double().max()) <= 0.6
+    # (2) independence + (4) permutation
+    for b in (0, 37, 63):
+        d1, i1, c1 = model.predict(x[b:b + 1].contiguous())
+        torch.cuda.synchronize()
+        assert int(c1[0]) == int(cnt[b]) and torch.equal(i1[0], idx[b]) and torch.equal(d1[0], det[b])
+    perm = torch.randperm(64, generator=torch.Generator().manual_seed(1))
+    dp, ip, cp = model.predict(x[perm.cuda()].contiguous())
+    torch.cuda.synchronize()
+    assert torch.equal(cp.cpu(), cnt.cpu()[perm]) and torch.equal(ip.cpu(), idx.cpu()[perm]) and torch.equal(dp.cpu(), det.cpu()[perm])
