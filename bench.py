@@ -172,6 +172,11 @@ def run_b200_arm(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     B = args.batch
+    if args.scaling == 'strong':
+        # fixed global batch (args.batch images in total), contiguous shards per rank (global B=64 -> 8 img/GPU at W=8)
+        if args.batch % world != 0:
+            raise SystemExit('--scaling strong needs --batch divisible by the number of GPUs')
+        B = args.batch // world
     model = synth.build_yolov5s(calibrated=True)
     K, W = args.steps, max(3, args.warmup)
 
@@ -344,7 +349,7 @@ def run_b200_arm(args):
                             'launches of one step (ncu, profiles/r01); per-layer numbers in profiles/'}
         cpu_v, cores, spt, sample = cpu_reference_throughput(args.cpu_steps, 1) if args.cpu_steps > 0 else (None, 0, 0, 'skipped')
         line = {'metric': METRIC, 'value': round(value, 2), 'unit': 'images/sec', 'n_gpus': world, 'steps': K, 'warmup': W,
-                'ms_per_step': round(ms_per_step, 4), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'ms_per_step': round(ms_per_step, 4), 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
                 'dtype': 'fp16x3-split (fp32-equivalent, fp32 accumulate)', 'data': 'synthetic',
                 'config': {'workload': 'YOLOv5-s 640x640 forward+decode+NMS, bs64 per GPU (conf/coco_yolov5_s.yml; BASELINE.json configs[1])',
                            'global_batch': world * B, 'per_gpu_batch': B, 'parallelism': f'dp{world}', 'conf_thres': 0.001, 'iou_thres': 0.6,
@@ -375,6 +380,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=64, help='images per GPU per step (BASELINE: 64)')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'], help='weak: --batch images per GPU (default); strong: --batch images in total')
     ap.add_argument('--graph', type=int, default=0, help='1: replay the step as a CUDA graph (no per-conv-segment events)')
     ap.add_argument('--cpu-steps', type=int, default=3, help='bs8 CPU baseline steps timed on rank 0 (0 = skip)')
     args = ap.parse_args()

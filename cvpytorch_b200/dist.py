@@ -43,3 +43,31 @@ def all_gather_detections(det, det_idx, det_count, group=None, out=None):
         out = torch.empty((world * packed.shape[0], packed.shape[1]), dtype=packed.dtype, device=packed.device)
     dist.all_gather_into_tensor(out, packed, group=group)
     return unpack_detections(out, det.shape[1])
+
+
+def all_gather_fcos_detections(scores, classes, boxes, counts, group=None):
+    """FCOS (BASELINE.json config 5, "NCCL box all-gather"): padded per-image results of FCOS.predict --
+    scores [B,K] f32, classes [B,K] i32/i64, boxes [B,K,4] f32, counts [B] i32 -- packed into ONE f32 tensor [B, K*6+1]
+    (ints bit-cast) and gathered with a single all_gather_into_tensor; returns the global (rank-major) tensors."""
+    B, K = scores.shape
+    packed = torch.cat([scores.reshape(B, K), classes.to(torch.int32).view(torch.float32).reshape(B, K), boxes.reshape(B, K * 4),
+                        counts.to(torch.int32).view(torch.float32).reshape(B, 1)], 1).contiguous()
+    world = dist.get_world_size(group)
+    out = torch.empty((world * B, packed.shape[1]), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(out, packed, group=group)
+    G = out.shape[0]
+    return (out[:, :K].contiguous(), out[:, K:2 * K].contiguous().view(torch.int32), out[:, 2 * K:6 * K].reshape(G, K, 4).contiguous(),
+            out[:, 6 * K:].contiguous().view(torch.int32).reshape(G))
+
+
+def all_gather_label_maps(labels, group=None):
+    """Segmentation (BASELINE.json config 3): int64 label maps [B,H,W] (EncoderDecoder 'val' output) travel as uint8
+    (class ids < 256; 2 MB per 1024x2048 image instead of 16 MB) in one all_gather_into_tensor and are widened to int64 again
+    for API parity with encoder_decoder.py:133."""
+    if int(labels.numel()) and (int(labels.max()) > 255 or int(labels.min()) < 0):
+        raise ValueError('label ids must fit uint8 for the packed gather')
+    u8 = labels.to(torch.uint8).contiguous()
+    world = dist.get_world_size(group)
+    out = torch.empty((world * u8.shape[0],) + tuple(u8.shape[1:]), dtype=torch.uint8, device=u8.device)
+    dist.all_gather_into_tensor(out, u8, group=group)
+    return out.to(torch.int64)

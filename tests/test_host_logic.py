@@ -143,3 +143,39 @@ def test_all_gather_detections_gloo_world2():
         assert d.shape == (6, 7, 6) and i.shape == (6, 7) and c.tolist() == [1, 0, 7, 2, 0, 7]
         assert float(d[0, 0, 0]) == 0.0 and float(d[3, 0, 0]) == 1.0 and float(d[5, 0, 0]) == 3.0
         assert int(i[3, 0]) == 1000 and int(i[0, 6]) == 6
+
+
+def _gloo_worker_fcos_seg(rank, world, port, q):
+    import torch.distributed as dist
+    from cvpytorch_b200.dist import all_gather_fcos_detections, all_gather_label_maps
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    B, K = 2, 5
+    scores = torch.arange(B * K, dtype=torch.float32).view(B, K) + 100 * rank
+    classes = torch.arange(B * K, dtype=torch.int64).view(B, K) % 80 + 1
+    boxes = torch.arange(B * K * 4, dtype=torch.float32).view(B, K, 4) + 0.5 * rank
+    counts = torch.tensor([K, rank], dtype=torch.int32)
+    s, c, bx, n = all_gather_fcos_detections(scores, classes, boxes, counts)
+    lab = (torch.arange(B * 4 * 6).view(B, 4, 6) % 19 + rank).to(torch.int64)
+    g = all_gather_label_maps(lab)
+    q.put((rank, s.clone(), c.clone(), bx.clone(), n.clone(), g.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_all_gather_fcos_and_label_maps_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 30500 + os.getpid() % 1000
+    procs = [ctx.Process(target=_gloo_worker_fcos_seg, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, s, c, bx, n, g in res:
+        assert s.shape == (4, 5) and c.dtype == torch.int32 and bx.shape == (4, 5, 4) and n.tolist() == [5, 0, 5, 1]
+        assert float(s[0, 0]) == 0.0 and float(s[2, 0]) == 100.0 and float(bx[2, 0, 0]) == 0.5 and int(c[3, 4]) == 10
+        assert g.dtype == torch.int64 and g.shape == (4, 4, 6) and int(g[0, 0, 1]) == 1 and int(g[2, 0, 1]) == 2
