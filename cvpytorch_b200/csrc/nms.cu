@@ -17,6 +17,7 @@
 // -> per-image greedy scan (warp-ballot compaction, 512x512 bit mask in shared memory, single-warp resolve).
 #include <cooperative_groups.h>
 #include <cuda_fp16.h>
+#include <math_constants.h>
 
 #include "internal.h"
 
@@ -748,6 +749,290 @@ extern "C" int cvb_yolo_nms(const float* prediction, const CvbNmsParams* p, floa
   return CVB_OK;
 }
 
+
+// =====================================================================================================================
+// YOLOX post-processing (src/models/yolox.py:18-68; torchvision.ops.batched_nms at :64 is third-party, un-vendored)
+// =====================================================================================================================
+namespace cvb {
+
+__device__ __forceinline__ float sigmoid_x(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+
+// One warp per head location.  Record = (x1, y1, x2, y2, obj, class_conf, class_pred, obj * class_conf):
+//   xy = (p + grid) * stride, wh = exp(p) * stride (:33-35), sigmoid on obj / classes (:37-39), corners = c -/+ wh / 2 (:46-51),
+//   class_conf, class_pred = max over the class sigmoids, first maximum wins (:57).
+__global__ void __launch_bounds__(256) yolox_decode_kernel(const float* __restrict__ ro, int ro_pitch, const float* __restrict__ cls, int cls_pitch,
+                                                           int B, int H, int W, int nc, float stride, float* __restrict__ cand, long long A,
+                                                           long long off) {
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const long long npix = (long long)B * H * W;
+  if (warp >= npix) return;
+  const int hw = H * W;
+  const int b = (int)(warp / hw);
+  const int p = (int)(warp - (long long)b * hw);
+  const int py = p / W, px = p - py * W;
+  const float* c = cls + (size_t)warp * cls_pitch;
+  float best = -1.0f;
+  int bi = 0x7fffffff;
+  for (int k = lane; k < nc; k += 32) {
+    const float sc = sigmoid_x(__ldg(c + k));
+    if (sc > best) {
+      best = sc;
+      bi = k;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ob > best || (ob == best && oi < bi)) {
+      best = ob;
+      bi = oi;
+    }
+  }
+  if (lane == 0) {
+    const float* r = ro + (size_t)warp * ro_pitch;
+    const float cx = __fmul_rn(__fadd_rn(__ldg(r), (float)px), stride);
+    const float cy = __fmul_rn(__fadd_rn(__ldg(r + 1), (float)py), stride);
+    const float w = __fmul_rn(expf(__ldg(r + 2)), stride);
+    const float h = __fmul_rn(expf(__ldg(r + 3)), stride);
+    const float obj = sigmoid_x(__ldg(r + 4));
+    const float hw2 = __fdiv_rn(w, 2.0f), hh2 = __fdiv_rn(h, 2.0f);
+    float4* o = reinterpret_cast<float4*>(cand + ((size_t)b * A + off + p) * 8);
+    o[0] = make_float4(__fsub_rn(cx, hw2), __fsub_rn(cy, hh2), __fadd_rn(cx, hw2), __fadd_rn(cy, hh2));
+    o[1] = make_float4(obj, best, (float)bi, __fmul_rn(obj, best));
+  }
+}
+
+constexpr int kXThreads = 1024;
+constexpr int kXKeys = 16384;   // candidate capacity per image (head locations; 8972 at 640x640)
+constexpr int kXChunk = 512;
+
+struct YoloxSmem {
+  uint64_t keys[kXKeys];
+  float4 cbox[kXChunk];    // boxes as seen by NMS (class offset added in coordinate-trick mode)
+  float carea[kXChunk];
+  int ccls[kXChunk];
+  uint32_t cidx[kXChunk];
+  uint32_t mask[kXChunk][kXChunk / 32];
+  uint32_t keeplist[kXChunk];
+  uint32_t warp_cnt[kXThreads / 32];
+  float red[kXThreads / 32];
+  uint32_t n, m_alive, new_kept;
+  float unit;
+};
+
+// One CTA per image: score filter (obj * class_conf >= conf_thre, :58), stable descending order (score, then lower index),
+// torchvision.ops.batched_nms: more than `vanilla_above` boxes -> per-class NMS on the raw boxes (_batched_nms_vanilla),
+// else one NMS on boxes + class * (max_coordinate + 1) (_batched_nms_coordinate_trick); IoU in fp32, compared in double,
+// areas without +1.  Rows (x1, y1, x2, y2, obj, class_conf, class_pred) are written in kept (score) order.
+__global__ void __launch_bounds__(kXThreads) yolox_nms_kernel(const float* __restrict__ cand, int A, float conf, double iou_thr,
+                                                              int vanilla_above, float* __restrict__ det, int* __restrict__ count,
+                                                              float4* __restrict__ kbox_g, float* __restrict__ karea_g, int* __restrict__ kcls_g) {
+  extern __shared__ uint8_t xs_raw[];
+  YoloxSmem& S = *reinterpret_cast<YoloxSmem*>(xs_raw);
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* cb = cand + (size_t)b * A * 8;
+  float4* kbox = kbox_g + (size_t)b * A;
+  float* karea = karea_g + (size_t)b * A;
+  int* kcls = kcls_g + (size_t)b * A;
+  float* dout = det + (size_t)b * A * 7;
+  if (tid == 0) S.n = 0;
+  __syncthreads();
+  float cmax = -CUDART_INF_F;
+  for (int i = tid; i < A; i += kXThreads) {
+    const float4 hi = __ldg(reinterpret_cast<const float4*>(cb + (size_t)i * 8 + 4));
+    if (hi.w >= conf) {
+      const float4 bx = __ldg(reinterpret_cast<const float4*>(cb + (size_t)i * 8));
+      cmax = fmaxf(cmax, fmaxf(fmaxf(bx.x, bx.y), fmaxf(bx.z, bx.w)));
+      S.keys[atomicAdd(&S.n, 1u)] = ((uint64_t)__float_as_uint(hi.w) << 32) | (uint64_t)(0xFFFFFFFFu - (uint32_t)i);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+  if (lane == 0) S.red[warp] = cmax;
+  __syncthreads();
+  const int n = (int)S.n;
+  if (tid == 0) {
+    float m = -CUDART_INF_F;
+    for (int w = 0; w < kXThreads / 32; ++w) m = fmaxf(m, S.red[w]);
+    S.unit = __fadd_rn(m, 1.0f);  // max_coordinate + 1 (torchvision/ops/boxes.py _batched_nms_coordinate_trick)
+  }
+  if (n == 0) {
+    if (tid == 0) count[b] = 0;
+    return;
+  }
+  int npad = 1;
+  while (npad < n) npad <<= 1;
+  for (int i = n + tid; i < npad; i += kXThreads) S.keys[i] = 0ull;
+  for (int k = 2; k <= npad; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      __syncthreads();
+      for (int t = tid; t < npad / 2; t += kXThreads) {
+        const int i = 2 * j * (t / j) + (t % j);
+        const uint64_t x = S.keys[i], y = S.keys[i + j];
+        const bool desc = (i & k) == 0;
+        if (desc ? (x < y) : (x > y)) {
+          S.keys[i] = y;
+          S.keys[i + j] = x;
+        }
+      }
+    }
+  __syncthreads();
+  const bool vanilla = n > vanilla_above;
+  const float unit = S.unit;
+  int kept_n = 0;
+  for (int base = 0; base < n; base += kXChunk) {
+    const int i = base + tid;
+    bool alive = tid < kXChunk && i < n;
+    float4 box = make_float4(0, 0, 0, 0);
+    float area = 0.0f;
+    int cls = 0;
+    uint32_t idx = 0;
+    if (alive) {
+      idx = 0xFFFFFFFFu - (uint32_t)(S.keys[i] & 0xFFFFFFFFull);
+      const float4 bx = __ldg(reinterpret_cast<const float4*>(cb + (size_t)idx * 8));
+      const float4 hi = __ldg(reinterpret_cast<const float4*>(cb + (size_t)idx * 8 + 4));
+      cls = (int)hi.z;
+      if (vanilla) {
+        box = bx;
+      } else {
+        const float offv = __fmul_rn((float)cls, unit);
+        box = make_float4(__fadd_rn(bx.x, offv), __fadd_rn(bx.y, offv), __fadd_rn(bx.z, offv), __fadd_rn(bx.w, offv));
+      }
+      area = __fmul_rn(__fsub_rn(box.z, box.x), __fsub_rn(box.w, box.y));
+      for (int k = 0; k < kept_n; ++k) {
+        if (vanilla && kcls[k] != cls) continue;
+        if (iou_gt(kbox[k], karea[k], box, area, iou_thr)) {
+          alive = false;
+          break;
+        }
+      }
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, alive);
+    if (lane == 0) S.warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t v = S.warp_cnt[lane];
+      uint32_t inc = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+      }
+      S.warp_cnt[lane] = inc - v;
+      if (lane == 31) S.m_alive = inc;
+    }
+    __syncthreads();
+    const int m = (int)S.m_alive;
+    if (alive) {
+      const int pos = (int)S.warp_cnt[warp] + __popc(bal & ((1u << lane) - 1));
+      S.cbox[pos] = box;
+      S.carea[pos] = area;
+      S.ccls[pos] = cls;
+      S.cidx[pos] = idx;
+    }
+    __syncthreads();
+    const int words = (m + 31) >> 5;
+    if (tid < m) {
+      const float4 me = S.cbox[tid];
+      const float ma = S.carea[tid];
+      const int mc = S.ccls[tid];
+      for (int wd = 0; wd < words; ++wd) {
+        uint32_t bits = 0;
+        const int c0 = wd << 5;
+        const int c1 = min(m, c0 + 32);
+        for (int c = max(c0, tid + 1); c < c1; ++c)
+          if ((!vanilla || S.ccls[c] == mc) && iou_gt(me, ma, S.cbox[c], S.carea[c], iou_thr)) bits |= 1u << (c & 31);
+        S.mask[tid][wd] = bits;
+      }
+    }
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t removed = 0;
+      int nk = 0;
+      for (int r = 0; r < m; ++r) {
+        const uint32_t rw = __shfl_sync(0xffffffffu, removed, r >> 5);
+        if (!((rw >> (r & 31)) & 1u)) {
+          if (lane == 0) S.keeplist[nk] = (uint32_t)r;
+          ++nk;
+          if (lane < words) removed |= S.mask[r][lane];
+        }
+      }
+      if (lane == 0) S.new_kept = (uint32_t)nk;
+    }
+    __syncthreads();
+    const int nk = (int)S.new_kept;
+    for (int t = tid; t < nk; t += kXThreads) {
+      const int r = (int)S.keeplist[t];
+      const int o = kept_n + t;
+      kbox[o] = S.cbox[r];
+      karea[o] = S.carea[r];
+      kcls[o] = S.ccls[r];
+      const float* src = cb + (size_t)S.cidx[r] * 8;
+      float* d = dout + (size_t)o * 7;
+#pragma unroll
+      for (int q = 0; q < 7; ++q) d[q] = __ldg(src + q);
+    }
+    kept_n += nk;
+    __threadfence_block();
+    __syncthreads();
+  }
+  if (tid == 0) count[b] = kept_n;
+}
+
+}  // namespace cvb
+
+extern "C" size_t cvb_yolox_workspace_bytes(int32_t B, int32_t A) {
+  if (B <= 0 || A <= 0) return 0;
+  return (size_t)B * A * (sizeof(float4) + sizeof(float) + sizeof(int));
+}
+
+extern "C" int cvb_yolox_decode(const CvbView* reg_obj, const CvbView* cls, int32_t nc, float stride, float* cand, int64_t A, int64_t off,
+                                void* stream) {
+  using namespace cvb;
+  CVB_REQUIRE(reg_obj && cls && reg_obj->base && cls->base && cand, "yolox_decode: null argument");
+  CVB_REQUIRE(reg_obj->plane_stride == 0 && cls->plane_stride == 0, "yolox_decode: inputs must be fp32 NHWC views");
+  CVB_REQUIRE(reg_obj->B == cls->B && reg_obj->H == cls->H && reg_obj->W == cls->W && reg_obj->C >= 5 && cls->C >= nc && nc > 0,
+              "yolox_decode: shape mismatch");
+  CVB_REQUIRE(off >= 0 && off + (int64_t)cls->H * cls->W <= A && (reinterpret_cast<uintptr_t>(cand) & 15) == 0, "yolox_decode: bad output range");
+  const long long npix = (long long)cls->B * cls->H * cls->W;
+  const long long blocks = (npix * 32 + 255) / 256;
+  yolox_decode_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(static_cast<const float*>(reg_obj->base), reg_obj->c_pitch,
+                                                                        static_cast<const float*>(cls->base), cls->c_pitch, cls->B, cls->H, cls->W, nc,
+                                                                        stride, cand, A, off);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}
+
+extern "C" int cvb_yolox_nms(const float* cand, int32_t B, int32_t A, float conf_thres, double iou_thres, int32_t vanilla_above, float* det,
+                             int32_t* det_count, void* workspace, size_t workspace_bytes, void* stream) {
+  using namespace cvb;
+  CVB_REQUIRE(cand && det && det_count && workspace && B > 0 && A > 0, "yolox_nms: null argument / bad shape");
+  CVB_REQUIRE(A <= kXKeys, "yolox_nms: at most %d locations per image (got %d)", kXKeys, A);
+  CVB_REQUIRE(workspace_bytes >= cvb_yolox_workspace_bytes(B, A) && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "yolox_nms: workspace");
+  CVB_REQUIRE((reinterpret_cast<uintptr_t>(cand) & 15) == 0, "yolox_nms: candidate records must be 16-byte aligned");
+  static bool attr_set = false;
+  if (!attr_set) {
+    CVB_CHECK_CUDA(cudaFuncSetAttribute(yolox_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(YoloxSmem)));
+    attr_set = true;
+  }
+  float4* kbox = static_cast<float4*>(workspace);
+  float* karea = reinterpret_cast<float*>(kbox + (size_t)B * A);
+  int* kcls = reinterpret_cast<int*>(karea + (size_t)B * A);
+  yolox_nms_kernel<<<B, kXThreads, sizeof(YoloxSmem), as_stream(stream)>>>(cand, A, conf_thres, iou_thres, vanilla_above, det, det_count, kbox, karea,
+                                                                          kcls);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}
 
 // =====================================================================================================================
 // FCOS post-processing (src/models/detects/fcos_detect.py:42-153)

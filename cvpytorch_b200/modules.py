@@ -198,12 +198,17 @@ class SPPF(_EmitModule):
     def __init__(self, in_channels, out_channels, kernel_sizes=(5, 9, 13), conv_cfg=None, norm_cfg=dict(type='BN', requires_grad=True),
                  act_cfg=dict(type='Swish'), init_cfg=None):
         super().__init__()
-        if not isinstance(kernel_sizes, int) or kernel_sizes != 5:
-            raise NotImplementedError('only the chained 5x5 SPPF (kernel_sizes=5) is on the B200 hot path')
+        # int 5: three chained 5x5 pools; (5, 9, 13): three parallel pools of the same input -- identical values (a chain of two /
+        # three 5x5 max pools IS the 9x9 / 13x13 max pool), so both run the same fused kernel
+        if not ((isinstance(kernel_sizes, int) and kernel_sizes == 5) or tuple(kernel_sizes) == (5, 9, 13)):
+            raise NotImplementedError('only SPPF with kernel_sizes=5 (chained) or (5, 9, 13) (parallel) is on the B200 hot path')
         self.kernel_sizes = kernel_sizes
         hidden = in_channels // 2
         self.conv1 = ConvModule(in_channels, hidden, 1, stride=1, conv_cfg=conv_cfg, norm_cfg=norm_cfg, act_cfg=act_cfg)
-        self.m = nn.MaxPool2d(kernel_size=kernel_sizes, stride=1, padding=kernel_sizes // 2)  # parameter-free; kept for repr parity
+        if isinstance(kernel_sizes, int):
+            self.m = nn.MaxPool2d(kernel_size=kernel_sizes, stride=1, padding=kernel_sizes // 2)  # parameter-free; kept for repr parity
+        else:
+            self.m = nn.ModuleList([nn.MaxPool2d(kernel_size=ks, stride=1, padding=ks // 2) for ks in kernel_sizes])
         self.conv2 = ConvModule(hidden * 4, out_channels, 1, stride=1, conv_cfg=conv_cfg, norm_cfg=norm_cfg, act_cfg=act_cfg)
 
     def emit(self, g, x, name='', out=None):

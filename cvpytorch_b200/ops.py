@@ -343,3 +343,31 @@ def upsample_argmax(logits_view, nc, labels):
     B, Ho, Wo = labels.shape
     assert labels.dtype == torch.int64 and labels.is_contiguous()
     _lib.check(_lib.lib().cvb_upsample_argmax(byref(logits_view), nc, labels.data_ptr(), Ho, Wo, _stream()), 'cvb_upsample_argmax')
+
+
+# --------------------------------------------------------------------------------------- YOLOX post-processing
+class YoloxWorkspace:
+    """Caller-owned buffers of the YOLOX post-process: candidate records [B,A,8], kept rows det [B,A,7], count [B], NMS scratch."""
+
+    def __init__(self, B, A, device='cuda'):
+        self.B, self.A = B, A
+        self.cand = torch.zeros((B, A, 8), dtype=torch.float32, device=device)
+        self.det = torch.zeros((B, A, 7), dtype=torch.float32, device=device)
+        self.count = torch.zeros((B,), dtype=torch.int32, device=device)
+        nbytes = int(_lib.lib().cvb_yolox_workspace_bytes(B, A))
+        self.scratch = torch.empty((nbytes + 15) // 16 * 4, dtype=torch.float32, device=device)
+        self.scratch_bytes = nbytes
+
+
+def yolox_decode(reg_obj_view, cls_view, num_classes, stride, ws, off):
+    _lib.check(_lib.lib().cvb_yolox_decode(byref(reg_obj_view), byref(cls_view), num_classes, float(stride), ws.cand.data_ptr(), ws.A, off,
+                                           _stream()), 'cvb_yolox_decode')
+
+
+def yolox_nms(ws, conf_thres, iou_thres, vanilla_above=1000, cand=None):
+    """cand: optional foreign candidate tensor [B,A,8] (tests); default = the records written by yolox_decode."""
+    c = ws.cand if cand is None else cand
+    assert c.is_cuda and c.dtype == torch.float32 and c.is_contiguous() and tuple(c.shape) == (ws.B, ws.A, 8)
+    _lib.check(_lib.lib().cvb_yolox_nms(c.data_ptr(), ws.B, ws.A, float(conf_thres), float(iou_thres), int(vanilla_above), ws.det.data_ptr(),
+                                        ws.count.data_ptr(), ws.scratch.data_ptr(), ws.scratch_bytes, _stream()), 'cvb_yolox_nms')
+    return ws.det, ws.count

@@ -227,3 +227,58 @@ def build_deeplab(calibrated=True):
     model.load_state_dict(deeplab_state_dict(calibrated), strict=True)
     model.eval()
     return model
+
+
+# ================================================================================================= YOLOX-s
+YOLOX_CALIB_PATH = os.path.join(os.path.dirname(CALIB_PATH), 'yolox_calib.npz')
+YOLOX_CFG = {'TYPE': 'yolox_s',
+             'BACKBONE': {'name': 'CSPDarknet', 'subtype': 'yolox_s', 'out_stages': [2, 3, 4], 'output_stride': 32, 'pretrained': False},
+             'NECK': {'name': 'YOLOXNeck', 'channels': [256, 512, 1024]},
+             'HEAD': {'name': 'YOLOXHead', 'in_channels': [256, 512, 1024]}}
+
+
+def yolox_template_state_dict(num_classes=80):
+    from . import yolox_models as XM
+    bb = XM.build_backbone(YOLOX_CFG['BACKBONE'])
+    nk = XM.build_neck({**YOLOX_CFG['NECK'], 'depth_mul': 0.33, 'width_mul': 0.5})
+    hd = XM.build_head({**YOLOX_CFG['HEAD'], 'depth_mul': 0.33, 'width_mul': 0.5, 'num_classes': num_classes})
+    t = {}
+    for p, m in (('backbone.', bb), ('neck.', nk), ('head.', hd)):
+        for k, v in m.state_dict().items():
+            t[p + k] = v
+    return t
+
+
+def yolox_apply_calibration(sd, calib):
+    """BN statistics of the calibration pass + predictor scales / biases chosen so that a 640x640 noise image yields a few
+    thousand candidates with overlapping boxes (the un-calibrated head emits none: sigmoid(-4.6)^2 << 0.01)."""
+    for k in list(sd.keys()):
+        if k.endswith('running_mean') or k.endswith('running_var'):
+            sd[k] = torch.from_numpy(np.asarray(calib[k])).float().clone()
+    sc = np.asarray(calib['pred_scale'])  # [3 levels][cls, reg, obj]
+    for i in range(3):
+        sd[f'head.cls_preds.{i}.weight'] = sd[f'head.cls_preds.{i}.weight'] * float(sc[i, 0])
+        sd[f'head.reg_preds.{i}.weight'] = sd[f'head.reg_preds.{i}.weight'] * float(sc[i, 1])
+        sd[f'head.obj_preds.{i}.weight'] = sd[f'head.obj_preds.{i}.weight'] * float(sc[i, 2])
+        sd[f'head.cls_preds.{i}.bias'] = torch.full_like(sd[f'head.cls_preds.{i}.bias'], -2.0)
+        sd[f'head.obj_preds.{i}.bias'] = torch.full_like(sd[f'head.obj_preds.{i}.bias'], -2.0)
+        sd[f'head.reg_preds.{i}.bias'] = torch.tensor([0.0, 0.0, 1.6, 1.6])  # wh ~ 5 strides: neighbouring boxes overlap
+    return sd
+
+
+def yolox_state_dict(calibrated=True):
+    sd = base_state_dict(yolox_template_state_dict())
+    if calibrated:
+        if not os.path.exists(YOLOX_CALIB_PATH):
+            raise FileNotFoundError(f'{YOLOX_CALIB_PATH} missing: run tools/make_golden_yolox.py in the build container')
+        sd = yolox_apply_calibration(sd, np.load(YOLOX_CALIB_PATH))
+    return sd
+
+
+def build_yolox(calibrated=True):
+    from . import yolox_models as XM
+    dictionary = [{f'c{i}': 1.0} for i in range(80)]
+    model = XM.YOLOX(dictionary=dictionary, model_cfg=dict(YOLOX_CFG))
+    model.load_state_dict(yolox_state_dict(calibrated), strict=True)
+    model.eval()
+    return model

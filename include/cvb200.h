@@ -234,6 +234,26 @@ int cvb_fcos_nms(const float* scores, const int32_t* classes, const float* boxes
                  float iou_thres, int32_t topk, float* out_scores, int32_t* out_classes, float* out_boxes, int32_t* out_loc,
                  int32_t* out_count, int32_t* status, void* stream);
 
+/*
+ * YOLOX post-processing, replaces yolox_post_process (src/models/yolox.py:18-68) incl. the third-party
+ * torchvision.ops.batched_nms call at :64.
+ *
+ * cvb_yolox_decode: one head level.  reg_obj / cls: fp32 NHWC views [B,h,w,>=5] (reg 4, obj 1) and [B,h,w,>=nc] (class logits),
+ * i.e. the three predictors of heads/yolox_head.py:74-86 before their torch.cat.  Writes one 8-float record per location into
+ * cand[B, A, 8] at rows off .. off + h*w:  (x1, y1, x2, y2, obj, class_conf, class_pred, obj * class_conf) with
+ * xy = (p + grid) * stride, wh = exp(p) * stride (:33-35), sigmoids (:37-39), corner form (:46-51), best class (:57).
+ *
+ * cvb_yolox_nms: per image keeps locations with obj * class_conf >= conf_thres (:58), then batched_nms(boxes, scores, class, iou_thres):
+ * stable descending score order; more than `vanilla_above` boxes (torchvision: numel > 4000 on CPU tensors, i.e. 1000 boxes;
+ * 5000 on CUDA tensors) -> class-wise NMS on the raw boxes, else one NMS on boxes + class * (max_coordinate + 1); fp32 IoU
+ * compared in double, areas without +1.  det[B, A, 7] receives the kept rows (x1, y1, x2, y2, obj, class_conf, class_pred) in
+ * score order, det_count[B] their number (the reference returns None for 0).  A <= 16384.  workspace: cvb_yolox_workspace_bytes.
+ */
+size_t cvb_yolox_workspace_bytes(int32_t B, int32_t A);
+int cvb_yolox_decode(const CvbView* reg_obj, const CvbView* cls, int32_t nc, float stride, float* cand, int64_t A, int64_t off, void* stream);
+int cvb_yolox_nms(const float* cand, int32_t B, int32_t A, float conf_thres, double iou_thres, int32_t vanilla_above, float* det,
+                  int32_t* det_count, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Library info / errors */
 const char* cvb_last_error_string(void);
 int cvb_version(void);
