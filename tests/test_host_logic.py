@@ -112,6 +112,13 @@ def test_shard_range_covers_batch():
         assert spans[0][0] == 0 and spans[-1][1] == gb and all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
 
 
+def _free_port():
+    import socket
+    with socket.socket() as sk:
+        sk.bind(('127.0.0.1', 0))
+        return sk.getsockname()[1]
+
+
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
     from cvpytorch_b200.dist import all_gather_detections
@@ -131,7 +138,7 @@ def test_all_gather_detections_gloo_world2():
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 1000
+    port = _free_port()
     procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
@@ -167,7 +174,7 @@ def test_all_gather_fcos_and_label_maps_gloo_world2():
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    port = 30500 + os.getpid() % 1000
+    port = _free_port()
     procs = [ctx.Process(target=_gloo_worker_fcos_seg, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
