@@ -347,7 +347,8 @@ def run_b200_arm(args):
                     'note': 'algorithmic FLOPs 2*M*N*K of the fp32 reference graph (1051.75 GFLOP/bs64); the kernel issues 3 fp16 MMA products per fp32 '
                             'product (hi/lo split, fp32-equivalent accuracy), so frac <= 1/3 by construction; traffic = dram read+write of the conv '
                             'launches of one step (ncu, profiles/r01); per-layer numbers in profiles/'}
-        cpu_v, cores, spt, sample = cpu_reference_throughput(args.cpu_steps, 1) if args.cpu_steps > 0 else (None, 0, 0, 'skipped')
+        cpu_v, cores, spt, sample = cpu_reference_throughput(args.cpu_steps, 1) if (args.cpu_steps > 0 and world == 1) else (
+            None, 0, 0, 'skipped (timed at N=1 only)' if world > 1 else 'skipped')
         line = {'metric': METRIC, 'value': round(value, 2), 'unit': 'images/sec', 'n_gpus': world, 'steps': K, 'warmup': W,
                 'ms_per_step': round(ms_per_step, 4), 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
                 'dtype': 'fp16x3-split (fp32-equivalent, fp32 accumulate)', 'data': 'synthetic',

@@ -823,6 +823,7 @@ struct YoloxSmem {
   uint32_t keeplist[kXChunk];
   uint32_t warp_cnt[kXThreads / 32];
   float red[kXThreads / 32];
+  int cls_head[1024];      // per-class (hashed by class & 1023) chain of kept boxes: head index, links in knext (-1 = end)
   uint32_t n, m_alive, new_kept;
   float unit;
 };
@@ -833,7 +834,8 @@ struct YoloxSmem {
 // areas without +1.  Rows (x1, y1, x2, y2, obj, class_conf, class_pred) are written in kept (score) order.
 __global__ void __launch_bounds__(kXThreads) yolox_nms_kernel(const float* __restrict__ cand, int A, float conf, double iou_thr,
                                                               int vanilla_above, float* __restrict__ det, int* __restrict__ count,
-                                                              float4* __restrict__ kbox_g, float* __restrict__ karea_g, int* __restrict__ kcls_g) {
+                                                              float4* __restrict__ kbox_g, float* __restrict__ karea_g, int* __restrict__ kcls_g,
+                                                              int* __restrict__ knext_g) {
   extern __shared__ uint8_t xs_raw[];
   YoloxSmem& S = *reinterpret_cast<YoloxSmem*>(xs_raw);
   const int b = blockIdx.x;
@@ -842,8 +844,10 @@ __global__ void __launch_bounds__(kXThreads) yolox_nms_kernel(const float* __res
   float4* kbox = kbox_g + (size_t)b * A;
   float* karea = karea_g + (size_t)b * A;
   int* kcls = kcls_g + (size_t)b * A;
+  int* knext = knext_g + (size_t)b * A;
   float* dout = det + (size_t)b * A * 7;
   if (tid == 0) S.n = 0;
+  for (int i = tid; i < 1024; i += kXThreads) S.cls_head[i] = -1;
   __syncthreads();
   float cmax = -CUDART_INF_F;
   for (int i = tid; i < A; i += kXThreads) {
@@ -907,11 +911,20 @@ __global__ void __launch_bounds__(kXThreads) yolox_nms_kernel(const float* __res
         box = make_float4(__fadd_rn(bx.x, offv), __fadd_rn(bx.y, offv), __fadd_rn(bx.z, offv), __fadd_rn(bx.w, offv));
       }
       area = __fmul_rn(__fsub_rn(box.z, box.x), __fsub_rn(box.w, box.y));
-      for (int k = 0; k < kept_n; ++k) {
-        if (vanilla && kcls[k] != cls) continue;
-        if (iou_gt(kbox[k], karea[k], box, area, iou_thr)) {
-          alive = false;
-          break;
+      if (vanilla) {
+        // class-wise NMS: only kept boxes of the same class can suppress -> walk that class's chain (any order)
+        for (int k = S.cls_head[cls & 1023]; k >= 0; k = knext[k]) {
+          if (kcls[k] == cls && iou_gt(kbox[k], karea[k], box, area, iou_thr)) {
+            alive = false;
+            break;
+          }
+        }
+      } else {
+        for (int k = 0; k < kept_n; ++k) {
+          if (iou_gt(kbox[k], karea[k], box, area, iou_thr)) {
+            alive = false;
+            break;
+          }
         }
       }
     }
@@ -975,6 +988,7 @@ __global__ void __launch_bounds__(kXThreads) yolox_nms_kernel(const float* __res
       kbox[o] = S.cbox[r];
       karea[o] = S.carea[r];
       kcls[o] = S.ccls[r];
+      knext[o] = atomicExch(&S.cls_head[S.ccls[r] & 1023], o);
       const float* src = cb + (size_t)S.cidx[r] * 8;
       float* d = dout + (size_t)o * 7;
 #pragma unroll
@@ -991,7 +1005,7 @@ __global__ void __launch_bounds__(kXThreads) yolox_nms_kernel(const float* __res
 
 extern "C" size_t cvb_yolox_workspace_bytes(int32_t B, int32_t A) {
   if (B <= 0 || A <= 0) return 0;
-  return (size_t)B * A * (sizeof(float4) + sizeof(float) + sizeof(int));
+  return (size_t)B * A * (sizeof(float4) + sizeof(float) + 2 * sizeof(int));
 }
 
 extern "C" int cvb_yolox_decode(const CvbView* reg_obj, const CvbView* cls, int32_t nc, float stride, float* cand, int64_t A, int64_t off,
@@ -1027,8 +1041,9 @@ extern "C" int cvb_yolox_nms(const float* cand, int32_t B, int32_t A, float conf
   float4* kbox = static_cast<float4*>(workspace);
   float* karea = reinterpret_cast<float*>(kbox + (size_t)B * A);
   int* kcls = reinterpret_cast<int*>(karea + (size_t)B * A);
+  int* knext = kcls + (size_t)B * A;
   yolox_nms_kernel<<<B, kXThreads, sizeof(YoloxSmem), as_stream(stream)>>>(cand, A, conf_thres, iou_thres, vanilla_above, det, det_count, kbox, karea,
-                                                                          kcls);
+                                                                          kcls, knext);
   CVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return CVB_OK;
