@@ -17,14 +17,19 @@ def main():
     which = sys.argv[2] if len(sys.argv) > 2 else 'yolov5s'
     reps = 5
     dev = torch.device('cuda:0')
+    SH = SW = 640
     if which == 'fcos':
-        model, S = synth.build_fcos(True), 800
+        model, SH, SW = synth.build_fcos(True), 800, 800
+    elif which == 'deeplab':
+        model, SH, SW = synth.build_deeplab(True), 1024, 2048
+    elif which == 'yolox':
+        model = synth.build_yolox(True)
     else:
-        model, S = synth.build_yolov5s(True), 640
-    G = model.build_graph(B, S, S, dev)
+        model = synth.build_yolov5s(True)
+    G = model.build_graph(B, SH, SW, dev)
     g = G['g']
     torch.manual_seed(1029)
-    G['holder']['x'] = torch.randn(B, 3, S, S, device=dev)
+    G['holder']['x'] = torch.randn(B, 3, SH, SW, device=dev)
     g.run()
     torch.cuda.synchronize()
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
