@@ -414,7 +414,7 @@ __global__ void __launch_bounds__(kDecodeThreads) yolo_decode_fast_kernel(const 
                                                                           int no, const float* __restrict__ anchors_px, float stride,
                                                                           float* __restrict__ z, long long z_rows, long long z_off,
                                                                           uint32_t* __restrict__ hist, float* __restrict__ rowmax,
-                                                                          float conf) {
+                                                                          float conf, uint32_t nx_magic) {
   extern __shared__ uint32_t s_hist[];  // [kNmsBins] when HIST
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NW = kDecodeThreads / 32;
@@ -430,19 +430,16 @@ __global__ void __launch_bounds__(kDecodeThreads) yolo_decode_fast_kernel(const 
   const float* rbase = raw + ((size_t)b * npix + pix0) * pitch;
   float* zb = z + ((size_t)b * z_rows + z_off) * no;        // row index inside the level: a * npix + pix
   float* rmb = HIST ? rowmax + (size_t)b * z_rows + z_off : nullptr;
-  const int nrows = cpix * na;
   const bool v2 = (64 + lane) < no;
   const bool is_cls = lane >= 5;
-  for (int r0 = warp * R; r0 < nrows; r0 += NW * R) {
+  // rows = (anchor a, pixel p): explicit loop nest, so the only division left is pixel -> (py, px), done with a multiply-high
+  // (nx_magic = ceil(2^32 / nx), exact while pix * nx < 2^32: checked on the host)
+  for (int a = 0; a < na; ++a)
+  for (int p0 = warp * R; p0 < cpix; p0 += NW * R) {
     float v[R][3];
-    int av[R], pv[R];
 #pragma unroll
     for (int i = 0; i < R; ++i) {
-      const int rr = min(r0 + i, nrows - 1);
-      const int a = rr / cpix;
-      const int p = rr - a * cpix;
-      av[i] = a;
-      pv[i] = p;
+      const int p = min(p0 + i, cpix - 1);
       const float* src = rbase + (uint32_t)(p * pitch + a * no) + lane;
       v[i][0] = __ldg(src);
       v[i][1] = __ldg(src + 32);
@@ -450,10 +447,9 @@ __global__ void __launch_bounds__(kDecodeThreads) yolo_decode_fast_kernel(const 
     }
 #pragma unroll
     for (int i = 0; i < R; ++i) {
-      const bool ok = (r0 + i) < nrows;  // tail rows are computed on clamped inputs and not stored (keeps the shuffles convergent)
-      const int a = av[i];
-      const int pix = pix0 + pv[i];
-      const int py = pix / nx, px = pix - py * nx;
+      const bool ok = (p0 + i) < cpix;  // tail rows are computed on clamped inputs and not stored (keeps the shuffles convergent)
+      const int pix = pix0 + min(p0 + i, cpix - 1);
+      const int py = (int)__umulhi((uint32_t)pix, nx_magic), px = pix - py * nx;
       const uint32_t orow = (uint32_t)(a * npix + pix);
       float* dst = zb + (size_t)orow * no + lane;
       const float y0 = sigmoid_fast(v[i][0]);
@@ -1084,7 +1080,9 @@ extern "C" int cvb_yolo_decode(const CvbView* raw, int32_t na, int32_t no, const
   uint32_t* hist = static_cast<uint32_t*>(nms_workspace);
   float* rowmax = nms_workspace ? reinterpret_cast<float*>(static_cast<uint8_t*>(nms_workspace) + nms_ws_rowmax_offset(raw->B)) : nullptr;
   const float* rawp = static_cast<const float*>(raw->base);
-  if (xperm == nullptr && no >= 64 && (long long)kDecodePix * raw->c_pitch + (long long)na * no < 0x7fffffffLL) {
+  const uint32_t nx_magic = (uint32_t)((0x100000000ULL + (unsigned long long)raw->W - 1) / (unsigned long long)raw->W);
+  if (xperm == nullptr && no >= 64 && raw->W > 1 && (long long)kDecodePix * raw->c_pitch + (long long)na * no < 0x7fffffffLL &&
+      (unsigned long long)raw->H * raw->W * raw->W < 0x100000000ULL) {
     static bool fast_attr_set = false;
     if (!fast_attr_set) {
       CVB_CHECK_CUDA(cudaFuncSetAttribute(yolo_decode_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsBins * (int)sizeof(uint32_t)));
@@ -1094,13 +1092,13 @@ extern "C" int cvb_yolo_decode(const CvbView* raw, int32_t na, int32_t no, const
     cudaStream_t st = as_stream(stream);
     if (!hist)
       yolo_decode_fast_kernel<false, false><<<grid, kDecodeThreads, 0, st>>>(rawp, raw->H, raw->W, raw->c_pitch, na, no, anchors_px, stride, z, z_rows,
-                                                                             z_off, nullptr, nullptr, conf_thres);
+                                                                             z_off, nullptr, nullptr, conf_thres, nx_magic);
     else if (multi_label)
       yolo_decode_fast_kernel<true, true><<<grid, kDecodeThreads, smem, st>>>(rawp, raw->H, raw->W, raw->c_pitch, na, no, anchors_px, stride, z, z_rows,
-                                                                              z_off, hist, rowmax, conf_thres);
+                                                                              z_off, hist, rowmax, conf_thres, nx_magic);
     else
       yolo_decode_fast_kernel<true, false><<<grid, kDecodeThreads, smem, st>>>(rawp, raw->H, raw->W, raw->c_pitch, na, no, anchors_px, stride, z, z_rows,
-                                                                               z_off, hist, rowmax, conf_thres);
+                                                                               z_off, hist, rowmax, conf_thres, nx_magic);
   } else {
     yolo_decode_kernel<<<grid, kDecodeThreads, smem, as_stream(stream)>>>(rawp, raw->H, raw->W, raw->c_pitch, na, no, anchors_px, stride, z, z_rows,
                                                                           z_off, xperm, hist, rowmax, conf_thres, multi_label);
