@@ -186,3 +186,30 @@ def test_all_gather_fcos_and_label_maps_gloo_world2():
         assert s.shape == (4, 5) and c.dtype == torch.int32 and bx.shape == (4, 5, 4) and n.tolist() == [5, 0, 5, 1]
         assert float(s[0, 0]) == 0.0 and float(s[2, 0]) == 100.0 and float(bx[2, 0, 0]) == 0.5 and int(c[3, 4]) == 10
         assert g.dtype == torch.int64 and g.shape == (4, 4, 6) and int(g[0, 0, 1]) == 1 and int(g[2, 0, 1]) == 2
+
+
+def test_yolox_factories_and_contract_on_cpu():
+    from cvpytorch_b200 import _lib, synth
+    from cvpytorch_b200 import yolox_models as XM
+    with pytest.raises(NotImplementedError):
+        XM.build_backbone({'name': 'NoSuchBackbone'})
+    with pytest.raises(NotImplementedError):
+        XM.build_head({'name': 'NoSuchHead'})
+    # the reference YAML's (unbuildable) backbone name is accepted and mapped onto the composite that runs
+    cfg = dict(synth.YOLOX_CFG)
+    cfg['BACKBONE'] = {'name': 'CspDarkNet', 'out_stages': [2, 3, 4], 'output_stride': 32, 'pretrained': False}
+    m = XM.YOLOX(dictionary=[{f'c{i}': 1.0} for i in range(80)], model_cfg=cfg)
+    assert list(m.state_dict().keys()) == list(synth.yolox_template_state_dict().keys())
+    m.load_state_dict(synth.yolox_state_dict(calibrated=True), strict=True)
+    m.eval()
+    assert m.dummy_input.shape == (1, 3, 640, 640) and m.conf_thr == 0.01 and m.nms_thr == 0.65
+    assert m(torch.zeros(1, 3, 64, 64), None, 'infer') is None
+    with pytest.raises(_lib.CvbError):
+        m(torch.zeros(1, 3, 64, 64), None, 'val')  # CPU tensor: no fallback
+    with pytest.raises(RuntimeError):
+        m(torch.zeros(1, 3, 64, 64), None, 'train')
+    # Focus weight re-ordering: reference patch order (tl, bl, tr, br) -> loader order (tl, tr, bl, br), 4 zero pad channels
+    w = torch.arange(2 * 12 * 9, dtype=torch.float64).view(2, 12, 3, 3)
+    w16 = XM.focus_weights_to_s2d(w)
+    assert torch.equal(w16[:, 0:3], w[:, 0:3]) and torch.equal(w16[:, 3:6], w[:, 6:9]) and torch.equal(w16[:, 6:9], w[:, 3:6])
+    assert torch.equal(w16[:, 9:12], w[:, 9:12]) and float(w16[:, 12:].abs().max()) == 0.0
