@@ -942,6 +942,48 @@ __global__ void __launch_bounds__(256) upsample_argmax_kernel(const float* __res
   out[((size_t)b * Ho + ho) * Wo + wo] = (long long)bi;
 }
 
+// ------------------------------------------------------------------ output side
+// Detection rows back to original-image coordinates, in place, for the first count[b] rows of every image:
+//   x -= pad[1]; y -= pad[0]; x /= scale[1]; y /= scale[0]; clip to [0, width] / [0, height]     (src/models/yolov5.py:274-281,
+//   src/models/yolox.py:171-178, src/models/fcos.py:150-161) -- fp32 subtract / IEEE divide / min-max like the numpy lines.
+__global__ void rescale_clip_boxes_kernel(float* __restrict__ rows, int M, int row_stride, const int* __restrict__ count,
+                                          const float* __restrict__ pads, const float* __restrict__ scales, const float* __restrict__ wh) {
+  const int b = blockIdx.y;
+  const int n = min(count[b], M);
+  const float p0 = pads[b * 2], p1 = pads[b * 2 + 1], s0 = scales[b * 2], s1 = scales[b * 2 + 1], w = wh[b * 2], h = wh[b * 2 + 1];
+  for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+    float* q = rows + ((size_t)b * M + r) * row_stride;
+    const float x1 = __fdiv_rn(__fsub_rn(q[0], p1), s1), y1 = __fdiv_rn(__fsub_rn(q[1], p0), s0);
+    const float x2 = __fdiv_rn(__fsub_rn(q[2], p1), s1), y2 = __fdiv_rn(__fsub_rn(q[3], p0), s0);
+    q[0] = fminf(fmaxf(x1, 0.0f), w);
+    q[1] = fminf(fmaxf(y1, 0.0f), h);
+    q[2] = fminf(fmaxf(x2, 0.0f), w);
+    q[3] = fminf(fmaxf(y2, 0.0f), h);
+  }
+}
+
+// Segmentation confusion matrix (src/evaluator/eval_segmentation.py:52-57): cm[gt * nc + pred] += 1 for every pixel with
+// 0 <= gt < nc.  Shared-memory privatised counters per CTA (nc <= 64), flushed with 64-bit global atomics.
+__global__ void __launch_bounds__(256) confusion_matrix_kernel(const long long* __restrict__ gt, const long long* __restrict__ pred, long long n,
+                                                               int nc, unsigned long long* __restrict__ cm) {
+  extern __shared__ uint32_t s_cm[];
+  const int bins = nc * nc;
+  for (int i = threadIdx.x; i < bins; i += blockDim.x) s_cm[i] = 0;
+  __syncthreads();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long g = gt[i];
+    if (g >= 0 && g < nc) {
+      const long long p = pred[i];
+      if (p >= 0 && p < nc) atomicAdd(&s_cm[(int)g * nc + (int)p], 1u);  // np.bincount would raise on p outside [0, nc): not counted here
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < bins; i += blockDim.x) {
+    const uint32_t c = s_cm[i];
+    if (c) atomicAdd(&cm[i], (unsigned long long)c);
+  }
+}
+
 static int check_split_view(const CvbView* v, const char* what) {
   CVB_REQUIRE(v != nullptr && v->base != nullptr, "%s: null view", what);
   CVB_REQUIRE(v->c_pitch >= v->C && v->plane_stride % 2 == 0, "%s: bad view", what);
@@ -1244,6 +1286,29 @@ extern "C" int cvb_upsample_argmax(const CvbView* logits, int32_t nc, int64_t* l
   dim3 grid(ceil_div(Wo, 256), Ho, logits->B);
   upsample_argmax_kernel<<<grid, 256, 0, as_stream(stream)>>>(static_cast<const float*>(logits->base), logits->H, logits->W, logits->c_pitch, nc,
                                                              reinterpret_cast<long long*>(labels), Ho, Wo);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}
+
+extern "C" int cvb_rescale_clip_boxes(float* rows, int32_t B, int32_t M, int32_t row_stride, const int32_t* count, const float* pads,
+                                      const float* scales, const float* wh, void* stream) {
+  CVB_REQUIRE(rows && count && pads && scales && wh && B > 0 && M > 0 && row_stride >= 4, "rescale_clip_boxes: bad argument");
+  CVB_REQUIRE(B <= 65535, "rescale_clip_boxes: batch too large for the launch grid");
+  dim3 grid(ceil_div(M, 256) < 8 ? ceil_div(M, 256) : 8, B);
+  rescale_clip_boxes_kernel<<<grid, 256, 0, as_stream(stream)>>>(rows, M, row_stride, count, pads, scales, wh);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}
+
+extern "C" int cvb_confusion_matrix(const int64_t* gt, const int64_t* pred, int64_t n, int32_t num_classes, int64_t* cm, void* stream) {
+  CVB_REQUIRE(gt && pred && cm && n >= 0 && num_classes > 0 && num_classes <= 64, "confusion_matrix: bad argument (num_classes <= 64)");
+  if (n == 0) return CVB_OK;
+  long long grid = (n + 256LL * 16 - 1) / (256LL * 16);
+  if (grid > 148 * 8) grid = 148 * 8;
+  confusion_matrix_kernel<<<(int)grid, 256, (size_t)num_classes * num_classes * sizeof(uint32_t), as_stream(stream)>>>(
+      reinterpret_cast<const long long*>(gt), reinterpret_cast<const long long*>(pred), n, num_classes, reinterpret_cast<unsigned long long*>(cm));
   CVB_CHECK_CUDA(cudaGetLastError());
   count_launch();
   return CVB_OK;

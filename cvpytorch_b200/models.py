@@ -377,21 +377,15 @@ class YOLOv5(_GraphCache):
             raise RuntimeError("YOLOv5 (B200): only mode='val' (inference) is implemented; training stays on the reference")
         det, _, cnt = self.predict(imgs)
         losses = {}  # val-mode loss (yolov5.py:258) is a training diagnostic; not computed on the B200 path
-        det_h = det.cpu()
+        # yolov5.py:267-282 on the device (cvb_rescale_clip_boxes: same fp32 subtract / divide / clip as the numpy lines), then ONE
+        # device->host copy instead of one per image
+        rows = det.clone()
+        pads, scales, wh = ops.targets_to_device_geometry(targets, rows.shape[0], imgs.shape[2:], rows.device)
+        ops.rescale_clip_boxes(rows, cnt, pads, scales, wh)
+        det_h = rows.cpu()
         cnt_h = cnt.cpu().tolist()
         outputs = []
-        for i, pred in enumerate(det_h[b, :cnt_h[b]] for b in range(det_h.shape[0])):
-            t = targets[i] if targets is not None else {}
-            scale = np.asarray(t['scales'].cpu() if 'scales' in t else [1.0, 1.0], dtype=np.float32)
-            pad = np.asarray(t['pads'].cpu() if 'pads' in t else [0.0, 0.0], dtype=np.float32)
-            width = float(t['width']) if 'width' in t else float(imgs.shape[3])
-            height = float(t['height']) if 'height' in t else float(imgs.shape[2])
-            b = pred[:, :4].numpy().copy()          # yolov5.py:267-282
-            b[:, [0, 2]] -= pad[1]
-            b[:, [1, 3]] -= pad[0]
-            b[:, [0, 2]] /= scale[1]
-            b[:, [1, 3]] /= scale[0]
-            b[:, [0, 2]] = b[:, [0, 2]].clip(0, width)
-            b[:, [1, 3]] = b[:, [1, 3]].clip(0, height)
-            outputs.append({"boxes": torch.tensor(b), "labels": pred[:, 5], "scores": pred[:, 4]})
+        for b in range(det_h.shape[0]):
+            pred = det_h[b, :cnt_h[b]]
+            outputs.append({"boxes": pred[:, :4].clone(), "labels": pred[:, 5], "scores": pred[:, 4]})
         return losses, outputs

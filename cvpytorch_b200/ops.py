@@ -371,3 +371,46 @@ def yolox_nms(ws, conf_thres, iou_thres, vanilla_above=1000, cand=None):
     _lib.check(_lib.lib().cvb_yolox_nms(c.data_ptr(), ws.B, ws.A, float(conf_thres), float(iou_thres), int(vanilla_above), ws.det.data_ptr(),
                                         ws.count.data_ptr(), ws.scratch.data_ptr(), ws.scratch_bytes, _stream()), 'cvb_yolox_nms')
     return ws.det, ws.count
+
+
+# --------------------------------------------------------------------------------------- output side
+def rescale_clip_boxes(rows, count, pads, scales, wh):
+    """In place: rows [B,M,>=4] fp32 CUDA (x1,y1,x2,y2 first), count [B] int32, pads / scales / wh [B,2] fp32 CUDA (wh = width, height)."""
+    _require_cuda(rows, 'rescale_clip_boxes')
+    assert rows.dtype == torch.float32 and rows.is_contiguous() and rows.dim() == 3 and count.dtype == torch.int32
+    for t in (pads, scales, wh):
+        assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (rows.shape[0], 2)
+    B, M, S = rows.shape
+    _lib.check(_lib.lib().cvb_rescale_clip_boxes(rows.data_ptr(), B, M, S, count.data_ptr(), pads.data_ptr(), scales.data_ptr(), wh.data_ptr(),
+                                                 _stream()), 'cvb_rescale_clip_boxes')
+    return rows
+
+
+def targets_to_device_geometry(targets, B, default_hw, device):
+    """(pads, scales, wh) [B,2] fp32 device tensors from the reference's target dicts (identity when a key is missing)."""
+    pads = torch.zeros((B, 2), dtype=torch.float32)
+    scales = torch.ones((B, 2), dtype=torch.float32)
+    wh = torch.tensor([[float(default_hw[1]), float(default_hw[0])]] * B, dtype=torch.float32)
+    for i in range(B):
+        t = targets[i] if targets is not None and i < len(targets) else {}
+        if 'pads' in t:
+            pads[i] = torch.as_tensor(t['pads']).float().cpu()
+        if 'scales' in t:
+            scales[i] = torch.as_tensor(t['scales']).float().cpu()
+        if 'width' in t:
+            wh[i, 0] = float(t['width'])
+        if 'height' in t:
+            wh[i, 1] = float(t['height'])
+    return pads.to(device), scales.to(device), wh.to(device)
+
+
+def confusion_matrix(gt, pred, num_classes, out=None):
+    """out [nc,nc] int64 CUDA (accumulated) += confusion matrix of the int64 CUDA label maps gt / pred (eval_segmentation.py:52-57)."""
+    _require_cuda(gt, 'confusion_matrix')
+    assert gt.dtype == torch.int64 and pred.dtype == torch.int64 and gt.shape == pred.shape and pred.is_cuda
+    gt, pred = gt.contiguous(), pred.contiguous()
+    if out is None:
+        out = torch.zeros((num_classes, num_classes), dtype=torch.int64, device=gt.device)
+    _lib.check(_lib.lib().cvb_confusion_matrix(gt.data_ptr(), pred.data_ptr(), gt.numel(), num_classes, out.data_ptr(), _stream()),
+               'cvb_confusion_matrix')
+    return out

@@ -354,25 +354,18 @@ class YOLOX(_GraphCache):
         if isinstance(imgs, (list, tuple)):
             imgs = torch.stack(list(imgs))
         det, cnt = self.predict(imgs)
-        det_h, cnt_h = det.cpu(), cnt.cpu().tolist()
         losses = {}  # val-mode loss (yolox.py:156) is a training diagnostic; not computed on the B200 path
+        # yolox.py:165-178 on the device (cvb_rescale_clip_boxes), then ONE device->host copy of the kept prefix
+        kmax = max(int(cnt.max()), 1)
+        rows = det[:, :kmax].contiguous()
+        pads, scales, wh = ops.targets_to_device_geometry(targets, rows.shape[0], imgs.shape[2:], rows.device)
+        ops.rescale_clip_boxes(rows, cnt, pads, scales, wh)
+        det_h, cnt_h = rows.cpu(), cnt.cpu().tolist()
         outputs = []
         for i in range(det_h.shape[0]):
             pred = det_h[i, :cnt_h[i]]
-            t = targets[i] if targets is not None else {}
             if pred.shape[0] == 0:  # yolox.py:182-184
                 outputs.append({"boxes": torch.empty((0, 4)), "labels": torch.empty((0, 1)), "scores": torch.empty((0, 1))})
                 continue
-            scale = np.asarray(t['scales'].cpu() if 'scales' in t else [1.0, 1.0], dtype=np.float32)
-            pad = np.asarray(t['pads'].cpu() if 'pads' in t else [0.0, 0.0], dtype=np.float32)
-            width = float(t['width']) if 'width' in t else float(imgs.shape[3])
-            height = float(t['height']) if 'height' in t else float(imgs.shape[2])
-            b = pred[:, :4].numpy().copy()          # yolox.py:165-178
-            b[:, [0, 2]] -= pad[1]
-            b[:, [1, 3]] -= pad[0]
-            b[:, [0, 2]] /= scale[1]
-            b[:, [1, 3]] /= scale[0]
-            b[:, [0, 2]] = b[:, [0, 2]].clip(0, width)
-            b[:, [1, 3]] = b[:, [1, 3]].clip(0, height)
-            outputs.append({"boxes": torch.from_numpy(b), "labels": pred[:, 6], "scores": pred[:, 4] * pred[:, 5]})
+            outputs.append({"boxes": pred[:, :4].clone(), "labels": pred[:, 6], "scores": pred[:, 4] * pred[:, 5]})
         return losses, outputs

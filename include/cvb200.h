@@ -254,6 +254,20 @@ int cvb_yolox_decode(const CvbView* reg_obj, const CvbView* cls, int32_t nc, flo
 int cvb_yolox_nms(const float* cand, int32_t B, int32_t A, float conf_thres, double iou_thres, int32_t vanilla_above, float* det,
                   int32_t* det_count, void* workspace, size_t workspace_bytes, void* stream);
 
+/*
+ * Output side of the path, on the device instead of a per-image `.cpu().numpy()` loop.
+ *
+ * cvb_rescale_clip_boxes: rows [B, M, row_stride] fp32 (x1, y1, x2, y2 first), in place for the first count[b] rows:
+ *   x -= pad[1]; y -= pad[0]; x /= scale[1]; y /= scale[0]; clip to [0, width] / [0, height]
+ *   (src/models/yolov5.py:274-281, src/models/yolox.py:171-178, src/models/fcos.py:150-161); pads / scales / wh = device [B,2] fp32
+ *   (wh = width, height).  Same fp32 operations as the numpy lines: bit-identical results.
+ * cvb_confusion_matrix: cm[num_classes, num_classes] (int64, accumulated) += bincount(num_classes * gt[mask] + pred[mask]) with
+ *   mask = 0 <= gt < num_classes (src/evaluator/eval_segmentation.py:52-57); gt / pred = int64 label maps of n pixels; num_classes <= 64.
+ */
+int cvb_rescale_clip_boxes(float* rows, int32_t B, int32_t M, int32_t row_stride, const int32_t* count, const float* pads, const float* scales,
+                           const float* wh, void* stream);
+int cvb_confusion_matrix(const int64_t* gt, const int64_t* pred, int64_t n, int32_t num_classes, int64_t* cm, void* stream);
+
 /* Library info / errors */
 const char* cvb_last_error_string(void);
 int cvb_version(void);

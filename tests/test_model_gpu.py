@@ -120,6 +120,20 @@ def test_forward_val_contract(model):
         assert o['boxes'].shape[1] == 4 and o['boxes'].device.type == 'cpu'
         assert float(o['boxes'].min()) >= 0.0 and float(o['boxes'].max()) <= 128.0
         assert o['boxes'].shape[0] == o['labels'].shape[0] == o['scores'].shape[0] <= 300
+    # non-identity letterbox geometry: the device-side rescale/clip must equal the reference's numpy lines (yolov5.py:274-281)
+    targets2 = [{'labels': torch.zeros(1), 'boxes': torch.zeros(1, 4), 'scales': torch.tensor([0.4, 0.5]), 'pads': torch.tensor([3.0, 7.0]),
+                 'height': torch.tensor(300), 'width': torch.tensor(240)} for _ in range(2)]
+    _, outs2 = model(x, targets2, 'val')
+    det, _, cnt = model.predict(x)
+    for b, o in enumerate(outs2):
+        bb = det[b, :int(cnt[b]), :4].cpu().numpy().copy()
+        bb[:, [0, 2]] -= np.float32(7.0)
+        bb[:, [1, 3]] -= np.float32(3.0)
+        bb[:, [0, 2]] /= np.float32(0.5)
+        bb[:, [1, 3]] /= np.float32(0.4)
+        bb[:, [0, 2]] = bb[:, [0, 2]].clip(0, 240)
+        bb[:, [1, 3]] = bb[:, [1, 3]].clip(0, 300)
+        assert np.array_equal(o['boxes'].numpy(), bb)
 
 
 def test_cuda_graph_replay_matches_eager(model):

@@ -88,3 +88,41 @@ def test_decode_matches_reference_formula(cuda):
     err = float((got - ref).abs().max() / ref.abs().max())
     assert err < 5e-6, err  # sigmoid = ex2.approx + rcp.approx (|rel err| ~ 2^-22)
     assert float(z[:, :5].abs().max()) == 0.0
+
+
+def test_output_side_rescale_clip_and_confusion_matrix(cuda):
+    """SURVEY.md 8(f) rank 2: device-side box rescale/clip == the reference's numpy lines (yolov5.py:274-281) bit for bit;
+    device confusion matrix == eval_segmentation.py:52-57 (np.bincount) exactly."""
+    from cvpytorch_b200 import ops
+    rng = np.random.default_rng(3)
+    B, M = 5, 300
+    rows = rng.uniform(-50, 700, size=(B, M, 6)).astype(np.float32)
+    cnt = np.array([300, 0, 17, 299, 1], np.int32)
+    pads = rng.uniform(0, 40, size=(B, 2)).astype(np.float32)
+    scales = rng.uniform(0.3, 2.0, size=(B, 2)).astype(np.float32)
+    wh = np.array([[640, 480], [1280, 720], [333, 500], [640, 640], [50, 60]], np.float32)
+    out = ops.rescale_clip_boxes(torch.from_numpy(rows.copy()).cuda(), torch.from_numpy(cnt).cuda(), torch.from_numpy(pads).cuda(),
+                                 torch.from_numpy(scales).cuda(), torch.from_numpy(wh).cuda()).cpu().numpy()
+    for b in range(B):
+        k = int(cnt[b])
+        bb = rows[b, :k, :4].copy()              # the reference's lines, numpy float32
+        bb[:, [0, 2]] -= pads[b, 1]
+        bb[:, [1, 3]] -= pads[b, 0]
+        bb[:, [0, 2]] /= scales[b, 1]
+        bb[:, [1, 3]] /= scales[b, 0]
+        bb[:, [0, 2]] = bb[:, [0, 2]].clip(0, np.array(int(wh[b, 0])))
+        bb[:, [1, 3]] = bb[:, [1, 3]].clip(0, np.array(int(wh[b, 1])))
+        assert np.array_equal(out[b, :k, :4], bb), b
+        assert np.array_equal(out[b, k:], rows[b, k:]) and np.array_equal(out[b, :, 4:], rows[b, :, 4:])   # nothing else touched
+    # confusion matrix with ignore labels (255, -1) and accumulation over two updates
+    nc = 19
+    gt = rng.integers(-1, 21, size=(3, 97, 131)).astype(np.int64)
+    gt[gt == 20] = 255
+    pr = rng.integers(0, nc, size=gt.shape).astype(np.int64)
+    cm = ops.confusion_matrix(torch.from_numpy(gt).cuda(), torch.from_numpy(pr).cuda(), nc)
+    cm = ops.confusion_matrix(torch.from_numpy(gt[:1]).cuda(), torch.from_numpy(pr[:1]).cuda(), nc, out=cm)
+
+    def ref_matrix(g, p):
+        mask = (g >= 0) & (g < nc)
+        return np.bincount(nc * g[mask].astype('int') + p[mask], minlength=nc ** 2).reshape(nc, nc)
+    assert np.array_equal(cm.cpu().numpy(), ref_matrix(gt, pr) + ref_matrix(gt[:1], pr[:1]))
