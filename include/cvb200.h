@@ -176,8 +176,9 @@ int cvb_sppf_pool(const CvbView* x, const CvbView* y1, const CvbView* y2, const 
  *   z[b, z_off + (a*ny+y)*nx + x, :] = decode(sigmoid(raw))   (z row pitch = no floats, z_rows rows/img)
  *   xperm (optional) = raw permuted to [B,na,ny,nx,no]
  *   nms_workspace (optional): a workspace prepared with cvb_nms_workspace_reset(); the decode then also accumulates the
- *   NMS score histogram (conf_thres / multi_label as later passed to cvb_yolo_nms with hist_ready = 1), which saves
- *   one full pass over the prediction tensor.
+ *   NMS score histogram and the per-row best score (conf_thres / multi_label as later passed to cvb_yolo_nms with
+ *   hist_ready = 1; z_rows must then be the A of that call, the workspace must have been sized for it), which saves one full
+ *   pass over the prediction tensor and lets the NMS emit passes skip rows below their threshold.
  * replaces: YOLOv5Detect.forward src/models/detects/yolov5_detect.py:42-55, _make_grid :60-65.
  */
 int cvb_yolo_decode(const CvbView* raw, int32_t na, int32_t no, const float* anchors_px /*[na*2]*/, float stride,
@@ -191,7 +192,8 @@ int cvb_yolo_decode(const CvbView* raw, int32_t na, int32_t no, const float* anc
  * replaces: non_max_suppression src/models/yolov5.py:62-153 (multi_label / best-class, class-offset
  *           4096, max_nms 30000, max_det 300; the 10 s wall-clock break :149-151 is NOT reproduced),
  *           xywh2xyxy :52-59, torchvision.ops.nms (third party) called at :137.
- * workspace: cvb_nms_workspace_bytes(B, A, nc) bytes, caller-owned.
+ * workspace: cvb_nms_workspace_bytes(B, A, nc) bytes, caller-owned, 256-byte aligned (histogram, counters, 64-bit candidate keys,
+ *            per-row best scores).  The phase-B sort is one cooperative launch (grid = number of SMs).
  * status (device int32[4], optional): [0] overflow flag (candidate capacity exceeded), rest reserved.
  */
 typedef struct CvbNmsParams {
@@ -202,7 +204,7 @@ typedef struct CvbNmsParams {
   int32_t max_nms;     /* 30000 */
   int32_t max_det;     /* 300   */
   float max_wh;        /* 4096 class offset; 0 = agnostic */
-  int32_t hist_ready;  /* 1: the score histogram was already accumulated by cvb_yolo_decode (all levels) */
+  int32_t hist_ready;  /* 1: histogram + per-row best scores were already produced by cvb_yolo_decode (all levels) */
 } CvbNmsParams;
 
 size_t cvb_nms_workspace_bytes(int32_t B, int32_t A, int32_t nc);
