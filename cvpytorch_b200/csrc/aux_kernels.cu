@@ -1089,11 +1089,13 @@ extern "C" int cvb_sppf_pool(const CvbView* x, const CvbView* y1, const CvbView*
   CVB_REQUIRE(x->C % 8 == 0, "sppf: C must be a multiple of 8");
   const size_t smem = (size_t)x->H * x->W * 8 * sizeof(float) * 2;
   CVB_REQUIRE(smem <= 200 * 1024, "sppf: map %dx%d too large for the shared-memory pool kernel", x->H, x->W);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CVB_CHECK_CUDA(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  // one-time, thread-safe (C++11 static initialisation) opt-in to the large dynamic shared memory carve-out
+  static const cudaError_t attr_set_err = [] {
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    return e;
+  }();
+  CVB_CHECK_CUDA(attr_set_err);
   const int cgroups = x->C / 8;
   sppf_pool_kernel<<<x->B * cgroups, 256, smem, as_stream(stream)>>>(
       static_cast<const __half*>(x->base), x->H, x->W, x->c_pitch, x->plane_stride / 2, static_cast<__half*>(y1->base), y1->c_pitch,
@@ -1112,11 +1114,13 @@ extern "C" int cvb_yolo_decode(const CvbView* raw, int32_t na, int32_t no, const
   CVB_REQUIRE(nms_workspace == nullptr || z != nullptr, "yolo_decode: histogram needs the decoded output");
   CVB_REQUIRE((long long)raw->H * raw->W * na < 0x7fffffffLL, "yolo_decode: level too large");
   const size_t smem = nms_workspace ? (size_t)kNmsBins * sizeof(uint32_t) : 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    CVB_CHECK_CUDA(cudaFuncSetAttribute(yolo_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsBins * (int)sizeof(uint32_t)));
-    attr_set = true;
-  }
+  // one-time, thread-safe (C++11 static initialisation) opt-in to the large dynamic shared memory carve-out
+  static const cudaError_t attr_set_err = [] {
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(yolo_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsBins * (int)sizeof(uint32_t));
+    return e;
+  }();
+  CVB_CHECK_CUDA(attr_set_err);
   dim3 grid(ceil_div(raw->H * raw->W, kDecodePix), raw->B);
   CVB_REQUIRE(no <= 96, "yolo_decode: at most 91 classes supported (no=%d)", no);
   uint32_t* hist = static_cast<uint32_t*>(nms_workspace);
@@ -1125,12 +1129,14 @@ extern "C" int cvb_yolo_decode(const CvbView* raw, int32_t na, int32_t no, const
   const uint32_t nx_magic = (uint32_t)((0x100000000ULL + (unsigned long long)raw->W - 1) / (unsigned long long)raw->W);
   if (xperm == nullptr && no >= 64 && raw->W > 1 && (long long)kDecodePix * raw->c_pitch + (long long)na * no < 0x7fffffffLL &&
       (unsigned long long)raw->H * raw->W * raw->W < 0x100000000ULL) {
-    static bool fast_attr_set = false;
-    if (!fast_attr_set) {
-      CVB_CHECK_CUDA(cudaFuncSetAttribute(yolo_decode_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsBins * (int)sizeof(uint32_t)));
-      CVB_CHECK_CUDA(cudaFuncSetAttribute(yolo_decode_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsBins * (int)sizeof(uint32_t)));
-      fast_attr_set = true;
-    }
+    // one-time, thread-safe (C++11 static initialisation) opt-in to the large dynamic shared memory carve-out
+    static const cudaError_t fast_attr_set_err = [] {
+      cudaError_t e = cudaSuccess;
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(yolo_decode_fast_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsBins * (int)sizeof(uint32_t));
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(yolo_decode_fast_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kNmsBins * (int)sizeof(uint32_t));
+      return e;
+    }();
+    CVB_CHECK_CUDA(fast_attr_set_err);
     cudaStream_t st = as_stream(stream);
     if (!hist)
       yolo_decode_fast_kernel<false, false><<<grid, kDecodeThreads, 0, st>>>(rawp, raw->H, raw->W, raw->c_pitch, na, no, anchors_px, stride, z, z_rows,

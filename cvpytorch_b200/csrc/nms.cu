@@ -704,12 +704,14 @@ extern "C" int cvb_yolo_nms(const float* prediction, const CvbNmsParams* p, floa
   CVB_REQUIRE(stage_bytes <= 160 * 1024, "nms: too many classes (%d) for the shared-memory candidate stage", p->nc);
   const size_t gsmem = sizeof(GreedySmem) + (size_t)p->max_det * (sizeof(float4) + sizeof(float));
   CVB_REQUIRE(gsmem <= 200 * 1024, "nms: max_det too large");
-  static bool attr_set = false;
-  if (!attr_set) {
-    CVB_CHECK_CUDA(cudaFuncSetAttribute(nms_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CVB_CHECK_CUDA(cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  // one-time, thread-safe (C++11 static initialisation) opt-in to the large dynamic shared memory carve-out
+  static const cudaError_t attr_set_err = [] {
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nms_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(nms_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    return e;
+  }();
+  CVB_CHECK_CUDA(attr_set_err);
   if (!p->hist_ready) {
     nms_count_kernel<<<sgrid, kScanThreads, 0, st>>>(prediction, p->A, p->nc, p->conf_thres, p->multi_label, wsB);
     count_launch();
@@ -728,15 +730,15 @@ extern "C" int cvb_yolo_nms(const float* prediction, const CvbNmsParams* p, floa
   nms_emit_kernel<<<egrid, kScanThreads, stage_bytes, st>>>(prediction, p->A, p->nc, p->conf_thres, p->multi_label, wsB, status);
   count_launch(2);
   {
-    static int coop_grid = 0;
-    if (coop_grid == 0) {
+    // one CTA per SM: co-residency is guaranteed (required by the grid barriers); resolved once, thread-safe static initialisation
+    static const int coop_grid = [] {
       int dev = 0, sms = 0, per_sm = 0;
-      CVB_CHECK_CUDA(cudaGetDevice(&dev));
-      CVB_CHECK_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-      CVB_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bitonic_full_sort_kernel, 1024, 0));
-      CVB_REQUIRE(sms > 0 && per_sm > 0, "nms: cooperative sort kernel cannot be resident");
-      coop_grid = sms;  // one CTA per SM: co-residency guaranteed (required by the grid barriers)
-    }
+      if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+      if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bitonic_full_sort_kernel, 1024, 0) != cudaSuccess) return 0;
+      return (sms > 0 && per_sm > 0) ? sms : 0;
+    }();
+    CVB_REQUIRE(coop_grid > 0, "nms: cooperative sort kernel cannot be resident");
     int Bn = p->B;
     void* cargs[2] = {&wsB, &Bn};
     CVB_CHECK_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(bitonic_full_sort_kernel), dim3(coop_grid), dim3(1024), cargs, 0, st));
@@ -1033,11 +1035,13 @@ extern "C" int cvb_yolox_nms(const float* cand, int32_t B, int32_t A, float conf
   CVB_REQUIRE(A <= kXKeys, "yolox_nms: at most %d locations per image (got %d)", kXKeys, A);
   CVB_REQUIRE(workspace_bytes >= cvb_yolox_workspace_bytes(B, A) && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "yolox_nms: workspace");
   CVB_REQUIRE((reinterpret_cast<uintptr_t>(cand) & 15) == 0, "yolox_nms: candidate records must be 16-byte aligned");
-  static bool attr_set = false;
-  if (!attr_set) {
-    CVB_CHECK_CUDA(cudaFuncSetAttribute(yolox_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(YoloxSmem)));
-    attr_set = true;
-  }
+  // one-time, thread-safe (C++11 static initialisation) opt-in to the large dynamic shared memory carve-out
+  static const cudaError_t attr_set_err = [] {
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(yolox_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(YoloxSmem));
+    return e;
+  }();
+  CVB_CHECK_CUDA(attr_set_err);
   float4* kbox = static_cast<float4*>(workspace);
   float* karea = reinterpret_cast<float*>(kbox + (size_t)B * A);
   int* kcls = reinterpret_cast<int*>(karea + (size_t)B * A);
@@ -1374,11 +1378,13 @@ extern "C" int cvb_fcos_nms(const float* scores, const int32_t* classes, const f
   CVB_CHECK_CUDA(cudaMemsetAsync(out_classes, 0, (size_t)B * topk * sizeof(int32_t), st));
   CVB_CHECK_CUDA(cudaMemsetAsync(out_boxes, 0, (size_t)B * topk * 4 * sizeof(float), st));
   CVB_CHECK_CUDA(cudaMemsetAsync(out_loc, 0xFF, (size_t)B * topk * sizeof(int32_t), st));
-  static bool attr_set = false;
-  if (!attr_set) {
-    CVB_CHECK_CUDA(cudaFuncSetAttribute(fcos_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FcosSmem)));
-    attr_set = true;
-  }
+  // one-time, thread-safe (C++11 static initialisation) opt-in to the large dynamic shared memory carve-out
+  static const cudaError_t attr_set_err = [] {
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fcos_nms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FcosSmem));
+    return e;
+  }();
+  CVB_CHECK_CUDA(attr_set_err);
   fcos_nms_kernel<<<B, kFcosThreads, sizeof(FcosSmem), st>>>(scores, classes, boxes, N, score_thres, iou_thres, topk, out_scores, out_classes,
                                                             out_boxes, out_loc, out_count, status);
   CVB_CHECK_CUDA(cudaGetLastError());
