@@ -296,14 +296,6 @@ __global__ void sppf_pool_kernel(const __half* __restrict__ x, int H, int W, int
 // index arithmetic is 32-bit and per row.  While the scores are in registers the CTA also builds the NMS score
 // histogram of its image in shared memory (64 KB) and flushes the non-empty bins once -- this replaces the separate
 // counting pass over the 548 MB prediction tensor and keeps the hot bins out of global atomics.
-// sigmoid with two MUFU ops (ex2, rcp), |rel err| ~ 2^-22 (the reference's own CPU sigmoid is ~1 ulp; budget 1e-3)
-__device__ __forceinline__ float sigmoid_fast(float x) {
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-  return r;
-}
-
 constexpr int kDecodePix = 512;      // pixels per CTA (x na anchor rows)
 constexpr int kDecodeThreads = 512;  // 16 warps
 constexpr int kDecodeRows = 4;       // rows in flight per warp (all loads issued before the first use)

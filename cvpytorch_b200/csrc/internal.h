@@ -47,4 +47,15 @@ inline size_t nms_align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 inline size_t nms_ws_head_bytes(int B) { return nms_align_up((size_t)B * kNmsBins * 4, 256) + 6 * nms_align_up((size_t)B * 4, 256); }
 inline size_t nms_ws_rowmax_offset(int B) { return nms_ws_head_bytes(B) + (size_t)B * (kNmsCap + kNmsCapA) * 8; }
 
+#ifdef __CUDACC__
+// sigmoid with two MUFU ops (ex2, rcp), |rel err| ~ 2^-22 (the reference's own CPU sigmoid is ~1 ulp; parity budget 1e-3).  Shared by
+// the YOLOv5 / YOLOX / FCOS decode kernels so that every pass that recomputes a score gets the identical value.
+__device__ __forceinline__ float sigmoid_fast(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+#endif
+
 }  // namespace cvb

@@ -757,13 +757,6 @@ extern "C" int cvb_yolo_nms(const float* prediction, const CvbNmsParams* p, floa
 // =====================================================================================================================
 namespace cvb {
 
-__device__ __forceinline__ float sigmoid_x(float x) {
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-  return r;
-}
-
 // One warp per head location.  Record = (x1, y1, x2, y2, obj, class_conf, class_pred, obj * class_conf):
 //   xy = (p + grid) * stride, wh = exp(p) * stride (:33-35), sigmoid on obj / classes (:37-39), corners = c -/+ wh / 2 (:46-51),
 //   class_conf, class_pred = max over the class sigmoids, first maximum wins (:57).
@@ -782,7 +775,7 @@ __global__ void __launch_bounds__(256) yolox_decode_kernel(const float* __restri
   float best = -1.0f;
   int bi = 0x7fffffff;
   for (int k = lane; k < nc; k += 32) {
-    const float sc = sigmoid_x(__ldg(c + k));
+    const float sc = sigmoid_fast(__ldg(c + k));
     if (sc > best) {
       best = sc;
       bi = k;
@@ -803,7 +796,7 @@ __global__ void __launch_bounds__(256) yolox_decode_kernel(const float* __restri
     const float cy = __fmul_rn(__fadd_rn(__ldg(r + 1), (float)py), stride);
     const float w = __fmul_rn(expf(__ldg(r + 2)), stride);
     const float h = __fmul_rn(expf(__ldg(r + 3)), stride);
-    const float obj = sigmoid_x(__ldg(r + 4));
+    const float obj = sigmoid_fast(__ldg(r + 4));
     const float hw2 = __fdiv_rn(w, 2.0f), hh2 = __fdiv_rn(h, 2.0f);
     float4* o = reinterpret_cast<float4*>(cand + ((size_t)b * A + off + p) * 8);
     o[0] = make_float4(__fsub_rn(cx, hw2), __fsub_rn(cy, hh2), __fadd_rn(cx, hw2), __fadd_rn(cy, hh2));
@@ -1058,13 +1051,6 @@ extern "C" int cvb_yolox_nms(const float* cand, int32_t B, int32_t A, float conf
 // =====================================================================================================================
 namespace cvb {
 
-__device__ __forceinline__ float sigmoid_mufu(float x) {
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -1.4426950408889634f));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-  return r;
-}
-
 // One warp per location: max over class sigmoids (first maximum wins), score = sqrt(cls * sigmoid(cnt)), class id + 1,
 // box = (cx - l, cy - t, cx + r, cy + b) with ltrb = exp(raw * scale_i) (ScaleExp, fcos_head.py:13-19) and the location
 // centre (x*stride + stride//2, y*stride + stride//2) (coords_fmap2orig :14-31).
@@ -1083,7 +1069,7 @@ __global__ void __launch_bounds__(256) fcos_decode_kernel(const float* __restric
     float best = -1.0f;
     int bi = 0x7fffffff;
     for (int k = lane; k < nc; k += 32) {
-      const float p = sigmoid_mufu(__ldg(c + k));
+      const float p = sigmoid_fast(__ldg(c + k));
       if (p > best) {
         best = p;
         bi = k;
@@ -1100,7 +1086,7 @@ __global__ void __launch_bounds__(256) fcos_decode_kernel(const float* __restric
     }
     if (lane == 0) {
       const float* r = rc + row * rc_pitch;
-      const float cnt = sigmoid_mufu(__ldg(r + 4));
+      const float cnt = sigmoid_fast(__ldg(r + 4));
       const int py = pix / w, px = pix - py * w;
       const float half = (float)(((int)stride) / 2);
       const float cx = __fadd_rn(__fmul_rn((float)px, stride), half), cy = __fadd_rn(__fmul_rn((float)py, stride), half);
