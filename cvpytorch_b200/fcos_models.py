@@ -20,7 +20,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import _lib, ops
+from . import ops
 from .engine import GraphBuilder
 from .models import _GraphCache, _check_infer_input
 from .modules import folded

@@ -13,13 +13,12 @@ model-level module runs ONE fused graph end to end (split-NHWC internally, decod
 import math
 from copy import deepcopy
 
-import numpy as np
 import torch
 import torch.nn as nn
 
 from . import _lib, ops
-from .engine import GraphBuilder, Val
-from .modules import C3, Conv, ConvModule, CSPLayer, DownsamplingModule, SPPF, UpsamplingModule, folded
+from .engine import GraphBuilder
+from .modules import ConvModule, CSPLayer, DownsamplingModule, SPPF, UpsamplingModule, folded
 
 
 def _check_infer_input(module, x):

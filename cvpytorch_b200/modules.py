@@ -12,7 +12,6 @@ Mirrors (paths relative to /root/reference):
   DarknetBottleneck, CSPLayer, SPPF   src/models/modules/yolo_modules.py:40-104, :107-140, :165-194
   UpsamplingModule, DownsamplingModule  src/models/modules/yolo11_modules.py:388-408
 """
-import math
 
 import torch
 import torch.nn as nn

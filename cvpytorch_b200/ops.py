@@ -4,7 +4,6 @@ PyTorch is used only as plumbing (device memory, streams); all arithmetic on the
 libcvb200.so.  Host-side weight preparation (BN folding, hi/lo split, K-major packing) also lives here.
 """
 import ctypes
-import math
 from ctypes import byref, c_void_p
 
 import torch

@@ -8,7 +8,6 @@ tests/test_oracle_golden.py (the reference has no tests/KATs for this path, SURV
 
 Each function cites the reference code it restates (paths relative to /root/reference).
 """
-import math
 
 import torch
 import torch.nn.functional as F

@@ -7,9 +7,9 @@ YOLOv5-s oracle to fp16 / bf16 and reports the end-to-end error at 1x3x640x640 a
   bf16     both rounded to bf16                                                              -> 1.4e-1
 All are 10-100x outside the 1e-3 budget of BASELINE.json (the calibrated random network amplifies per-layer rounding ~28x),
 whereas the three-product fp16 split measures 2e-5 on the GPU (profiles/r01/e2e_error_vs_reference_golden.txt)."""
-import sys, os
+import sys
 sys.path.insert(0, '/root/repo')
-import torch, numpy as np, torch.nn.functional as F
+import torch, torch.nn.functional as F
 from oracle import yolov5_oracle as O
 from cvpytorch_b200 import synth
 torch.set_num_threads(8)
