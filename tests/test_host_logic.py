@@ -213,3 +213,28 @@ def test_yolox_factories_and_contract_on_cpu():
     w16 = XM.focus_weights_to_s2d(w)
     assert torch.equal(w16[:, 0:3], w[:, 0:3]) and torch.equal(w16[:, 3:6], w[:, 6:9]) and torch.equal(w16[:, 6:9], w[:, 3:6])
     assert torch.equal(w16[:, 9:12], w[:, 9:12]) and float(w16[:, 12:].abs().max()) == 0.0
+
+
+def test_focus_and_window_formulation_equivalence():
+    """YOLOX Focus (yolo_modules.py:29-37: cat(tl, bl, tr, br) -> 3x3 conv) == 3x3 conv over the loader's space-to-depth tensor with
+    focus_weights_to_s2d, and the row-window re-formulation used on the device (ops.window_weights: the three taps of a filter row laid
+    side by side over 4 adjacent pixels, one zero-padded) gives the same result."""
+    from cvpytorch_b200 import ops
+    from cvpytorch_b200.yolox_models import focus_weights_to_s2d
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 3, 12, 16, generator=g, dtype=torch.float64)
+    w = torch.randn(5, 12, 3, 3, generator=g, dtype=torch.float64)
+    ref = F.conv2d(torch.cat((x[..., ::2, ::2], x[..., 1::2, ::2], x[..., ::2, 1::2], x[..., 1::2, 1::2]), 1), w, None, 1, 1)
+    s2d = torch.zeros(2, 16, 6, 8, dtype=torch.float64)
+    for dy in range(2):
+        for dx in range(2):
+            for c in range(3):
+                s2d[:, (dy * 2 + dx) * 3 + c] = x[:, c, dy::2, dx::2]
+    w16 = focus_weights_to_s2d(w)
+    assert float((F.conv2d(s2d, w16, None, 1, 1) - ref).abs().max()) < 1e-12
+    # row-window form: input padded by one zero column on the left and two on the right (W + 3 columns), window of 4 pixels
+    ww = ops.window_weights(w16, 4)                       # [O, 4*16, 3, 1], k = kx*16 + c
+    xp = F.pad(s2d, (1, 2, 0, 0))                          # columns -1 .. W+1
+    win = torch.stack([xp[..., j:j + 8] for j in range(4)], 1).reshape(2, 64, 6, 8)   # channel = kx*16 + c of pixel (w - 1 + kx)
+    got = F.conv2d(win, ww, None, 1, (1, 0))
+    assert float((got - ref).abs().max()) < 1e-12
