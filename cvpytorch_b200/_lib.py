@@ -24,7 +24,7 @@ class CvbConvDesc(ctypes.Structure):
     _fields_ = [('inp', CvbView), ('out', CvbView), ('weights', c_void_p), ('cout_pad', c_int32),
                 ('bias', c_void_p), ('kh', c_int32), ('kw', c_int32), ('stride', c_int32), ('pad', c_int32),
                 ('dilation', c_int32), ('act', c_int32), ('out_kind', c_int32), ('residual', CvbView),
-                ('up_partial', CvbView), ('block_n', c_int32), ('sm_limit', c_int32), ('no_resident', c_int32), ('residual_before_act', c_int32), ('w_window', c_int32)]
+                ('up_partial', CvbView), ('block_n', c_int32), ('sm_limit', c_int32), ('no_resident', c_int32), ('residual_before_act', c_int32), ('w_window', c_int32), ('halo', c_int32)]
 
 
 class CvbNmsParams(ctypes.Structure):
@@ -39,6 +39,7 @@ SYMBOLS = {
     'cvb_conv_plan_run': (c_int32, [c_void_p, c_void_p]),
     'cvb_conv_plan_destroy': (None, [c_void_p]),
     'cvb_conv_plan_run_many': (c_int32, [POINTER(c_void_p), c_int32, c_void_p]),
+    'cvb_conv_plan_set_profile': (c_int32, [c_void_p, c_void_p, POINTER(c_int32)]),
     'cvb_nchw_to_split': (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, POINTER(CvbView), c_void_p]),
     'cvb_split_to_nchw': (c_int32, [POINTER(CvbView), c_void_p, c_void_p]),
     'cvb_f32nhwc_to_nchw': (c_int32, [POINTER(CvbView), c_void_p, c_void_p]),

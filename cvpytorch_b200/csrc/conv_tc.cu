@@ -71,6 +71,24 @@ struct alignas(64) ConvKArgs {
   int resid_pitch;        // elements per pixel
   const float* up;
   int up_pitch, up_H, up_W;
+  // ---- "halo" (copy / tap) mode: the activation tile is loaded ONCE per K chunk as one or a few boxes that include the filter
+  // halo ("copies"), and every filter tap is a row-shifted shared-memory descriptor view of a copy -- instead of one TMA box per tap.
+  // Cuts the L2 -> shared-memory fill traffic of a 3x3 layer up to 6x (the chip-wide L2 fill rate bounds those layers).
+  int halo;              // 0: classic, 1: one copy per horizontal tap offset (aligned views), 2: one copy per input map (full halo)
+  int n_copies;
+  int sb_stages;         // depth of the separate weight-tile ring (0: weights resident)
+  int kskip;             // K steps (of 16) skipped at the end of every chunk (zero weight columns of the row-window stems)
+  uint32_t a_slot_bytes; // bytes of one A ring slot (hi + lo planes of the largest copy)
+  uint32_t cp_bytes[6];  // bytes of ONE plane of copy c
+  uint32_t cp_lo_off[6]; // offset of the lo plane inside the slot
+  uint32_t cp_sbo[6];    // byte stride between the 8-row groups of a tap view of copy c (= one row of the copy's halo image)
+  uint16_t tap_off[kMaxTaps];  // first row of the tap's view inside its copy
+  int8_t cp_map[6], cp_dw[6], cp_dh[6], cp_ntaps[6];
+  int8_t tap_w[kMaxTaps];      // index of the tap in the packed weights (ky * kw + kx)
+  // the taps of copy c form an ny x nx grid: view offset = y * cp_row16 + x * (row bytes >> 4) (16-byte units), weight tap = w0 + y*wy + x*wx
+  uint32_t cp_row16[6];
+  int8_t cp_ny[6], cp_nx[6], cp_w0[6], cp_wy[6], cp_wx[6];
+  long long* prof;             // diagnostics (cvb_conv_plan_set_profile): per-CTA cycle counters of the three pipeline roles, or NULL
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
@@ -93,6 +111,18 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
   const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&hi));
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(x1 - hf.y), "f"(x0 - hf.x));
 }
+
+// diagnostics: cycles spent in a waiting primitive, accumulated per role (only when a profile buffer is attached)
+#define CVB_PROF_WAIT(slot, stmt)              \
+  do {                                         \
+    if (prof_on) {                             \
+      const long long _t0 = clock64();         \
+      stmt;                                    \
+      prof_acc[slot] += clock64() - _t0;       \
+    } else {                                   \
+      stmt;                                    \
+    }                                          \
+  } while (0)
 
 template <int CW>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[CW]) {
@@ -133,16 +163,19 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
     __trap();
   }
   const int STAGES = a.stages;
-  const int stage_bytes = a.b_resident ? 2 * A_BYTES : STAGE_BYTES;
+  const int stage_bytes = a.halo ? (int)a.a_slot_bytes : (a.b_resident ? 2 * A_BYTES : STAGE_BYTES);
   uint8_t* stage_base = smem;
-  uint8_t* b_res = smem + STAGES * stage_bytes;                                  // resident weights: k_iters x {hi, lo} tiles
-  uint8_t* out_stage0 = b_res + (a.b_resident ? a.taps * a.chunks * 2 * B_BYTES : 0);
+  uint8_t* b_res = smem + STAGES * stage_bytes;                                  // resident weights: k_iters x {hi, lo} tiles (halo mode: or the weight ring)
+  uint8_t* out_stage0 = b_res + (a.b_resident ? a.taps * a.chunks * 2 * B_BYTES : (a.halo ? a.sb_stages * 2 * B_BYTES : 0));
   uint8_t* res_stage = out_stage0 + a.out_bufs * Cfg::OUT_STAGE_BYTES;           // residual tile (same layout as an output tile)
   float* bias_s = reinterpret_cast<float*>(res_stage + (a.resid_tma ? Cfg::OUT_STAGE_BYTES : 0));
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + BLOCK_N);
+  const int SB = a.halo ? a.sb_stages : 0;
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
-  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* fullB = bars + 2 * STAGES;  // halo mode: separate ring of weight tiles
+  uint64_t* emptyB = fullB + SB;
+  uint64_t* tfull = emptyB + SB;
   uint64_t* tempty = tfull + 2;
   uint64_t* bfull = tempty + 2;  // resident weights have landed
   uint64_t* rfull = bfull + 1;   // residual tile has landed
@@ -162,6 +195,10 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
       for (int s = 0; s < STAGES; ++s) {
         mbar_init(&full[s], 1);
         mbar_init(&empty[s], 1);
+      }
+      for (int s = 0; s < SB; ++s) {
+        mbar_init(&fullB[s], 1);
+        mbar_init(&emptyB[s], 1);
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tfull[s], 1);
@@ -191,7 +228,10 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    if (elect_one()) {
+      const bool prof_on = a.prof != nullptr;
+      long long prof_acc[4] = {0, 0, 0, 0};
+      const long long prof_t0 = prof_on ? clock64() : 0;
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = 2 * a.a_box_bytes + (a.b_resident ? 0 : 2 * B_BYTES);
@@ -204,6 +244,47 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
         }
       }
       grid_dep_wait();  // activations are written by the previous kernel(s)
+      if (a.halo) {
+        // copy / tap mode: per (tile, K chunk) one box per copy (all filter rows -- and in mode 2 all filter columns -- of that
+        // chunk), then the weight tiles of the copy's taps in the order the MMA warp consumes them
+        int sb = 0;
+        uint32_t phase_b = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          const int nt = tile % a.tiles_n;
+          const int mt = tile / a.tiles_n;
+          const int wt = mt % a.tiles_w;
+          const int t2 = mt / a.tiles_w;
+          const int ht = t2 % a.tiles_h;
+          const int bt = t2 / a.tiles_h;
+          const int w0 = wt * a.TW, h0 = ht * a.TH, b0 = bt * a.NB, n0 = nt * BLOCK_N;
+          for (int ck = 0; ck < a.chunks; ++ck) {
+            int t = 0;
+            for (int c = 0; c < a.n_copies; ++c) {
+              CVB_PROF_WAIT(0, mbar_wait(&empty[stage], phase ^ 1, 100 + stage));
+              mbar_expect_tx(&full[stage], 2 * a.cp_bytes[c]);
+              uint8_t* sb_a = stage_base + stage * stage_bytes;
+              const CUtensorMap* mapA = &a.tmA[a.cp_map[c]];
+              tma_load_5d(mapA, &full[stage], sb_a, ck * BLOCK_K, w0 + a.cp_dw[c], h0 + a.cp_dh[c], b0, 0);
+              if (!a.a_fused) tma_load_5d(mapA, &full[stage], sb_a + a.cp_lo_off[c], ck * BLOCK_K, w0 + a.cp_dw[c], h0 + a.cp_dh[c], b0, 1);
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
+              if (!a.b_resident) {
+                for (int j = 0; j < a.cp_ntaps[c]; ++j, ++t) {
+                  CVB_PROF_WAIT(1, mbar_wait(&emptyB[sb], phase_b ^ 1, 150 + sb));
+                  mbar_expect_tx(&fullB[sb], 2 * B_BYTES);
+                  tma_load_3d(&a.tmB, &fullB[sb], b_res + sb * 2 * B_BYTES, a.tap_w[t] * a.cin + ck * BLOCK_K, n0, 0);
+                  if (++sb == SB) {
+                    sb = 0;
+                    phase_b ^= 1;
+                  }
+                }
+              }
+            }
+          }
+        }
+      } else
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int nt = tile % a.tiles_n;
         const int mt = tile / a.tiles_n;
@@ -217,7 +298,7 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
           const int cw = w0 + a.tap_dw[tap];
           const int ch = h0 + a.tap_dh[tap];
           for (int ck = 0; ck < a.chunks; ++ck) {
-            mbar_wait(&empty[stage], phase ^ 1, 100 + stage);
+            CVB_PROF_WAIT(0, mbar_wait(&empty[stage], phase ^ 1, 100 + stage));
             mbar_expect_tx(&full[stage], tx_bytes);
             uint8_t* sb = stage_base + stage * stage_bytes;
             tma_load_5d(mapA, &full[stage], sb, ck * BLOCK_K, cw, ch, b0, 0);  // fused: both planes in one box
@@ -233,19 +314,29 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
           }
         }
       }
+      if (prof_on) {  // producer: total cycles, waiting for a free A slot, waiting for a free weight slot
+        a.prof[blockIdx.x * 16 + 0] = clock64() - prof_t0;
+        a.prof[blockIdx.x * 16 + 1] = prof_acc[0];
+        a.prof[blockIdx.x * 16 + 2] = prof_acc[1];
+      }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
+      const bool prof_on = a.prof != nullptr;
+      long long prof_acc[4] = {0, 0, 0, 0};
+      const long long prof_t0 = prof_on ? clock64() : 0;
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      int hb = 0;             // halo mode: weight ring position
+      uint32_t hphase_b = 0;
       const int n_main = a.n_main;
       const uint32_t set_cols = (uint32_t)((n_main + 1) * BLOCK_N);
       if (a.b_resident && (int)blockIdx.x < total_tiles) mbar_wait(bfull, 0, 250);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tempty[acc], acc_phase ^ 1, 200 + acc);
+        CVB_PROF_WAIT(0, mbar_wait(&tempty[acc], acc_phase ^ 1, 200 + acc));
         tc_fence_after();
         // The tensor core's fp32 adder rounds toward zero, so a long accumulation chain shrinks |sum| by ~1.6e-8 per
         // MMA (measured, tools/precision_probe.py).  Chains are kept short: the hi*hi products rotate over n_main
@@ -253,8 +344,88 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
         const uint32_t d_base = tmem_base + (uint32_t)acc * set_cols;
         const uint32_t d_cross = d_base + (uint32_t)(n_main * BLOCK_N);
         int r = 0;
+        if (a.halo) {
+          // copy / tap mode: every tap is a row-shifted descriptor view of the copy in the current A slot; weight tiles come from
+          // the resident slab or from their own ring.  The taps of a copy form an ny x nx grid (filter rows x filter columns) whose
+          // view offsets and weight indices are affine in (y, x), so the loop needs no per-tap table: the single issuing thread is
+          // instruction-latency bound (measured: ~8 cycles per dependent instruction) and must spend fewer cycles preparing an MMA
+          // than the tensor pipe needs to execute it (~50 cycles at N <= 64, tools/mma_bench.cu).
+          constexpr int KSTEPS = BLOCK_K / 16;
+          constexpr uint32_t kLayout = SWZ == 128 ? 2u : (SWZ == 64 ? 4u : 6u);
+          constexpr uint64_t kDescHiB = ((uint64_t)((8u * SWZ) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)kLayout << 61);
+          const int ksteps = KSTEPS - a.kskip;
+          const uint32_t bres16 = (smem_u32(b_res) & 0x3FFFFu) >> 4;
+          const uint32_t wstep16 = (uint32_t)(a.chunks * 2 * B_BYTES) >> 4;  // resident slab: distance between consecutive weight taps
+          int it = 0;
+          for (int ck = 0; ck < a.chunks; ++ck) {
+            for (int c = 0; c < a.n_copies; ++c) {
+              const int ny = a.cp_ny[c], nx = a.cp_nx[c];
+              const uint32_t row16 = a.cp_row16[c], lo16 = a.cp_lo_off[c] >> 4;
+              const int w0 = a.cp_w0[c], wy = a.cp_wy[c], wx = a.cp_wx[c];
+              const uint64_t desc_hi_a = ((uint64_t)(a.cp_sbo[c] >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)kLayout << 61);
+              CVB_PROF_WAIT(1, mbar_wait(&full[stage], phase, 300 + stage));
+              tc_fence_after();
+              const uint32_t sa16 = ((smem_u32(stage_base + stage * stage_bytes) & 0x3FFFFu) >> 4) | 0x10000u;
+              for (int y = 0; y < ny; ++y) {
+                for (int x = 0; x < nx; ++x) {
+                  uint32_t b16;
+                  if (a.b_resident) {
+                    b16 = bres16 + (uint32_t)(w0 + y * wy + x * wx) * wstep16 + (uint32_t)ck * ((2u * B_BYTES) >> 4);
+                  } else {
+                    CVB_PROF_WAIT(2, mbar_wait(&fullB[hb], hphase_b, 350 + hb));
+                    tc_fence_after();
+                    b16 = bres16 + (uint32_t)hb * ((2u * B_BYTES) >> 4);
+                  }
+                  const uint64_t dah = desc_hi_a | (uint64_t)(sa16 + (uint32_t)y * row16 + (uint32_t)x * (SWZ >> 4));
+                  const uint64_t dal = dah + lo16;
+                  const uint64_t dbh = kDescHiB | (uint64_t)(b16 | 0x10000u);
+                  const uint64_t dbl = dbh + (B_BYTES >> 4);
+                  const uint32_t d_main = d_base + (uint32_t)(r * BLOCK_N);
+                  const bool first_main = it < n_main;
+                  if (a.mma_pair) {
+                    if constexpr (2 * BLOCK_N <= 256) {
+                      constexpr uint32_t IDESC2 = make_idesc_f16_f32(kTileM, 2 * BLOCK_N);
+#pragma unroll
+                      for (int k = 0; k < KSTEPS; ++k) {
+                        if (k < ksteps) {
+                          const uint64_t koff = (uint64_t)(k * 2);
+                          umma_f16(d_base, dah + koff, dbh + koff, IDESC2, (it | k) != 0 ? 1u : 0u);
+                          umma_f16(d_cross, dal + koff, dbh + koff, IDESC, 1u);
+                        }
+                      }
+                    }
+                  } else {
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k) {
+                      if (k < ksteps) {
+                        const uint64_t koff = (uint64_t)(k * 2);
+                        umma_f16(d_main, dah + koff, dbh + koff, IDESC, (first_main && k == 0) ? 0u : 1u);
+                        umma_f16(d_cross, dah + koff, dbl + koff, IDESC, (it | k) != 0 ? 1u : 0u);
+                        umma_f16(d_cross, dal + koff, dbh + koff, IDESC, 1u);
+                      }
+                    }
+                  }
+                  if (!a.b_resident) {
+                    umma_commit(&emptyB[hb]);
+                    if (++hb == SB) {
+                      hb = 0;
+                      hphase_b ^= 1;
+                    }
+                  }
+                  if (++r == n_main) r = 0;
+                  ++it;
+                }
+              }
+              umma_commit(&empty[stage]);  // all taps of this copy have been issued: the slot is free once they complete
+              if (++stage == STAGES) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        } else
         for (int it = 0; it < k_iters; ++it) {
-          mbar_wait(&full[stage], phase, 300 + stage);
+          CVB_PROF_WAIT(1, mbar_wait(&full[stage], phase, 300 + stage));
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + stage * stage_bytes);
           const uint32_t sbw = a.b_resident ? smem_u32(b_res + it * 2 * B_BYTES) : sa + 2 * A_BYTES;
@@ -299,6 +470,12 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
           acc_phase ^= 1;
         }
       }
+      if (prof_on) {  // MMA issuer: total cycles, waiting for a free accumulator, for activations, for weights
+        a.prof[blockIdx.x * 16 + 4] = clock64() - prof_t0;
+        a.prof[blockIdx.x * 16 + 5] = prof_acc[0];
+        a.prof[blockIdx.x * 16 + 6] = prof_acc[1];
+        a.prof[blockIdx.x * 16 + 7] = prof_acc[2];
+      }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..9)
@@ -314,6 +491,9 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
     const int nb = r2 / a.TH;
     constexpr int CW = OUT_GROUP_CH / 2;  // columns per warp per group (32, or 16 for 32-wide groups)
     constexpr int SUB = (BLOCK_N <= 64 && CW > 16) ? 16 : CW;  // columns held in registers at a time
+    const bool prof_on = a.prof != nullptr;
+    long long prof_acc[1] = {0};
+    const long long prof_t0 = prof_on ? clock64() : 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     int cur_n0 = -1;
@@ -394,7 +574,7 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
           }
         }
         if (g == 0) {
-          mbar_wait(&tfull[acc], acc_phase, 400 + acc);
+          CVB_PROF_WAIT(0, mbar_wait(&tfull[acc], acc_phase, 400 + acc));
           tc_fence_after();
         }
         // the staging tile written now was last read by the TMA store issued out_bufs groups ago
@@ -532,6 +712,10 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
       }
     }
     if (tid_e == 0) tma_store_wait_all0();
+    if (prof_on && tid_e == 0) {  // epilogue: total cycles, waiting for a finished accumulator
+      a.prof[blockIdx.x * 16 + 8] = clock64() - prof_t0;
+      a.prof[blockIdx.x * 16 + 9] = prof_acc[0];
+    }
   }
 
   tc_fence_before();
@@ -694,6 +878,258 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
     // keep 64-wide chunks: measured slower with twice the TMA operations.
     if (bn <= 64 && (cin == 64 || (cin == 128 && cout > 64)) && (d->kh * d->kw == 1 || win > 0)) bk = bk_small;
   }
+  // ---- filter taps: (input map, row offset, column offset) of every tap; stride 2 reads four "parity" maps
+  const int s = d->stride;
+  const int n_taps = win > 0 ? d->kh : d->kh * d->kw;
+  int8_t t_map[kMaxTaps], t_dh[kMaxTaps], t_dw[kMaxTaps];
+  if (win > 0) {
+    for (int ky = 0; ky < d->kh; ++ky) {
+      t_map[ky] = 0;
+      t_dh[ky] = (int8_t)(ky - d->pad);
+      t_dw[ky] = 0;  // the physical tensor carries the left zero column: window of output w starts at padded column w
+    }
+  } else {
+    for (int ky = 0; ky < d->kh; ++ky)
+      for (int kx = 0; kx < d->kw; ++kx) {
+        const int t = ky * d->kw + kx;
+        const int qy = ky * d->dilation - d->pad, qx = kx * d->dilation - d->pad;
+        CVB_REQUIRE(qy >= -127 && qy <= 127 && qx >= -127 && qx <= 127, "conv: tap offset %d/%d out of the supported range", qy, qx);
+        if (s == 1) {
+          t_map[t] = 0;
+          t_dh[t] = (int8_t)qy;
+          t_dw[t] = (int8_t)qx;
+        } else {
+          const int py = ((qy % 2) + 2) % 2, px = ((qx % 2) + 2) % 2;
+          t_map[t] = (int8_t)(py * 2 + px);
+          t_dh[t] = (int8_t)((qy - py) / 2);
+          t_dw[t] = (int8_t)((qx - px) / 2);
+        }
+      }
+  }
+
+  // ---- halo (copy / tap) mode decision: see ConvKArgs.  Geometry is fixed to 8 x 16 output pixels of one image per tile, so the
+  // 8-row groups of every tap view are 8 horizontally adjacent pixels and consecutive groups are one (halo) image row apart.
+  struct HaloCfg {
+    int mode = 0, bk = 0, resident = 0, sa = 0, sb = 0, out_bufs = 1, resid_tma = 0, ctas = 1, smem = 0;
+    int n_copies = 0, fused = 1;
+    int cp_map[6], cp_dw[6], cp_dh[6], cp_ntaps[6], cp_boxw[6], cp_boxh[6];
+    int cp_ny[6], cp_nx[6], cp_w0[6], cp_wy[6], cp_wx[6];  // taps of a copy as an ny x nx grid, weight tap = w0 + y*wy + x*wx
+    uint32_t cp_bytes[6], cp_lo_off[6], slot = 0;
+    int tap_w[kMaxTaps], tap_off[kMaxTaps];
+    int map_boxw[4], map_boxh[4];
+    int kskip = 0;
+    double cost = 0.0;
+    KernelEntry ke;
+  } hc;
+  static const bool two_ctas_on = [] {
+    const char* e = getenv("CVB_CTAS_PER_SM");  // A/B knob: 1 = always one CTA per SM
+    return !(e && atoi(e) == 1);
+  }();
+  static const bool resid_tma_on = [] {
+    const char* e = getenv("CVB_RESID_TMA");  // A/B knob: 0 = per-thread residual loads
+    return !(e && atoi(e) == 0);
+  }();
+  const bool can_pin = (ceil_div(cout, bn) == 1 || ceil_div(cout, bn) == 2 || ceil_div(cout, bn) == 4);
+  auto f_mma = [](int n) { return n / 2 > 50 ? n / 2 : 50; };  // cycles of one M=128, K=16 MMA (measured: tools/mma_bench.cu, floor of 50)
+  const int chain_all = n_taps * cin / 16;
+  const bool pair_mode_est = chain_all <= 160 && bn <= 128 && (bn == 128 || n_taps > 1);
+  const double kstep_clk = pair_mode_est ? f_mma(2 * bn) + f_mma(bn) : 3.0 * f_mma(bn);
+  const double kFillBpc = 40.0;  // L2 -> shared memory fill bandwidth per SM and clock when every SM pulls (measured ~6300 B/clk per chip)
+  const int halo_env = [] {
+    const char* e = getenv("CVB_HALO");  // A/B knob: 0 = classic one-box-per-tap loads everywhere, 1 / 2 = force that halo mode where possible
+    return e ? atoi(e) : -1;
+  }();
+  const bool has_resid = d->residual.base != nullptr;
+  const int HTW = 8, HTH = 16;
+  bool use_halo = false;
+  const int halo_req = d->halo != 0 ? d->halo : halo_env;  // per-plan request wins over the environment knob
+  if (n_taps > 1 && d->dilation == 1 && halo_req != 0 && halo_req != -2 && d->halo != -1) {
+    const int mode = halo_req == 1 ? 1 : 2;
+    // copies: mode 2 = one per input map (box covers every tap of the map); mode 1 = one per (map, column offset)
+    HaloCfg h;
+    h.mode = mode;
+    int nc = 0;
+    int order[kMaxTaps], n_ord = 0;
+    for (int m = 0; m < 4; ++m) {
+      int dwmin = 127, dwmax = -127, dhmin = 127, dhmax = -127, cnt = 0;
+      for (int t = 0; t < n_taps; ++t)
+        if (t_map[t] == m) {
+          dwmin = t_dw[t] < dwmin ? t_dw[t] : dwmin;
+          dwmax = t_dw[t] > dwmax ? t_dw[t] : dwmax;
+          dhmin = t_dh[t] < dhmin ? t_dh[t] : dhmin;
+          dhmax = t_dh[t] > dhmax ? t_dh[t] : dhmax;
+          ++cnt;
+        }
+      h.map_boxw[m] = h.map_boxh[m] = 0;
+      if (!cnt) continue;
+      h.map_boxh[m] = HTH + (dhmax - dhmin);
+      h.map_boxw[m] = mode == 2 ? HTW + (dwmax - dwmin) : HTW;
+      const int n_groups = mode == 2 ? 1 : (dwmax - dwmin + 1);
+      for (int gi = 0; gi < n_groups; ++gi) {
+        const int gdw = dwmin + gi;
+        int nt = 0;
+        int dhs[kMaxTaps], dws[kMaxTaps], ndh = 0, ndw = 0;
+        for (int t = 0; t < n_taps; ++t)
+          if (t_map[t] == m && (mode == 2 || t_dw[t] == gdw)) {
+            h.tap_w[n_ord] = t;
+            h.tap_off[n_ord] = (t_dh[t] - dhmin) * h.map_boxw[m] + (mode == 2 ? t_dw[t] - dwmin : 0);
+            order[n_ord++] = t;
+            ++nt;
+            bool seen = false;
+            for (int i = 0; i < ndh; ++i) seen |= dhs[i] == t_dh[t];
+            if (!seen) dhs[ndh++] = t_dh[t];
+            seen = false;
+            for (int i = 0; i < ndw; ++i) seen |= dws[i] == t_dw[t];
+            if (!seen) dws[ndw++] = t_dw[t];
+          }
+        if (!nt) continue;
+        if (nc >= 6) {
+          nc = 7;
+          break;
+        }
+        {
+          // the kernel walks the taps of a copy as an ny x nx grid with affine view offsets / weight indices: verify that structure
+          auto find = [&](int dh, int dw) {
+            for (int t = 0; t < n_taps; ++t)
+              if (t_map[t] == m && t_dh[t] == dh && t_dw[t] == dw) return t;
+            return -1;
+          };
+          bool affine = ndh * ndw == nt;
+          const int t00 = find(dhs[0], dws[0]);
+          const int wy = ndh > 1 ? find(dhs[1], dws[0]) - t00 : 0, wx = ndw > 1 ? find(dhs[0], dws[1]) - t00 : 0;
+          for (int y = 0; affine && y < ndh; ++y)
+            for (int x = 0; affine && x < ndw; ++x)
+              affine = find(dhs[y], dws[x]) == t00 + y * wy + x * wx && dhs[y] == dhmin + y && dws[x] == (mode == 2 ? dwmin + x : gdw);
+          if (!affine || t00 < 0 || t00 > 127 || wy > 127 || wx > 127 || wy < 0 || wx < 0) {
+            nc = 7;
+            break;
+          }
+          h.cp_ny[nc] = ndh;
+          h.cp_nx[nc] = ndw;
+          h.cp_w0[nc] = t00;
+          h.cp_wy[nc] = wy;
+          h.cp_wx[nc] = wx;
+        }
+        h.cp_map[nc] = m;
+        h.cp_dw[nc] = gdw;
+        h.cp_dh[nc] = dhmin;
+        h.cp_ntaps[nc] = nt;
+        h.cp_boxw[nc] = h.map_boxw[m];
+        h.cp_boxh[nc] = h.map_boxh[m];
+        ++nc;
+      }
+    }
+    (void)order;
+    bool ok = nc >= 1 && nc <= 6 && n_ord == n_taps;
+    for (int c = 0; ok && c < nc; ++c) ok = h.cp_boxw[c] <= 256 && h.cp_boxh[c] <= 256;
+    if (ok) {
+      h.n_copies = nc;
+      h.fused = 1;
+      for (int c = 0; c < nc; ++c)
+        if ((h.cp_boxw[c] * h.cp_boxh[c]) % 8 != 0) h.fused = 0;
+      // candidate K chunks: the classic choice first, then smaller ones (they may let the weights stay resident)
+      int bks[3], n_bk = 0;
+      if (win > 0) bks[n_bk++] = cin;  // row-window stems: one chunk per filter row, trailing zero weight columns are skipped
+      else {
+        for (int c : {64, 32, 16})
+          if (cin % c == 0 && (c >= 32 || n_bk == 0)) bks[n_bk++] = c;  // 16-wide chunks (32-byte rows) only when nothing else divides cin
+      }
+      // A/B knobs (read at every plan creation so one process can sweep them): K chunk, weight residency, CTAs per SM of the halo plans
+      const int bk_env = [] { const char* e = getenv("CVB_HALO_BK"); return e ? atoi(e) : 0; }();
+      const int res_env = [] { const char* e = getenv("CVB_HALO_RES"); return e ? atoi(e) : 1; }();
+      const int ctas_env = [] { const char* e = getenv("CVB_HALO_CTAS"); return e ? atoi(e) : 0; }();
+      const long long tiles_h = (long long)ceil_div(Wo, HTW) * ceil_div(Ho, HTH) * out.B * ceil_div(cout, bn);
+      HaloCfg best;
+      bool have = false;
+      for (int ctas = 2; ctas >= 1; --ctas) {
+        if (ctas == 2 && !(bn <= 64 && two_ctas_on)) continue;
+        if (ctas_env && ctas != ctas_env) continue;
+        const int budget = ctas == 2 ? kSmemBudget2 : kSmemBudget;
+        for (int bi = 0; bi < n_bk; ++bi) {
+          const int bkh = bks[bi];
+          if (bk_env && bkh != bk_env && win == 0) continue;
+          KernelEntry keh;
+          if (!lookup_kernel(bn, bkh, f32, &keh)) continue;
+          const int swz = bkh * 2;
+          const int chunks = cin / bkh;
+          uint32_t slot = 0;
+          double a_bytes = 0.0;
+          HaloCfg cand = h;
+          for (int c = 0; c < nc; ++c) {
+            const int rows = cand.cp_boxw[c] * cand.cp_boxh[c];
+            cand.cp_bytes[c] = (uint32_t)(rows * swz);
+            cand.cp_lo_off[c] = (uint32_t)(((rows + 7) / 8 * 8) * swz);
+            const uint32_t need = (cand.cp_lo_off[c] + cand.cp_bytes[c] + 1023u) / 1024u * 1024u;
+            slot = need > slot ? need : slot;
+            a_bytes += 2.0 * rows * swz;
+          }
+          a_bytes *= chunks;
+          const int b_stage = 2 * bn * swz;
+          const long long w_tot = (long long)n_taps * chunks * b_stage;
+          const int kskip = win > 0 ? ((win - d->kw) * in.C) / 16 : 0;
+          const double mma = ((double)n_taps * chunks * (bkh / 16 - kskip)) * kstep_clk;
+          for (int cfg = 0; cfg < 4; ++cfg) {
+            const int ob = (cfg & 2) ? 1 : 2;
+            const int rt = (cfg & 1) ? 0 : 1;
+            if (rt && !(has_resid && !f32 && resid_tma_on)) continue;
+            const int fixed = keh.tail_bytes + ob * keh.out_stage_bytes + (rt ? keh.out_stage_bytes : 0);
+            for (int res = 1; res >= 0; --res) {
+              int sa, sb = 0;
+              if (res) {
+                if (!(can_pin && !d->no_resident && res_env)) continue;
+                sa = (int)((budget - fixed - w_tot) / (long long)slot);
+              } else {
+                sb = 4;
+                sa = (budget - fixed - sb * b_stage) / (int)slot;
+                if (sa < 2) {
+                  sb = 3;
+                  sa = (budget - fixed - sb * b_stage) / (int)slot;
+                }
+              }
+              if (sa < 2) continue;
+              if (sa > 6) sa = 6;
+              const double fill = (a_bytes + (res ? 0.0 : (double)w_tot)) / kFillBpc;
+              double cost = (mma > fill ? mma : fill) + 300.0;
+              cost *= (ctas == 2 ? 0.93 : 1.0) * (ob == 2 ? 0.97 : 1.0) * ((rt || !has_resid) ? 1.0 : 1.02) * (sa >= 3 ? 1.0 : 1.05) *
+                      (bkh == 64 ? 1.0 : (bkh == 32 ? 1.01 : 1.03));
+              if (!have || cost < best.cost) {
+                best = cand;
+                best.bk = bkh;
+                best.resident = res;
+                best.sa = sa;
+                best.sb = sb;
+                best.out_bufs = ob;
+                best.resid_tma = rt;
+                best.ctas = ctas;
+                best.slot = slot;
+                best.kskip = kskip;
+                best.cost = cost;
+                best.ke = keh;
+                best.smem = fixed + sa * (int)slot + (res ? (int)w_tot : sb * b_stage);
+                have = true;
+              }
+            }
+          }
+        }
+      }
+      if (have) {
+        // classic estimate: one 128-row box per (tap, chunk); weights resident only below 64 KB
+        int cTW, cTH, cNB;
+        choose_box(out.B, Ho, Wo, &cTW, &cTH, &cNB);
+        const long long tiles_c = (long long)ceil_div(Wo, cTW) * ceil_div(Ho, cTH) * ceil_div(out.B, cNB) * ceil_div(cout, bn);
+        const int chunks_c = cin / bk;
+        const long long w_c = (long long)n_taps * chunks_c * 2 * bn * bk * 2;
+        const bool res_c = can_pin && !d->no_resident && w_c <= 64 * 1024;
+        const double fill_c = ((double)n_taps * chunks_c * kTileM * bk * 4 + (res_c ? 0.0 : (double)w_c)) / kFillBpc;
+        const double mma_c = (double)n_taps * cin / 16 * kstep_clk;
+        const double cost_c = (double)tiles_c * ((mma_c > fill_c ? mma_c : fill_c) + 300.0);
+        const double cost_h = (double)tiles_h * best.cost;
+        use_halo = halo_req > 0 ? true : cost_h < 0.95 * cost_c;
+        if (use_halo) hc = best;
+      }
+    }
+  }
+  if (use_halo) bk = hc.bk;
   KernelEntry ke;
   CVB_REQUIRE(lookup_kernel(bn, bk, f32, &ke), "conv: no kernel for block_n=%d block_k=%d", bn, bk);
 
@@ -704,6 +1140,11 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
 
   int TW, TH, NB;
   choose_box(out.B, Ho, Wo, &TW, &TH, &NB);
+  if (use_halo) {
+    TW = HTW;
+    TH = HTH;
+    NB = 1;
+  }
   a.TW = TW;
   a.TH = TH;
   a.NB = NB;
@@ -726,34 +1167,49 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   a.bias = d->bias;
   a.bias_len = d->cout_pad;
 
-  const int s = d->stride;
-  if (win > 0) {
-    for (int ky = 0; ky < d->kh; ++ky) {
-      a.tap_map[ky] = 0;
-      a.tap_dh[ky] = (int8_t)(ky - d->pad);
-      a.tap_dw[ky] = 0;  // the physical tensor carries the left zero column: window of output w starts at padded column w
+  for (int t = 0; t < n_taps; ++t) {
+    a.tap_map[t] = t_map[t];
+    a.tap_dh[t] = t_dh[t];
+    a.tap_dw[t] = t_dw[t];
+  }
+  if (use_halo) {
+    a.halo = hc.mode;
+    a.n_copies = hc.n_copies;
+    a.sb_stages = hc.sb;
+    a.kskip = hc.kskip;
+    a.a_slot_bytes = hc.slot;
+    a.a_fused = hc.fused;
+    for (int c = 0; c < hc.n_copies; ++c) {
+      a.cp_map[c] = (int8_t)hc.cp_map[c];
+      a.cp_dw[c] = (int8_t)hc.cp_dw[c];
+      a.cp_dh[c] = (int8_t)hc.cp_dh[c];
+      a.cp_ntaps[c] = (int8_t)hc.cp_ntaps[c];
+      a.cp_bytes[c] = hc.cp_bytes[c];
+      a.cp_lo_off[c] = hc.fused ? hc.cp_bytes[c] : hc.cp_lo_off[c];
+      a.cp_sbo[c] = (uint32_t)(hc.cp_boxw[c] * bk * 2);  // 8 consecutive accumulator rows = 8 horizontally adjacent pixels (TW == 8)
     }
-  } else
-  for (int ky = 0; ky < d->kh; ++ky)
-    for (int kx = 0; kx < d->kw; ++kx) {
-      const int t = ky * d->kw + kx;
-      const int qy = ky * d->dilation - d->pad, qx = kx * d->dilation - d->pad;
-      if (s == 1) {
-        a.tap_map[t] = 0;
-        a.tap_dh[t] = (int8_t)qy;
-        a.tap_dw[t] = (int8_t)qx;
-      } else {
-        const int py = ((qy % 2) + 2) % 2, px = ((qx % 2) + 2) % 2;
-        a.tap_map[t] = (int8_t)(py * 2 + px);
-        a.tap_dh[t] = (int8_t)((qy - py) / 2);
-        a.tap_dw[t] = (int8_t)((qx - px) / 2);
-      }
+    for (int t = 0; t < n_taps; ++t) {
+      a.tap_w[t] = (int8_t)hc.tap_w[t];
+      a.tap_off[t] = (uint16_t)hc.tap_off[t];
     }
+    for (int c = 0; c < hc.n_copies; ++c) {
+      a.cp_ny[c] = (int8_t)hc.cp_ny[c];
+      a.cp_nx[c] = (int8_t)hc.cp_nx[c];
+      a.cp_w0[c] = (int8_t)hc.cp_w0[c];
+      a.cp_wy[c] = (int8_t)hc.cp_wy[c];
+      a.cp_wx[c] = (int8_t)hc.cp_wx[c];
+      a.cp_row16[c] = (uint32_t)(hc.cp_boxw[c] * bk * 2) >> 4;
+    }
+  }
 
   int rc = CVB_OK;
   // ---- input maps: 5D (C, W, H, B, plane)
   {
-    const cuuint32_t box[5] = {(cuuint32_t)bk, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)NB, (cuuint32_t)(a.a_fused ? 2 : 1)};
+    cuuint32_t box[5] = {(cuuint32_t)bk, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)NB, (cuuint32_t)(a.a_fused ? 2 : 1)};
+    if (use_halo) {
+      box[1] = (cuuint32_t)hc.map_boxw[0];
+      box[2] = (cuuint32_t)hc.map_boxh[0];
+    }
     const long long pix = (long long)in.c_pitch * 2;  // bytes per pixel
     if (win > 0) {
       // overlapping-window view: element (k, w, h, b, p) = padded_input[p][b][h][w + k / C][k % C]; consecutive w overlap
@@ -771,6 +1227,10 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
           if (Wp <= 0 || Hp <= 0) {
             a.tmA[py * 2 + px] = a.tmA[0];
             continue;
+          }
+          if (use_halo && hc.map_boxw[py * 2 + px] > 0) {
+            box[1] = (cuuint32_t)hc.map_boxw[py * 2 + px];
+            box[2] = (cuuint32_t)hc.map_boxh[py * 2 + px];
           }
           const cuuint64_t dims[5] = {(cuuint64_t)cin, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)in.B, 2};
           const cuuint64_t str[4] = {(cuuint64_t)(pix * 2), (cuuint64_t)(pix * in.W * 2), (cuuint64_t)(pix * in.W * in.H),
@@ -820,11 +1280,7 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
     a.resid = static_cast<const __half*>(r.base);
     a.resid_plane = r.plane_stride / 2;
     a.resid_pitch = r.c_pitch;
-    static const bool resid_tma_on = [] {
-      const char* e = getenv("CVB_RESID_TMA");  // A/B knob: 0 = per-thread residual loads
-      return !(e && atoi(e) == 0);
-    }();
-    if (!f32 && resid_tma_on) {  // residual tile through TMA (same box / swizzle as the output tile)
+    if (!f32 && resid_tma_on && (!use_halo || hc.resid_tma)) {  // residual tile through TMA (same box / swizzle as the output tile)
       const int gch = bn >= 64 ? 64 : 32;
       const long long pixr = (long long)r.c_pitch * 2;
       const cuuint64_t dims[5] = {(cuuint64_t)cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)out.B, 2};
@@ -884,12 +1340,13 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
     }
     return (budget - base - ke.out_stage_bytes) / (a_stage + b_stage);
   };
-  static const bool two_ctas_on = [] {
-    const char* e = getenv("CVB_CTAS_PER_SM");  // A/B knob: 1 = always one CTA per SM
-    return !(e && atoi(e) == 1);
-  }();
   int stages = 0, ctas_per_sm = 1;
-  if (bn <= 64 && two_ctas_on) {
+  if (use_halo) {
+    stages = hc.sa;
+    a.b_resident = hc.resident;
+    a.out_bufs = hc.out_bufs;
+    ctas_per_sm = hc.ctas;
+  } else if (bn <= 64 && two_ctas_on) {
     // small-N tiles are bound by epilogue latency, not by smem capacity: two co-resident CTAs (each <= half the SM's shared
     // memory and <= 256 TMEM columns) overlap one tile's epilogue with the other's loads
     int res, ob;
@@ -903,6 +1360,10 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   }
   if (stages == 0) stages = plan_smem(kSmemBudget, a.b_resident, a.out_bufs);
   if (stages > 8) stages = 8;
+  if (use_halo && (a.resid_tma != hc.resid_tma)) {
+    delete p;
+    return set_error(CVB_ERR_INVALID, "conv: internal error (halo plan / residual staging mismatch)");
+  }
   if (stages < 2) {
     delete p;
     return set_error(CVB_ERR_INVALID, "conv: tile does not fit in shared memory (block_n=%d block_k=%d)", bn, bk);
@@ -949,6 +1410,7 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
     a.rz_gain = (float)(1.0 + rz_c * (double)((chain + n_main - 1) / n_main));
   }
   p->smem = base + stages * (a_stage + (a.b_resident ? 0 : b_stage)) + (a.b_resident ? k_iters * b_stage : 0) + a.out_bufs * ke.out_stage_bytes;
+  if (use_halo) p->smem = hc.smem;
   p->fn = ke.fn;
 
   static std::mutex mu;
@@ -983,8 +1445,9 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
     static const bool dbg = [] { const char* e = getenv("CVB_PLAN_DEBUG"); return e && atoi(e) != 0; }();
     if (dbg)
       fprintf(stderr, "[cvb plan] cin=%d cout=%d k=%dx%d s=%d out=%dx%dx%d bn=%d bk=%d stages=%d resident=%d out_bufs=%d ctas/sm=%d "
-              "tmem=%d n_main=%d nbuf=%d smem=%d grid=%d tiles=%lld resid_tma=%d\n", cin, cout, d->kh, d->kw, d->stride, out.B, Ho, Wo, bn, bk,
-              stages, a.b_resident, a.out_bufs, ctas_per_sm, a.tmem_cols, a.n_main, a.nbuf, p->smem, p->grid, total, a.resid_tma);
+              "tmem=%d n_main=%d nbuf=%d smem=%d grid=%d tiles=%lld resid_tma=%d halo=%d copies=%d sb=%d slot=%u kskip=%d pair=%d\n", cin, cout, d->kh, d->kw, d->stride, out.B, Ho, Wo, bn, bk,
+              stages, a.b_resident, a.out_bufs, ctas_per_sm, a.tmem_cols, a.n_main, a.nbuf, p->smem, p->grid, total, a.resid_tma, a.halo,
+              a.n_copies, a.sb_stages, a.a_slot_bytes, a.kskip, a.mma_pair);
   }
   *out_plan = p;
   return CVB_OK;
@@ -1025,3 +1488,10 @@ extern "C" int cvb_conv_plan_run_many(CvbConvPlan* const* plans, int32_t n, void
 }
 
 extern "C" void cvb_conv_plan_destroy(CvbConvPlan* p) { delete p; }
+
+extern "C" int cvb_conv_plan_set_profile(CvbConvPlan* p, long long* counters, int32_t* grid) {
+  CVB_REQUIRE(p != nullptr, "null plan");
+  p->args.prof = counters;
+  if (grid) *grid = p->grid;
+  return CVB_OK;
+}

@@ -44,27 +44,25 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
-// `tag` identifies the waiter in the watchdog message.
+// `tag` identifies the waiter in the watchdog message (printed only when built with -DCVB_WATCHDOG=2: the printf call site costs
+// ~30 instructions and a stack frame per inlined wait, and the single-thread producer / MMA loops are instruction-latency bound).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
 #if CVB_WATCHDOG
-  long long t0 = 0;
-  uint32_t spins = 0;
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins == 4096u) {
-      long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000LL) {  // ~2 s at 2 GHz
-        printf("[cvb200] mbarrier watchdog: block %d thread %d tag %d parity %u\n", (int)blockIdx.x, (int)threadIdx.x, tag,
-               parity);
-        __trap();
-      }
-      spins = 0;
+    if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz: trap instead of hanging the GPU
+#if CVB_WATCHDOG >= 2
+      printf("[cvb200] mbarrier watchdog: block %d thread %d tag %d parity %u\n", (int)blockIdx.x, (int)threadIdx.x, tag, parity);
+#endif
+      __trap();
     }
   }
 #else
   while (!mbar_try_wait(bar, parity)) {
   }
 #endif
+  (void)tag;
 }
 
 // ---------------------------------------------------------------- TMA

@@ -20,7 +20,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import ops
+from . import _lib, ops
 from .engine import GraphBuilder
 from .models import _GraphCache, _check_infer_input
 from .modules import folded
@@ -405,7 +405,9 @@ class FCOS(_GraphCache):
         return self._graphs[key]
 
     def predict(self, imgs):
-        """Device-only inference: (scores [B,K], classes [B,K] (1-based), boxes [B,K,4], loc [B,K], count [B]); no host sync."""
+        """Device-only inference: (scores [B,K], classes [B,K] (1-based), boxes [B,K,4], loc [B,K], count [B]); no host sync.
+        Graph-owned buffers (overwritten by the next call).  ``self._graph_for(imgs)['ws'].status[0] != 0`` flags a top-k
+        capacity overflow of the last run; ``forward()`` checks it and raises."""
         _check_infer_input(self, imgs)
         G = self._graph_for(imgs)
         G['holder']['x'] = imgs.contiguous().float()
@@ -422,6 +424,9 @@ class FCOS(_GraphCache):
             imgs = torch.stack(list(imgs), 0)
         sc, cl, bx, _, cnt = self.predict(imgs)
         sc, cl, bx, cnt = sc.cpu(), cl.cpu(), bx.cpu(), cnt.cpu().tolist()
+        if int(self._graph_for(imgs)['ws'].status[0]) != 0:
+            raise _lib.CvbError('FCOS NMS: more than 4096 scores share the top-k threshold bin; the candidate set of this batch would be '
+                                'truncated non-deterministically')
         img_h, img_w = imgs.shape[2:]
         outputs = []
         for i in range(imgs.shape[0]):

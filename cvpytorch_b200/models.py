@@ -27,6 +27,10 @@ def _check_infer_input(module, x):
                            '(training stays on the reference implementation)')
     if not (isinstance(x, torch.Tensor) and x.is_cuda):
         raise _lib.CvbError(f'{type(module).__name__}: input must be a CUDA tensor; there is no CPU fallback')
+    if x.device.index != torch.cuda.current_device():
+        # one device per process: plans, graph buffers and kernel launches all use the CURRENT device
+        raise _lib.CvbError(f'{type(module).__name__}: input lives on cuda:{x.device.index} but the current device is '
+                            f'cuda:{torch.cuda.current_device()}; call torch.cuda.set_device() first (one device per process)')
 
 
 class _GraphCache(nn.Module):
@@ -155,7 +159,7 @@ class YOLOv5Neck(_GraphCache):
     def forward(self, x):
         assert len(x) == len(self.in_channels)
         _check_infer_input(self, x[0])
-        key = tuple(tuple(t.shape) for t in x)
+        key = tuple(tuple(t.shape) for t in x) + (x[0].device.index,)
         if key not in self._graphs:
             B = x[0].shape[0]
             g = GraphBuilder(B, x[0].device)
@@ -220,7 +224,7 @@ class YOLOv5Detect(_GraphCache):
 
     def forward(self, x):
         _check_infer_input(self, x[0])
-        key = tuple(tuple(t.shape) for t in x)
+        key = tuple(tuple(t.shape) for t in x) + (x[0].device.index,)
         if key not in self._graphs:
             B = x[0].shape[0]
             g = GraphBuilder(B, x[0].device)
@@ -343,7 +347,9 @@ class YOLOv5(_GraphCache):
     def _graph_for(self, imgs, want_raw=False):
         u8 = imgs.dtype == torch.uint8
         B, H, W = (imgs.shape[0], imgs.shape[1], imgs.shape[2]) if u8 else (imgs.shape[0], imgs.shape[2], imgs.shape[3])
-        key = (B, H, W, imgs.device.index, want_raw, u8)
+        # the thresholds are baked into the decode histogram / NMS steps of a graph: they are part of the key so that changing
+        # model.conf_thres / iou_thres / max_det after the first forward takes effect (the reference reads them on every call, yolov5.py:262)
+        key = (B, H, W, imgs.device.index, want_raw, u8, float(self.conf_thres), float(self.iou_thres), int(self.max_det))
         if key not in self._graphs:
             self._graphs[key] = self.build_graph(B, H, W, imgs.device, want_raw, u8_input=u8)
         return self._graphs[key]
@@ -362,12 +368,19 @@ class YOLOv5(_GraphCache):
         return G['ws'].det, G['ws'].det_idx, G['ws'].det_count
 
     def predict(self, imgs):
-        """Device-only inference: returns (det [B,300,6], det_idx [B,300], det_count [B]) device tensors, no host sync."""
+        """Device-only inference: returns (det [B,300,6], det_idx [B,300], det_count [B]) device tensors, no host sync.
+        The tensors are the GRAPH-OWNED output buffers (overwritten by the next call with the same shape).  ``nms_status(imgs)``
+        returns the device status word of the last run ([0] != 0: the NMS candidate capacity overflowed and the result is invalid);
+        ``forward()`` checks it and raises."""
         _check_infer_input(self, imgs)
         G = self._graph_for(imgs)
         G['holder']['x'] = imgs.contiguous().float()
         G['g'].run()
         return G['ws'].det, G['ws'].det_idx, G['ws'].det_count
+
+    def nms_status(self, imgs):
+        """Device int32[4] status of the NMS stage of the graph that serves `imgs` ([0] = candidate-capacity overflow flag)."""
+        return self._graph_for(imgs)['ws'].status
 
     def forward(self, imgs, targets=None, mode='infer', **kwargs):
         if mode == 'infer':
@@ -383,6 +396,9 @@ class YOLOv5(_GraphCache):
         ops.rescale_clip_boxes(rows, cnt, pads, scales, wh)
         det_h = rows.cpu()
         cnt_h = cnt.cpu().tolist()
+        if int(self.nms_status(imgs)[0]) != 0:  # (the .cpu() above already synchronised)
+            raise _lib.CvbError('YOLOv5 NMS: candidate capacity overflow (more keys in the threshold bin than the workspace holds); '
+                                'the detections of this batch would be truncated non-deterministically')
         outputs = []
         for b in range(det_h.shape[0]):
             pred = det_h[b, :cnt_h[b]]

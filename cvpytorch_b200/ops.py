@@ -95,6 +95,9 @@ def pack_conv_weights(w64, b64, cin_pad=None, device='cuda'):
     w = torch.zeros((o_pad, kh, kw, cin_pad), dtype=torch.float64)
     w[:O, :, :, :I] = w64.permute(0, 2, 3, 1)
     w = w.reshape(o_pad, kh * kw * cin_pad)
+    if float(w.abs().max()) > 65504.0:  # fp16 hi would be inf and lo -inf -> NaN results; BN-folded weights are O(1)
+        raise _lib.CvbError(f'pack_conv_weights: |weight| up to {float(w.abs().max()):.3g} exceeds the fp16 range of the hi/lo operand '
+                            'format (65504); rescale the layer')
     hi = w.to(torch.float16)
     lo = (w - hi.double()).to(torch.float16)
     packed = torch.stack([hi, lo], 0).contiguous()
@@ -135,7 +138,7 @@ class ConvPlan:
     """Owns a CvbConvPlan handle (host-side TMA descriptors + launch shape) and keeps its tensors alive."""
 
     def __init__(self, inp, out, weights, bias, k, stride=1, pad=0, dilation=1, act=None, residual=None,
-                 up_partial=None, block_n=0, sm_limit=0, keepalive=(), w_window=0, no_resident=0, residual_before_act=0):
+                 up_partial=None, block_n=0, sm_limit=0, keepalive=(), w_window=0, no_resident=0, residual_before_act=0, halo=0):
         d = CvbConvDesc()
         d.inp, d.out = inp, out
         d.weights = weights.data_ptr()
@@ -151,6 +154,7 @@ class ConvPlan:
         d.w_window = w_window
         d.no_resident = no_resident
         d.residual_before_act = residual_before_act
+        d.halo = halo
         self._keep = (weights, bias) + tuple(keepalive)
         self.handle = c_void_p()
         _lib.check(_lib.lib().cvb_conv_plan_create(byref(d), byref(self.handle)), 'cvb_conv_plan_create')
@@ -179,16 +183,20 @@ def nchw_to_split(x, dst_view):
     _lib.check(_lib.lib().cvb_nchw_to_split(x.data_ptr(), B, C, H, W, byref(dst_view), _stream()), 'cvb_nchw_to_split')
 
 
-def split_to_nchw(src_view, out=None):
+def split_to_nchw(src_view, out=None, device=None):
+    """device: where to allocate `out` (default: the current CUDA device -- the library runs one device per process and
+    models._check_infer_input rejects tensors that live elsewhere)."""
     if out is None:
-        out = torch.empty((src_view.B, src_view.C, src_view.H, src_view.W), dtype=torch.float32, device='cuda')
+        out = torch.empty((src_view.B, src_view.C, src_view.H, src_view.W), dtype=torch.float32,
+                          device=device if device is not None else torch.device('cuda', torch.cuda.current_device()))
     _lib.check(_lib.lib().cvb_split_to_nchw(byref(src_view), out.data_ptr(), _stream()), 'cvb_split_to_nchw')
     return out
 
 
-def f32nhwc_to_nchw(src_view, out=None):
+def f32nhwc_to_nchw(src_view, out=None, device=None):
     if out is None:
-        out = torch.empty((src_view.B, src_view.C, src_view.H, src_view.W), dtype=torch.float32, device='cuda')
+        out = torch.empty((src_view.B, src_view.C, src_view.H, src_view.W), dtype=torch.float32,
+                          device=device if device is not None else torch.device('cuda', torch.cuda.current_device()))
     _lib.check(_lib.lib().cvb_f32nhwc_to_nchw(byref(src_view), out.data_ptr(), _stream()), 'cvb_f32nhwc_to_nchw')
     return out
 

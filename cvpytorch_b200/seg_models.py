@@ -169,7 +169,9 @@ class EncoderDecoder(_GraphCache):
         return self._graphs[key]
 
     def predict(self, imgs, out_hw=None):
-        """Device-only inference: int64 label map [B, Ho, Wo] (Ho, Wo default to the input size); no host sync."""
+        """Device-only inference: int64 label map [B, Ho, Wo] (Ho, Wo default to the input size); no host sync.
+        The returned tensor is the GRAPH-OWNED output buffer: the next call with the same shape overwrites it (zero-copy);
+        ``forward()`` returns a fresh tensor like the reference does."""
         _check_infer_input(self, imgs)
         G = self._graph_for(imgs, out_hw)
         G['holder']['x'] = imgs.contiguous().float()
@@ -179,9 +181,11 @@ class EncoderDecoder(_GraphCache):
     def forward(self, imgs, targets=None, mode='infer', epoch_num=0, step_num=0, **kwargs):
         if mode == 'val':
             out_hw = tuple(targets.shape[-2:]) if targets is not None else None
-            return self.predict(imgs, out_hw)  # encoder_decoder.py:131-133: argmax(bilinear(preds -> targets size))
+            # encoder_decoder.py:131-133: argmax(bilinear(preds -> targets size)); a fresh tensor per call like the reference (a caller may
+            # keep predictions of several batches), the zero-copy graph buffer is only handed out by predict()
+            return self.predict(imgs, out_hw).clone()
         if mode == 'infer':
             # the reference's 'infer' branch calls torch.argmax on a *list* and raises TypeError; the usable
             # inference path is 'val'.  Here 'infer' returns the label map at input resolution.
-            return self.predict(imgs)
+            return self.predict(imgs).clone()
         raise RuntimeError("EncoderDecoder (B200): training stays on the reference implementation")

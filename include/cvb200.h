@@ -85,6 +85,10 @@ typedef struct CvbConvDesc {
                            n*C must be 32 or 64.  Filter row ky reads input row h + ky - pad (rows outside the tensor are zero);
                            out.H is taken from the output view (allows the asymmetric 2-above/1-below padding of the
                            7x7/s2/p3 ResNet stem expressed as 4 rows over the space-to-depth input). */
+  int32_t halo;         /* activation loading of multi-tap layers.  0 = auto (cost model), -1 = classic: one TMA box per filter tap,
+                           1 / 2 = force "halo" mode where the layer allows it: the 8x16-pixel tile is loaded once per K chunk including
+                           the filter halo (2: one box per input map; 1: one box per horizontal tap offset) and every tap is a
+                           row-shifted shared-memory descriptor view of it -- up to 6x less L2->SM fill traffic for 3x3 layers. */
 } CvbConvDesc;
 
 typedef struct CvbConvPlan CvbConvPlan;
@@ -92,6 +96,11 @@ typedef struct CvbConvPlan CvbConvPlan;
 int cvb_conv_plan_create(const CvbConvDesc* desc, CvbConvPlan** plan);
 int cvb_conv_plan_run(const CvbConvPlan* plan, void* stream);
 void cvb_conv_plan_destroy(CvbConvPlan* plan);
+/* Diagnostics: attach a device buffer of grid * 16 int64 cycle counters (NULL detaches); every CTA then records how long its TMA
+ * producer, MMA issuer and epilogue spent in total and waiting on each pipeline barrier
+ * ([0..2] producer: total, wait free A slot, wait free weight slot; [4..7] MMA: total, wait accumulator, wait activations, wait
+ * weights; [8..9] epilogue: total, wait accumulator).  *grid receives the number of CTAs.  Used by tools/conv_pipeline_profile.py. */
+int cvb_conv_plan_set_profile(CvbConvPlan* plan, long long* counters, int32_t* grid);
 /* Run n plans back to back on one stream (one C call per forward instead of one per layer). */
 int cvb_conv_plan_run_many(CvbConvPlan* const* plans, int32_t n, void* stream);
 

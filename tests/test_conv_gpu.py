@@ -14,7 +14,7 @@ def _rel(a, b):
     return float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-12))
 
 
-def _run_conv(cin, cout, k, s, p, B, H, W, act='silu', residual=False, up=False, f32_out=False, block_n=0, seed=0, dil=1, no_resident=0):
+def _run_conv(cin, cout, k, s, p, B, H, W, act='silu', residual=False, up=False, f32_out=False, block_n=0, seed=0, dil=1, no_resident=0, halo=0):
     from cvpytorch_b200 import ops
     g = torch.Generator().manual_seed(seed)
     x = torch.randn(B, cin, H, W, generator=g)
@@ -47,7 +47,7 @@ def _run_conv(cin, cout, k, s, p, B, H, W, act='silu', residual=False, up=False,
         ref = ref + r.cuda()
     plan = ops.ConvPlan(tin.view(), tout.view(0, cout), wp, bp, k, s, p, dil, act,
                         residual=res_t.view() if res_t else None, up_partial=up_t.view() if up_t else None,
-                        block_n=block_n, no_resident=no_resident)
+                        block_n=block_n, no_resident=no_resident, halo=halo)
     plan.run()
     out = ops.f32nhwc_to_nchw(tout.view(0, cout)) if f32_out else ops.split_to_nchw(tout.view(0, cout))
     torch.cuda.synchronize()
@@ -191,3 +191,62 @@ def test_conv_3x3_shapes(cuda):
     assert _run_conv(64, 64, 3, 1, 1, 4, 160, 160, residual=True) < TOL
     assert _run_conv(32, 32, 3, 1, 1, 2, 160, 160, residual=True) < TOL
     assert _run_conv(512, 64, 3, 1, 1, 1, 16, 16) < TOL   # chain of 288 MMAs: two main accumulators (three-MMA form)
+
+
+# (cin, cout, k, s, p, B, H, W) -- layers the halo (copy / tap) loader applies to: every tap is a row-shifted descriptor view of a box
+# that was loaded once per K chunk including the filter halo (include/cvb200.h CvbConvDesc.halo)
+HALO = [
+    (32, 32, 3, 1, 1, 2, 32, 32),      # BLOCK_K 32 (64B swizzle), resident weights
+    (64, 64, 3, 1, 1, 2, 32, 32),      # 128B swizzle
+    (64, 64, 3, 1, 1, 3, 80, 80),      # many tiles per CTA: ring wrap-around of the A slots and the weight ring
+    (128, 128, 3, 1, 1, 2, 40, 40),    # two K chunks, streamed weights, partial tiles in H (40 = 2.5 x 16)
+    (256, 256, 3, 1, 1, 1, 20, 20),    # two N tiles, ragged W (20 = 2.5 x 8)
+    (64, 64, 3, 1, 1, 1, 13, 19),      # ragged map
+    (32, 64, 3, 2, 1, 2, 64, 64),      # stride 2: four parity maps with their own halo boxes
+    (64, 128, 3, 2, 1, 2, 32, 32),
+    (128, 128, 3, 2, 1, 1, 26, 38),    # stride 2, odd parity-map sizes
+    (64, 64, 3, 2, 1, 1, 13, 19),
+    (96, 64, 3, 1, 1, 1, 16, 24),      # cin not a multiple of 64
+    (512, 64, 3, 1, 1, 1, 16, 16),     # chain of 288 MMAs: two main accumulators
+]
+
+
+@pytest.mark.parametrize('mode', [1, 2])
+@pytest.mark.parametrize('cfg', HALO, ids=lambda c: 'x'.join(map(str, c)))
+def test_conv_halo_modes(cuda, cfg, mode):
+    cin, cout, k, s, p, B, H, W = cfg
+    err = _run_conv(cin, cout, k, s, p, B, H, W, halo=mode)
+    assert err < TOL, f'rel err {err}'
+    assert _run_conv(cin, cout, k, s, p, B, H, W, halo=-1) < TOL  # classic loader on the same layer
+
+
+@pytest.mark.parametrize('mode', [1, 2])
+def test_conv_halo_epilogues(cuda, mode):
+    assert _run_conv(64, 64, 3, 1, 1, 2, 48, 48, residual=True, halo=mode) < TOL
+    assert _run_conv(32, 32, 3, 1, 1, 2, 160, 160, residual=True, halo=mode) < TOL
+    assert _run_conv(64, 64, 3, 1, 1, 2, 32, 32, act='relu', halo=mode) < TOL
+    assert _run_conv(64, 128, 3, 1, 1, 2, 32, 32, act=None, f32_out=True, halo=mode) < TOL
+    assert _run_conv(64, 64, 3, 1, 1, 2, 32, 32, no_resident=1, halo=mode) < TOL
+    assert _run_conv(128, 128, 3, 1, 1, 4, 80, 80, residual=True, halo=mode) < TOL  # more tiles than SMs
+
+
+@pytest.mark.parametrize('mode', [-1, 1, 2])
+def test_stem_window_halo(cuda, mode):
+    """row-window stem through the halo loader: one box of 18 window rows per tile, the three filter rows are views of it, and the
+    K step of the all-zero fourth window column is skipped"""
+    from cvpytorch_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    for (B, H, W) in [(2, 64, 96), (1, 128, 136), (2, 320, 320)]:
+        x = torch.randn(B, 3, H, W, generator=g)
+        w = torch.randn(32, 3, 6, 6, generator=g) / 108 ** 0.5
+        b = torch.randn(32, generator=g)
+        ref = F.silu(F.conv2d(x.cuda(), w.cuda(), b.cuda(), 2, 2))
+        t = ops.SplitTensor(B, H // 2, W // 2 + 3, 16)
+        ops.stem_s2d(x.cuda().contiguous(), t.view())
+        wp, bp = ops.pack_conv_weights(ops.window_weights(ops.stem_weights_to_s2d(w.double()), 4), b.double())
+        out = ops.SplitTensor(B, H // 2, W // 2, 32)
+        plan = ops.ConvPlan(t.view(), out.view(), wp, bp, 3, 1, 1, 1, 'silu', w_window=4, halo=mode)
+        plan.run()
+        y = ops.split_to_nchw(out.view())
+        torch.cuda.synchronize()
+        assert _rel(y, ref) < TOL, (B, H, W, mode)
