@@ -88,6 +88,7 @@ struct alignas(64) ConvKArgs {
   // the taps of copy c form an ny x nx grid: view offset = y * cp_row16 + x * (row bytes >> 4) (16-byte units), weight tap = w0 + y*wy + x*wx
   uint32_t cp_row16[6];
   int8_t cp_ny[6], cp_nx[6], cp_w0[6], cp_wy[6], cp_wx[6];
+  int dbg;                     // diagnostics (CVB_DBG, results are WRONG): bit 0 = no TMA stores, bit 1 = activations loaded only for the first ring pass, bit 2 = epilogue skips the math / staging
   long long* prof;             // diagnostics (cvb_conv_plan_set_profile): per-CTA cycle counters of the three pipeline roles, or NULL
 };
 
@@ -128,6 +129,36 @@ template <int CW>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[CW]) {
   if constexpr (CW == 32) tmem_ld_32x32(taddr, v);
   else tmem_ld_32x16(taddr, v);
+}
+
+// The MMAs of one (filter tap, K chunk): KSTEPS K steps of 16 over the hi / lo activation views and the hi / lo weight tiles.
+//   PAIR: A_hi x [B_hi | B_lo] as ONE MMA of N = 2 * BLOCK_N into (main | cross), then A_lo x B_hi into cross -- 2 MMAs per K step
+//   else: three MMAs per K step (hi*hi -> d_main, hi*lo and lo*hi -> d_cross)
+// Descriptor low words in 16-byte units (a16: hi activation view, a16 + lo16: lo view, b16: hi weight tile, + bl16: lo tile); the
+// high words are loop invariants.  `nz` = 0 only for the first tap of a tile (the first MMA then overwrites the accumulators).
+template <int BLOCK_N, int KSTEPS, bool PAIR, bool KSKIP>
+__device__ __forceinline__ void issue_tap(uint32_t a16, uint32_t lo16, uint32_t a_hi, uint32_t b16, uint32_t bl16, uint32_t b_hi,
+                                          uint32_t d_base, uint32_t d_main, uint32_t d_cross, uint32_t nz, uint32_t main_nz, int ksteps) {
+  constexpr uint32_t IDESC = make_idesc_f16_f32(kTileM, BLOCK_N);
+  if constexpr (PAIR) {
+    constexpr uint32_t IDESC2 = make_idesc_f16_f32(kTileM, 2 * BLOCK_N <= 256 ? 2 * BLOCK_N : BLOCK_N);
+#pragma unroll
+    for (int k = 0; k < KSTEPS; ++k) {
+      if (!KSKIP || k < ksteps) {
+        umma_f16_lh(d_base, a16 + 2 * k, a_hi, b16 + 2 * k, b_hi, IDESC2, k == 0 ? nz : 1u);
+        umma_f16_lh(d_cross, a16 + lo16 + 2 * k, a_hi, b16 + 2 * k, b_hi, IDESC, 1u);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < KSTEPS; ++k) {
+      if (!KSKIP || k < ksteps) {
+        umma_f16_lh(d_main, a16 + 2 * k, a_hi, b16 + 2 * k, b_hi, IDESC, k == 0 ? main_nz : 1u);
+        umma_f16_lh(d_cross, a16 + 2 * k, a_hi, b16 + bl16 + 2 * k, b_hi, IDESC, k == 0 ? nz : 1u);
+        umma_f16_lh(d_cross, a16 + lo16 + 2 * k, a_hi, b16 + 2 * k, b_hi, IDESC, 1u);
+      }
+    }
+  }
 }
 
 template <int BLOCK_N, int BLOCK_K, bool OUT_F32>
@@ -228,7 +259,7 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (elect_one()) {
+    if (elect_one() && !(a.dbg & 16)) {
       const bool prof_on = a.prof != nullptr;
       long long prof_acc[4] = {0, 0, 0, 0};
       const long long prof_t0 = prof_on ? clock64() : 0;
@@ -261,11 +292,15 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
             int t = 0;
             for (int c = 0; c < a.n_copies; ++c) {
               CVB_PROF_WAIT(0, mbar_wait(&empty[stage], phase ^ 1, 100 + stage));
+              if ((a.dbg & 2) && (tile != (int)blockIdx.x)) {
+                mbar_arrive(&full[stage]);  // diagnostics: no data movement after the first tile
+              } else {
               mbar_expect_tx(&full[stage], 2 * a.cp_bytes[c]);
               uint8_t* sb_a = stage_base + stage * stage_bytes;
               const CUtensorMap* mapA = &a.tmA[a.cp_map[c]];
               tma_load_5d(mapA, &full[stage], sb_a, ck * BLOCK_K, w0 + a.cp_dw[c], h0 + a.cp_dh[c], b0, 0);
               if (!a.a_fused) tma_load_5d(mapA, &full[stage], sb_a + a.cp_lo_off[c], ck * BLOCK_K, w0 + a.cp_dw[c], h0 + a.cp_dh[c], b0, 1);
+              }
               if (++stage == STAGES) {
                 stage = 0;
                 phase ^= 1;
@@ -334,9 +369,33 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
       uint32_t hphase_b = 0;
       const int n_main = a.n_main;
       const uint32_t set_cols = (uint32_t)((n_main + 1) * BLOCK_N);
-      if (a.b_resident && (int)blockIdx.x < total_tiles) mbar_wait(bfull, 0, 250);
+      // shared-memory descriptor words (see make_kmajor_desc): low word = start address >> 4 | LBO 1 << 16; high word = SBO >> 4 |
+      // version 1 << 14 | swizzle layout << 29.  Everything below is kept in 16-byte units so that one 32-bit add moves a view.
+      constexpr int KSTEPS = BLOCK_K / 16;
+      constexpr uint32_t kLayout = SWZ == 128 ? 2u : (SWZ == 64 ? 4u : 6u);
+      constexpr uint32_t kHiStd = ((8u * SWZ) >> 4) | (1u << 14) | (kLayout << 29);
+      constexpr uint32_t kB16 = (uint32_t)B_BYTES >> 4;
+      const uint32_t ring16 = ((smem_u32(stage_base) & 0x3FFFFu) >> 4) | 0x10000u;
+      const uint32_t bres16 = ((smem_u32(b_res) & 0x3FFFFu) >> 4) | 0x10000u;
+      const uint32_t stage16 = (uint32_t)stage_bytes >> 4;
+      const bool pair = a.mma_pair != 0 && 2 * BLOCK_N <= 256, resident = a.b_resident != 0, kskip = a.kskip != 0;
+      const int ksteps = KSTEPS - a.kskip;
+      const int chunks = a.chunks;
+      // one tap with the loop-invariant mode flags resolved at compile time inside (the branches are uniform and cheap, the MMA
+      // sequences themselves are straight-line code)
+      auto tap = [&](uint32_t a16, uint32_t lo16, uint32_t a_hi, uint32_t b16, uint32_t d_base, uint32_t d_main, uint32_t d_cross,
+                     uint32_t nz, uint32_t main_nz) {
+        if (pair) {
+          if (!kskip) issue_tap<BLOCK_N, KSTEPS, true, false>(a16, lo16, a_hi, b16, kB16, kHiStd, d_base, d_main, d_cross, nz, main_nz, ksteps);
+          else issue_tap<BLOCK_N, KSTEPS, true, true>(a16, lo16, a_hi, b16, kB16, kHiStd, d_base, d_main, d_cross, nz, main_nz, ksteps);
+        } else {
+          if (!kskip) issue_tap<BLOCK_N, KSTEPS, false, false>(a16, lo16, a_hi, b16, kB16, kHiStd, d_base, d_main, d_cross, nz, main_nz, ksteps);
+          else issue_tap<BLOCK_N, KSTEPS, false, true>(a16, lo16, a_hi, b16, kB16, kHiStd, d_base, d_main, d_cross, nz, main_nz, ksteps);
+        }
+      };
+      if (resident && (int)blockIdx.x < total_tiles) mbar_wait(bfull, 0, 250);
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        CVB_PROF_WAIT(0, mbar_wait(&tempty[acc], acc_phase ^ 1, 200 + acc));
+        if (!(a.dbg & 8)) CVB_PROF_WAIT(0, mbar_wait(&tempty[acc], acc_phase ^ 1, 200 + acc));
         tc_fence_after();
         // The tensor core's fp32 adder rounds toward zero, so a long accumulation chain shrinks |sum| by ~1.6e-8 per
         // MMA (measured, tools/precision_probe.py).  Chains are kept short: the hi*hi products rotate over n_main
@@ -344,68 +403,33 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
         const uint32_t d_base = tmem_base + (uint32_t)acc * set_cols;
         const uint32_t d_cross = d_base + (uint32_t)(n_main * BLOCK_N);
         int r = 0;
+        int it = 0;
         if (a.halo) {
           // copy / tap mode: every tap is a row-shifted descriptor view of the copy in the current A slot; weight tiles come from
           // the resident slab or from their own ring.  The taps of a copy form an ny x nx grid (filter rows x filter columns) whose
-          // view offsets and weight indices are affine in (y, x), so the loop needs no per-tap table: the single issuing thread is
-          // instruction-latency bound (measured: ~8 cycles per dependent instruction) and must spend fewer cycles preparing an MMA
-          // than the tensor pipe needs to execute it (~50 cycles at N <= 64, tools/mma_bench.cu).
-          constexpr int KSTEPS = BLOCK_K / 16;
-          constexpr uint32_t kLayout = SWZ == 128 ? 2u : (SWZ == 64 ? 4u : 6u);
-          constexpr uint64_t kDescHiB = ((uint64_t)((8u * SWZ) >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)kLayout << 61);
-          const int ksteps = KSTEPS - a.kskip;
-          const uint32_t bres16 = (smem_u32(b_res) & 0x3FFFFu) >> 4;
-          const uint32_t wstep16 = (uint32_t)(a.chunks * 2 * B_BYTES) >> 4;  // resident slab: distance between consecutive weight taps
-          int it = 0;
-          for (int ck = 0; ck < a.chunks; ++ck) {
+          // view offsets and weight indices are affine in (y, x), so the loop needs no per-tap table.
+          const uint32_t wstep16 = (uint32_t)chunks * 2u * kB16;  // resident slab: distance between consecutive weight taps
+          for (int ck = 0; ck < chunks; ++ck) {
             for (int c = 0; c < a.n_copies; ++c) {
               const int ny = a.cp_ny[c], nx = a.cp_nx[c];
               const uint32_t row16 = a.cp_row16[c], lo16 = a.cp_lo_off[c] >> 4;
-              const int w0 = a.cp_w0[c], wy = a.cp_wy[c], wx = a.cp_wx[c];
-              const uint64_t desc_hi_a = ((uint64_t)(a.cp_sbo[c] >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)kLayout << 61);
-              CVB_PROF_WAIT(1, mbar_wait(&full[stage], phase, 300 + stage));
+              const uint32_t a_hi = (a.cp_sbo[c] >> 4) | (1u << 14) | (kLayout << 29);
+              const uint32_t wy16 = (uint32_t)a.cp_wy[c] * wstep16, wx16 = (uint32_t)a.cp_wx[c] * wstep16;
+              uint32_t brow16 = bres16 + (uint32_t)a.cp_w0[c] * wstep16 + (uint32_t)ck * 2u * kB16;
+              if (!(a.dbg & 8)) CVB_PROF_WAIT(1, mbar_wait(&full[stage], phase, 300 + stage));
               tc_fence_after();
-              const uint32_t sa16 = ((smem_u32(stage_base + stage * stage_bytes) & 0x3FFFFu) >> 4) | 0x10000u;
-              for (int y = 0; y < ny; ++y) {
-                for (int x = 0; x < nx; ++x) {
-                  uint32_t b16;
-                  if (a.b_resident) {
-                    b16 = bres16 + (uint32_t)(w0 + y * wy + x * wx) * wstep16 + (uint32_t)ck * ((2u * B_BYTES) >> 4);
-                  } else {
+              uint32_t arow16 = ring16 + (uint32_t)stage * stage16;
+              for (int y = 0; y < ny; ++y, arow16 += row16, brow16 += wy16) {
+                uint32_t a16 = arow16, bx16 = brow16;
+                for (int x = 0; x < nx; ++x, a16 += (SWZ >> 4), bx16 += wx16) {
+                  uint32_t b16 = bx16;
+                  if (!resident) {
                     CVB_PROF_WAIT(2, mbar_wait(&fullB[hb], hphase_b, 350 + hb));
                     tc_fence_after();
-                    b16 = bres16 + (uint32_t)hb * ((2u * B_BYTES) >> 4);
+                    b16 = bres16 + (uint32_t)hb * 2u * kB16;
                   }
-                  const uint64_t dah = desc_hi_a | (uint64_t)(sa16 + (uint32_t)y * row16 + (uint32_t)x * (SWZ >> 4));
-                  const uint64_t dal = dah + lo16;
-                  const uint64_t dbh = kDescHiB | (uint64_t)(b16 | 0x10000u);
-                  const uint64_t dbl = dbh + (B_BYTES >> 4);
-                  const uint32_t d_main = d_base + (uint32_t)(r * BLOCK_N);
-                  const bool first_main = it < n_main;
-                  if (a.mma_pair) {
-                    if constexpr (2 * BLOCK_N <= 256) {
-                      constexpr uint32_t IDESC2 = make_idesc_f16_f32(kTileM, 2 * BLOCK_N);
-#pragma unroll
-                      for (int k = 0; k < KSTEPS; ++k) {
-                        if (k < ksteps) {
-                          const uint64_t koff = (uint64_t)(k * 2);
-                          umma_f16(d_base, dah + koff, dbh + koff, IDESC2, (it | k) != 0 ? 1u : 0u);
-                          umma_f16(d_cross, dal + koff, dbh + koff, IDESC, 1u);
-                        }
-                      }
-                    }
-                  } else {
-#pragma unroll
-                    for (int k = 0; k < KSTEPS; ++k) {
-                      if (k < ksteps) {
-                        const uint64_t koff = (uint64_t)(k * 2);
-                        umma_f16(d_main, dah + koff, dbh + koff, IDESC, (first_main && k == 0) ? 0u : 1u);
-                        umma_f16(d_cross, dah + koff, dbl + koff, IDESC, (it | k) != 0 ? 1u : 0u);
-                        umma_f16(d_cross, dal + koff, dbh + koff, IDESC, 1u);
-                      }
-                    }
-                  }
-                  if (!a.b_resident) {
+                  tap(a16, lo16, a_hi, b16, d_base, d_base + (uint32_t)(r * BLOCK_N), d_cross, it != 0 ? 1u : 0u, it >= n_main ? 1u : 0u);
+                  if (!resident) {
                     umma_commit(&emptyB[hb]);
                     if (++hb == SB) {
                       hb = 0;
@@ -423,52 +447,32 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
               }
             }
           }
-        } else
-        for (int it = 0; it < k_iters; ++it) {
-          CVB_PROF_WAIT(1, mbar_wait(&full[stage], phase, 300 + stage));
-          tc_fence_after();
-          const uint32_t sa = smem_u32(stage_base + stage * stage_bytes);
-          const uint32_t sbw = a.b_resident ? smem_u32(b_res + it * 2 * B_BYTES) : sa + 2 * A_BYTES;
-          const uint64_t dah = make_kmajor_desc<SWZ>(sa);
-          const uint64_t dal = make_kmajor_desc<SWZ>(sa + a.a_lo_off);
-          const uint64_t dbh = make_kmajor_desc<SWZ>(sbw);
-          const uint64_t dbl = make_kmajor_desc<SWZ>(sbw + B_BYTES);
-          const uint32_t d_main = d_base + (uint32_t)(r * BLOCK_N);
-          const bool first_main = it < n_main;
-          if (a.mma_pair) {
-            // one accumulator chain (n_main == 1): the lo weight tile directly follows the hi tile in smem and the cross
-            // accumulator directly follows the main one in TMEM, so A_hi x [B_hi | B_lo] is ONE MMA of N = 2 * BLOCK_N --
-            // two MMAs and two A-operand reads per K step instead of three
-            if constexpr (2 * BLOCK_N <= 256) {
-              constexpr uint32_t IDESC2 = make_idesc_f16_f32(kTileM, 2 * BLOCK_N);
-#pragma unroll
-              for (int k = 0; k < BLOCK_K / 16; ++k) {
-                const uint64_t koff = (uint64_t)(k * 2);
-                umma_f16(d_base, dah + koff, dbh + koff, IDESC2, (it | k) != 0 ? 1u : 0u);
-                umma_f16(d_cross, dal + koff, dbh + koff, IDESC, 1u);
-              }
+        } else {
+          const uint32_t lo16 = a.a_lo_off >> 4;
+          uint32_t bres_it16 = bres16;
+          for (; it < k_iters; ++it, bres_it16 += 2u * kB16) {
+            if (!(a.dbg & 8)) CVB_PROF_WAIT(1, mbar_wait(&full[stage], phase, 300 + stage));
+            tc_fence_after();
+            const uint32_t a16 = ring16 + (uint32_t)stage * stage16;
+            const uint32_t b16 = resident ? bres_it16 : a16 + ((2u * A_BYTES) >> 4);
+            tap(a16, lo16, kHiStd, b16, d_base, d_base + (uint32_t)(r * BLOCK_N), d_cross, it != 0 ? 1u : 0u, it >= n_main ? 1u : 0u);
+            umma_commit(&empty[stage]);  // frees this smem stage once the MMAs above have read it
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
             }
-          } else {
-#pragma unroll
-            for (int k = 0; k < BLOCK_K / 16; ++k) {
-              const uint64_t koff = (uint64_t)(k * 2);  // 32 bytes per UMMA_K step, in 16-byte units
-              umma_f16(d_main, dah + koff, dbh + koff, IDESC, (first_main && k == 0) ? 0u : 1u);
-              umma_f16(d_cross, dah + koff, dbl + koff, IDESC, (it | k) != 0 ? 1u : 0u);
-              umma_f16(d_cross, dal + koff, dbh + koff, IDESC, 1u);
-            }
+            if (++r == n_main) r = 0;
           }
-          umma_commit(&empty[stage]);  // frees this smem stage once the MMAs above have read it
-          if (++stage == STAGES) {
-            stage = 0;
-            phase ^= 1;
-          }
-          if (++r == n_main) r = 0;
         }
         umma_commit(&tfull[acc]);  // accumulators complete -> epilogue
         if (++acc == a.nbuf) {
           acc = 0;
           acc_phase ^= 1;
         }
+      }
+      if (a.dbg & 8) {  // diagnostics: the issuer ran without waiting for anybody; drain the tensor pipe before the teardown
+        umma_commit(rfull);
+        mbar_wait(rfull, 0, 999);
       }
       if (prof_on) {  // MMA issuer: total cycles, waiting for a free accumulator, for activations, for weights
         a.prof[blockIdx.x * 16 + 4] = clock64() - prof_t0;
@@ -513,7 +517,7 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
       tma_load_5d(&a.tmR, rfull, res_stage + Cfg::OUT_PLANE_BYTES, c0, wt_ * a.TW, ht_ * a.TH, bt_ * a.NB, 1);
     };
     if (a.resid_tma && tid_e == 0 && (int)blockIdx.x < total_tiles) issue_residual(blockIdx.x, 0);
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = (a.dbg & 16) ? total_tiles : (int)blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int nt = tile % a.tiles_n;
       const int mt = tile / a.tiles_n;
       const int wt = mt % a.tiles_w;
@@ -587,6 +591,7 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
         ++gcount;
 #pragma unroll
         for (int sc = 0; sc < CW / SUB; ++sc) {
+          if (a.dbg & 4) break;  // diagnostics: no tcgen05.ld / math / staging
           const int col = col0 + sc * SUB;
           if (sc > 0) load_extras(sc);
           if constexpr (!OUT_F32) {
@@ -691,7 +696,7 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
         named_bar_sync(1, kEpiThreads);
         if (tid_e == 0) {
           const int c0 = n0 + g * OUT_GROUP_CH;
-          if (c0 < a.cout) {
+          if (c0 < a.cout && !(a.dbg & 1)) {
             tma_store_5d(&a.tmO, out_stage, c0, w0, h0, b0, 0);
             if constexpr (!OUT_F32) tma_store_5d(&a.tmO, out_stage + Cfg::OUT_PLANE_BYTES, c0, w0, h0, b0, 1);
           }
@@ -944,7 +949,9 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   bool use_halo = false;
   const int halo_req = d->halo != 0 ? d->halo : halo_env;  // per-plan request wins over the environment knob
   if (n_taps > 1 && d->dilation == 1 && halo_req != 0 && halo_req != -2 && d->halo != -1) {
-    const int mode = halo_req == 1 ? 1 : 2;
+    // measured (tools/conv_pipeline_profile.py, profiles/r02): the halo loader pays off where two CTAs share an SM (BLOCK_N <= 64: the
+    // second CTA's MMAs fill the tensor-pipe bubbles of the first); mode 1 (aligned copies) wins for 32-channel inputs, mode 2 above
+    const int mode = halo_req == 1 ? 1 : (halo_req == 2 ? 2 : (cin <= 32 && win == 0 ? 1 : 2));
     // copies: mode 2 = one per input map (box covers every tap of the map); mode 1 = one per (map, column offset)
     HaloCfg h;
     h.mode = mode;
@@ -1044,6 +1051,7 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
       for (int ctas = 2; ctas >= 1; --ctas) {
         if (ctas == 2 && !(bn <= 64 && two_ctas_on)) continue;
         if (ctas_env && ctas != ctas_env) continue;
+        if (!ctas_env && halo_req <= 0 && ctas == 1) continue;  // auto mode: only the two-CTAs-per-SM plans have been measured faster
         const int budget = ctas == 2 ? kSmemBudget2 : kSmemBudget;
         for (int bi = 0; bi < n_bk; ++bi) {
           const int bkh = bks[bi];
@@ -1412,6 +1420,10 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   p->smem = base + stages * (a_stage + (a.b_resident ? 0 : b_stage)) + (a.b_resident ? k_iters * b_stage : 0) + a.out_bufs * ke.out_stage_bytes;
   if (use_halo) p->smem = hc.smem;
   p->fn = ke.fn;
+  {
+    const char* e = getenv("CVB_DBG");  // diagnostics only (tools/conv_pipeline_profile.py): results are wrong when set
+    a.dbg = e ? atoi(e) : 0;
+  }
 
   static std::mutex mu;
   {

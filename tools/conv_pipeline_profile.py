@@ -17,7 +17,7 @@ flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
 
 
 def profile(cin, cout, k, s, H, W, B, env, label):
-    for kk in ('CVB_HALO', 'CVB_HALO_BK', 'CVB_HALO_CTAS', 'CVB_HALO_RES'):
+    for kk in ('CVB_HALO', 'CVB_HALO_BK', 'CVB_HALO_CTAS', 'CVB_HALO_RES', 'CVB_DBG'):
         os.environ.pop(kk, None)
     os.environ.update(env)
     g = torch.Generator().manual_seed(0)
@@ -47,6 +47,18 @@ def profile(cin, cout, k, s, H, W, B, env, label):
           f'MMA wait acc {c[5] / tot:5.1%} act {c[6] / tot:5.1%} wgt {c[7] / tot:5.1%} issue {(c[4] - c[5] - c[6] - c[7]) / tot:5.1%} | '
           f'epilogue wait acc {c[9] / max(c[8], 1):5.1%}', flush=True)
 
+
+if len(sys.argv) > 1 and sys.argv[1] == 'dbg':
+    # which concurrent activity slows the MMAs of the halo loader down?  (diagnostic switches, see ConvKArgs.dbg; results are wrong)
+    for L in [(64, 64, 3, 1, 80, 80, 64), (128, 128, 3, 1, 40, 40, 64)]:
+        print(f'layer cin {L[0]} cout {L[1]} k{L[2]} s{L[3]} {L[4]}x{L[5]} B{L[6]}')
+        for halo, ctas in (('0', '0'), ('2', '1'), ('2', '2')):
+            for dbg in (0, 7, 31):
+                env = {'CVB_HALO': halo, 'CVB_DBG': str(dbg)}
+                if ctas != '0':
+                    env['CVB_HALO_CTAS'] = ctas
+                profile(*L, env, f'  halo={halo} ctas={ctas} dbg={dbg}')
+    sys.exit(0)
 
 for L in LAYERS:
     print(f'layer cin {L[0]} cout {L[1]} k{L[2]} s{L[3]} {L[4]}x{L[5]} B{L[6]}')
