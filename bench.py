@@ -1,15 +1,19 @@
 #!/usr/bin/env python
-"""bench.py -- images/sec of the YOLOv5-s 640x640 bs64 forward hot path (backbone+neck+detect+decode+batched NMS).
+"""bench.py -- images/sec of the detector / segmenter forward hot path on B200.
 
   python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
   python bench.py --impl reference ...                      (CPU arm: the reference's algorithm on the host cores)
+  python bench.py --config {yolov5s,fcos,deeplab,yolox}     (default yolov5s = the headline, BASELINE.json configs[1]; the others are
+                                                             configs[4], configs[2] and the inference half of configs[3])
 
 One JSON line on rank 0.  `value`: inputs resident in HBM (device time, CUDA events, max over ranks).  `e2e`: the
 same metric through the public pipeline API with pinned HOST buffers (H2D of every step's frames and D2H of every
-step's detections inside the timed region).  `roofline`: the conv stack (the dominant kernel family), algorithmic
+step's results inside the timed region).  `roofline`: the conv stack (the dominant kernel family), algorithmic
 FLOPs / measured duration against the measured cuBLAS bf16 peak.  `cpu_baseline`: the oracle port on the host cores.
 """
 import argparse
+import glob
+import hashlib
 import json
 import os
 import subprocess
@@ -25,6 +29,48 @@ import torch  # noqa: E402
 
 METRIC = 'images/sec YOLOv5-s 640x640 bs64 forward (backbone+neck+detect+decode+NMS)'
 ALG_GFLOP_PER_IMG = 16.43359375  # 1051.75 GFLOP / 64 (2*M*N*K over the 60 convs)
+
+# secondary configurations (BASELINE.json configs[4], [2], inference half of [3]); per-GPU batch, input size, model builder
+SECONDARY = {
+    'fcos': dict(metric='images/sec FCOS ResNet50 800x800 bs32 forward (backbone+FPN+centerness head+decode+top-k+NMS)', batch=32, hw=(800, 800),
+                 workload='FCOS R50 800x800 forward+decode+NMS, bs32 per GPU (conf/coco_fcos.yml; BASELINE.json configs[4])',
+                 collective='one all_gather_into_tensor of [B,1000*6+1] f32 (scores, classes, boxes, count) per step'),
+    'deeplab': dict(metric='images/sec DeepLabv3+ ResNet50 1024x2048 bs16 forward (backbone+ASPP+decoder+upsample+argmax)', batch=16, hw=(1024, 2048),
+                    workload='DeepLabv3+ R50v1c 1024x2048 forward+argmax, bs16 per GPU (cityscapes_deeplabv3plus_r50.yml; BASELINE.json configs[2])',
+                    collective='one all_gather_into_tensor of the uint8 label maps [B,1024,2048] per step'),
+    'yolox': dict(metric='images/sec YOLOX-s 640x640 bs64 forward (backbone+neck+head+decode+batched_nms; inference half of configs[3])', batch=64,
+                  hw=(640, 640), workload='YOLOX-s 640x640 forward+decode+batched_nms, bs64 per GPU (inference half of BASELINE.json configs[3])',
+                  collective='one all_gather_into_tensor of [B,A,7] rows + counts per step'),
+}
+
+
+def csrc_sha1():
+    """Hash of the CUDA sources: stamps profile-derived numbers (roofline.traffic) with the kernel version they were captured on."""
+    h = hashlib.sha1()
+    for f in sorted(glob.glob(os.path.join(ROOT, 'cvpytorch_b200', 'csrc', '*'))):
+        if f.endswith(('.cu', '.cuh', '.h')):
+            h.update(open(f, 'rb').read())
+    return h.hexdigest()[:12]
+
+
+def measured_conv_traffic(batch):
+    """DRAM bytes of the conv launches of one step from the newest committed ncu launch list (tools/launch_summary.py).  Returned only
+    when it was captured on the CURRENT kernel sources (source_sha1 stamp) -- a stale capture reads as null, never as a number."""
+    best = None
+    for f in sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*', 'conv_traffic.json'))):
+        try:
+            tj = json.load(open(f))
+        except Exception:
+            continue
+        if int(tj.get('batch', 0)) == batch:
+            best = (f, tj)
+    if best is None:
+        return None, 'no capture'
+    f, tj = best
+    rel = os.path.relpath(f, ROOT)
+    if tj.get('source_sha1') != csrc_sha1():
+        return None, f'{rel} was captured on kernel sources {tj.get("source_sha1", "unstamped")}, current {csrc_sha1()}: stale, not reported'
+    return int(tj['conv_dram_bytes_per_step']), f'{rel} (ncu dram read+write of the conv launches of one step, kernel sources {tj["source_sha1"]})'
 
 
 def env_int(k, d):
@@ -160,25 +206,17 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
-def run_b200_arm(args):
+def _dist_setup():
     import torch.distributed as dist
-    from cvpytorch_b200 import _lib, synth
-    from cvpytorch_b200.runtime import InferencePipeline
     world = env_int('WORLD_SIZE', 1)
     rank = env_int('RANK', 0)
     local = env_int('LOCAL_RANK', 0)
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
+    from cvpytorch_b200.runtime import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local)  # before any pinned allocation: host buffers land on the GPU's NUMA node
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    B = args.batch
-    if args.scaling == 'strong':
-        # fixed global batch (args.batch images in total), contiguous shards per rank (global B=64 -> 8 img/GPU at W=8)
-        if args.batch % world != 0:
-            raise SystemExit('--scaling strong needs --batch divisible by the number of GPUs')
-        B = args.batch // world
-    model = synth.build_yolov5s(calibrated=True)
-    K, W = args.steps, max(3, args.warmup)
 
     def barrier():
         if world > 1:
@@ -192,22 +230,83 @@ def run_b200_arm(args):
             return float(t[0])
         return ms
 
+    return dist, world, rank, local, dev, numa, barrier, max_over_ranks
+
+
+def _peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        return {}
+
+
+def time_conv_stack(g, K2=10):
+    """The conv launches of one step replayed back to back as their OWN CUDA graph (same launch conditions as the timed graph replays,
+    no aux kernels in between), CUDA events around K2 replays -> ms per step of the conv stack for the roofline."""
+    from cvpytorch_b200 import ops
+    plans = [s[1] for s in g.steps if s[0] == 'conv']
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ops.run_plans(plans)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    cg = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(cg):
+        ops.run_plans(plans)
+    for _ in range(2):
+        cg.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K2):
+        cg.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / K2
+
+
+def per_layer_bound_ms(g, B, peak_tf, hbm):
+    bound_ms = 0.0
+    for (_n, cin, cout, k, s_, Ho, Wo) in g.layer_log:
+        fl = 2.0 * B * Ho * Wo * cout * cin * k * k
+        by = 4.0 * (B * (Ho * s_) * (Wo * s_) * cin + B * Ho * Wo * cout) + 4.0 * cout * cin * k * k
+        bound_ms += max(3 * fl / (peak_tf * 1e12), by / (hbm * 1e9)) * 1e3
+    return bound_ms
+
+
+def run_b200_arm(args):
+    from cvpytorch_b200 import _lib, synth
+    from cvpytorch_b200 import dist as cdist
+    from cvpytorch_b200 import ops
+    from cvpytorch_b200.runtime import InferencePipeline
+    dist, world, rank, local, dev, numa, barrier, max_over_ranks = _dist_setup()
+    B = args.batch
+    if args.scaling == 'strong':
+        # fixed global batch (args.batch images in total), contiguous shards per rank (SURVEY.md 8e: global B=64 -> 8 img/GPU at W=8)
+        if args.batch % world != 0:
+            raise SystemExit('--scaling strong needs --batch divisible by the number of GPUs')
+        B = args.batch // world
+    model = synth.build_yolov5s(calibrated=True)
+    K, W = args.steps, max(3, args.warmup)
+
     # ------------------------------------------------------------- device-resident arm ("value")
     G = model.build_graph(B, 640, 640, dev)
     g, ws = G['g'], G['ws']
-    x_dev = synthetic_frames(B, seed=1029 + rank).to(dev)
-    G['holder']['x'] = x_dev
-    M = ws.max_det
-    gathered = torch.empty((world * B, M * 7 + 1), dtype=torch.float32, device=dev)
-    from cvpytorch_b200 import dist as cdist
+    NBUF = 4  # distinct device-resident input batches, used round robin (every timed step reads a different 315 MB buffer)
+    x_devs = [synthetic_frames(B, seed=1029 + rank + 97 * i).to(dev) for i in range(NBUF)]
+    G['holder']['x'] = x_devs[0]
+    gathered = torch.empty((world, cdist.packed_len(B, ws.max_det)), dtype=torch.float32, device=dev)
 
-    conv_segments = []  # (start_idx, end_idx) of consecutive conv steps -> event pairs
+    def tail():  # the one collective of the path, from the buffer the NMS kernels wrote (no packing kernels)
+        if world > 1:
+            cdist.all_gather_packed(ws.packed, gathered)
+
     steps_list = g.steps
 
     def run_step(events=None):
-        """One pass of the hot path.  events: list to append (start, end) CUDA event pairs around the conv segments."""
+        """One eager pass of the hot path.  events: list to append (start, end) CUDA event pairs around the conv segments."""
         i, n = 0, len(steps_list)
-        from cvpytorch_b200 import ops
         while i < n:
             kind, obj = steps_list[i]
             if kind == 'conv':
@@ -225,22 +324,27 @@ def run_b200_arm(args):
             else:
                 obj()
                 i += 1
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, cdist.pack_detections(ws.det, ws.det_idx, ws.det_count))
+        tail()
 
+    graphs = []
     if args.graph:
-        g.capture()
+        if world > 1:
+            tail()  # NCCL communicator must exist before a capture can record the collective
+            torch.cuda.synchronize()
+        for i in range(NBUF):  # one captured step per input buffer (activation buffers are shared); the all-gather is part of the graph
+            G['holder']['x'] = x_devs[i]
+            g._graph = None
+            graphs.append(g.capture(warmup=2 if i == 0 else 1, tail=tail if world > 1 else None))
 
-    def do_step(events=None):
+    def do_step(i, events=None):
         if args.graph:
-            g.replay()
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, cdist.pack_detections(ws.det, ws.det_idx, ws.det_count))
+            graphs[i % NBUF].replay()
         else:
+            G['holder']['x'] = x_devs[i % NBUF]
             run_step(events)
 
-    for _ in range(W):
-        do_step()
+    for i in range(W):
+        do_step(i)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -250,8 +354,8 @@ def run_b200_arm(args):
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_start.record()
-    for _ in range(K):
-        do_step(ev if not args.graph else None)
+    for i in range(K):
+        do_step(i, ev if not args.graph else None)
     t_end.record()
     barrier()
     total_ms = max_over_ranks(t_start.elapsed_time(t_end))
@@ -260,25 +364,25 @@ def run_b200_arm(args):
     value = world * B * K / (total_ms / 1e3)
     launches = _lib.launch_count() - n0
     conv_ms = None
+    conv_how = 'CUDA events around the conv segments of the timed eager steps'
     if ev:
         conv_ms = sum(a.elapsed_time(b) for a, b in ev) / K
     if args.graph:
-        # graph replays do not pass through the C ABI: one eager pass (outside the timed region) counts the kernels of a step
-        # and times the conv segments with CUDA events for the roofline
-        K2 = min(K, 10)
+        # graph replays do not pass through the C ABI: one eager pass (outside the timed region) counts the kernels of a step; the conv
+        # stack is timed as its own CUDA graph (all conv launches of a step back to back, same launch conditions as the timed replays)
         n1 = _lib.launch_count()
-        ev2 = []
-        for _ in range(K2):
-            run_step(ev2)
+        G['holder']['x'] = x_devs[0]
+        run_step()
         torch.cuda.synchronize()
-        launches = (_lib.launch_count() - n1) // K2 * K
-        conv_ms = sum(a.elapsed_time(b) for a, b in ev2) / K2
+        launches = (_lib.launch_count() - n1) * K
+        conv_ms = time_conv_stack(g, K2=min(max(K, 5), 20))
+        conv_how = 'the %d conv launches of one step replayed as their own CUDA graph, CUDA events around %d replays' % (g.n_convs, min(max(K, 5), 20))
     overflow = int(ws.status[0].item())
 
     # ------------------------------------------------------------- end-to-end arm ("e2e"): pinned host in, host out
     def time_pipeline(pipe, hosts):
         for i in range(W):
-            pipe.result(pipe.submit(hosts[i % 2]))
+            pipe.result(pipe.submit(hosts[i % len(hosts)]))
         barrier()
         smp = ClockSampler(local)
         if rank == 0:
@@ -287,7 +391,7 @@ def run_b200_arm(args):
         e0.record()
         slots = []
         for i in range(K):
-            slots.append(pipe.submit(hosts[i % 2]))
+            slots.append(pipe.submit(hosts[i % len(hosts)]))
             if i >= 1:
                 pipe.result(slots[i - 1])  # host reads the previous step's detections while this one runs
         last = pipe.result(slots[-1])
@@ -297,8 +401,9 @@ def run_b200_arm(args):
         ms = max_over_ranks(e0.elapsed_time(e1))
         return ms, last, (smp.stop() if rank == 0 else None)
 
+    del graphs, x_devs
     pipe = InferencePipeline(model, B, 640, 640, dev, depth=2, use_cuda_graph=True)
-    hosts = [synthetic_frames(B, seed=2000 + rank * 16 + i).pin_memory() for i in range(2)]
+    hosts = [synthetic_frames(B, seed=2000 + rank * 16 + i).pin_memory() for i in range(3)]
     e2e_ms, last, e2e_clk = time_pipeline(pipe, hosts)
     e2e_value = world * B * K / (e2e_ms / 1e3)
     kept_mean = float(last[2].float().mean())
@@ -307,6 +412,7 @@ def run_b200_arm(args):
 
     # same end-to-end loop fed with camera-side uint8 HWC frames (ToTensor + Normalize fused into the stem loader)
     pipe8 = InferencePipeline(model, B, 640, 640, dev, depth=2, use_cuda_graph=True, uint8_frames=True)
+
     def frames_u8(seed):
         # uint8 frames whose transformed values follow the same N(0,1) statistics as the fp32 arm (quantised to 1/255, clipped to [0,1]):
         # the NMS workload is data dependent, uniform byte noise would time a different candidate regime
@@ -317,47 +423,32 @@ def run_b200_arm(args):
         u = ((z * sd + m) * 255.0).round_().clamp_(0, 255).to(torch.uint8)   # tensor (RGB, CHW) order
         return u.flip(1).permute(0, 2, 3, 1).contiguous().pin_memory()      # camera order: HWC, BGR
 
-    hosts8 = [frames_u8(3000 + rank * 16 + i) for i in range(2)]
+    hosts8 = [frames_u8(3000 + rank * 16 + i) for i in range(3)]
     e2e8_ms, _, e2e8_clk = time_pipeline(pipe8, hosts8)
     e2e8_value = world * B * K / (e2e8_ms / 1e3)
     h2d8, d2h8 = pipe8.h2d_bytes, pipe8.d2h_bytes
 
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
-        except Exception:
-            pass
+        peaks = _peaks()
         peak_tf = float(peaks.get('bf16_tflops_sustained', 1400.0))
         peak_src = 'measured bf16_tflops_sustained (MEASURED_PEAKS.json)' if peaks else 'fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)'
         roof = None
         if conv_ms:
             ach = ALG_GFLOP_PER_IMG * B / conv_ms  # GFLOP / ms == TFLOP/s
-            # DRAM bytes of the conv launches of one bs64 step, from the committed ncu launch list (tools/launch_summary.py)
-            traffic = None
-            try:
-                tj = json.load(open(os.path.join(ROOT, 'profiles', 'r01', 'conv_traffic.json')))
-                if int(tj.get('batch', 0)) == B:
-                    traffic = int(tj['conv_dram_bytes_per_step'])
-            except Exception:
-                pass
-            # per-layer conv roofline: sum_i max(3 * flops_i / P_tensor, bytes_i / BW_hbm) with the stored 4 B/element
+            traffic, traffic_src = measured_conv_traffic(B)
             hbm = float(peaks.get('hbm_gbs', 6500.0))
-            bound_ms = 0.0
-            for (_n, cin, cout, k, s_, Ho, Wo) in g.layer_log:
-                fl = 2.0 * B * Ho * Wo * cout * cin * k * k
-                by = 4.0 * (B * (Ho * s_) * (Wo * s_) * cin + B * Ho * Wo * cout) + 4.0 * cout * cin * k * k
-                bound_ms += max(3 * fl / (peak_tf * 1e12), by / (hbm * 1e9)) * 1e3
+            bound_ms = per_layer_bound_ms(g, B, peak_tf, hbm)
             roof = {'bound': 'tensor', 'achieved': round(ach, 2), 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': round(ach / peak_tf, 4),
-                    'traffic': traffic, 'kernel': 'conv_tc_kernel<*> (all %d fused conv launches of one step)' % g.n_convs,
-                    'conv_ms_per_step': round(conv_ms, 4), 'peak_source': peak_src,
-                    'algorithmic_bytes_per_step': int(7.80e9 * B / 64),
+                    'traffic': traffic, 'traffic_source': traffic_src,
+                    'kernel': 'conv_tc_kernel<*> (all %d fused conv launches of one step)' % g.n_convs,
+                    'conv_ms_per_step': round(conv_ms, 4), 'conv_ms_how': conv_how, 'peak_source': peak_src,
+                    'algorithmic_bytes_per_step': int(7.80e9 * B / 64), 'kernel_sources_sha1': csrc_sha1(),
                     'per_layer_roofline': {'bound_ms': round(bound_ms, 4), 'frac': round(bound_ms / conv_ms, 4),
                                            'definition': 'sum over the conv layers of max(3*flops/P_tensor, bytes/BW_hbm): three fp16 MMA products per '
                                                          'fp32 product, activations stored as fp16 hi+lo (4 B/element); P = %.1f TF/s, BW = %.1f GB/s' % (peak_tf, hbm)},
                     'note': 'algorithmic FLOPs 2*M*N*K of the fp32 reference graph (1051.75 GFLOP/bs64); the kernel issues 3 fp16 MMA products per fp32 '
                             'product (hi/lo split, fp32-equivalent accuracy), so frac <= 1/3 by construction; traffic = dram read+write of the conv '
-                            'launches of one step (ncu, profiles/r01); per-layer numbers in profiles/'}
+                            'launches of one step (ncu), reported only when captured on the current kernel sources; per-layer numbers in profiles/'}
         cpu_v, cores, spt, sample = cpu_reference_throughput(args.cpu_steps, 1) if (args.cpu_steps > 0 and world == 1) else (
             None, 0, 0, 'skipped (timed at N=1 only)' if world > 1 else 'skipped')
         line = {'metric': METRIC, 'value': round(value, 2), 'unit': 'images/sec', 'n_gpus': world, 'steps': K, 'warmup': W,
@@ -366,9 +457,10 @@ def run_b200_arm(args):
                 'config': {'workload': 'YOLOv5-s 640x640 forward+decode+NMS, bs64 per GPU (conf/coco_yolov5_s.yml; BASELINE.json configs[1])',
                            'global_batch': world * B, 'per_gpu_batch': B, 'parallelism': f'dp{world}', 'conf_thres': 0.001, 'iou_thres': 0.6,
                            'weights': 'synthetic, BN-calibrated (tests/golden/yolov5s_calib.npz)', 'cuda_graph': bool(args.graph),
-                           'l2': 'per-step inputs 315 MB and activations > 126 MB L2 (no explicit flush needed)',
-                           'collective': 'one all_gather_into_tensor of [B,300*7+1] f32 per step' if world > 1 else 'none (N=1)',
-                           'kept_per_image_mean': kept_mean, 'nms_capacity_overflow': overflow},
+                           'l2': 'per-step inputs 315 MB (%d device buffers used round robin) and activations > 126 MB L2 (no explicit flush needed)' % NBUF,
+                           'collective': ('one all_gather_into_tensor of the NMS result buffer [B*300*7+B] f32 per step, captured inside the CUDA graph'
+                                          if args.graph else 'one eager all_gather_into_tensor per step') if world > 1 else 'none (N=1)',
+                           'numa_node': numa, 'kept_per_image_mean': kept_mean, 'nms_capacity_overflow': overflow},
                 'gpu_launches': int(launches),
                 'e2e': {'value': round(e2e_value, 2), 'unit': 'images/sec', 'h2d_bytes_per_step': h2d_f32, 'd2h_bytes_per_step': d2h_f32,
                         'ms_per_step': round(e2e_ms / K, 4), 'sm_mhz': (e2e_clk or {}).get('sm_mhz'),
@@ -378,11 +470,213 @@ def run_b200_arm(args):
                                      'api': 'InferencePipeline(uint8_frames=True): pinned host uint8 HWC frames in (ToTensor + Normalize fused into the stem '
                                             'loader, cvb_stem_s2d_u8), host detections out; an extension beyond the reference input contract'},
                 'clocks': clocks, 'roofline': roof,
-                'cpu_baseline': {'value': round(cpu_v, 3) if cpu_v else None, 'unit': 'images/sec', 'cores': cores, 'kind': 'port', 'sample': sample}}
+                'cpu_baseline': {'value': round(cpu_v, 3) if cpu_v else None, 'unit': 'images/sec', 'cores': cores, 'kind': 'port', 'sample': sample,
+                                 'note': 'oracle port with an early-exit numpy NMS: faster than the stock reference path (the reference\'s own '
+                                         'non_max_suppression is ~10x slower per image on CPU), i.e. generous to the CPU'}}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------ secondary configurations
+def _secondary_model(name):
+    from cvpytorch_b200 import synth
+    return {'fcos': synth.build_fcos, 'deeplab': synth.build_deeplab, 'yolox': synth.build_yolox}[name](True)
+
+
+def _secondary_cpu(name, steps, batch=1):
+    """Oracle port of the configuration on the host cores, bounded sample (bs1 steps)."""
+    from cvpytorch_b200 import synth
+    cfg = SECONDARY[name]
+    H, W = cfg['hw']
+    torch.manual_seed(1029)
+    x = torch.randn(batch, 3, H, W)
+    if name == 'fcos':
+        from oracle import fcos_oracle as O
+        sd = synth.fcos_state_dict(True)
+
+        def step():
+            _, _, cls, cnt, reg = O.forward(x, sd)
+            O.fcos_detect(cls, cnt, reg)
+    elif name == 'deeplab':
+        from oracle import deeplab_oracle as O
+        sd = synth.deeplab_state_dict(True)
+
+        def step():
+            O.forward(x, sd)
+    else:
+        from oracle import yolox_oracle as O
+        sd = synth.yolox_state_dict(True)
+
+        def step():
+            O.post_process(O.forward(x, sd))
+    small = x[:, :, :H // 4, :W // 4].contiguous()
+    probe_fn = {'fcos': lambda: __import__('oracle.fcos_oracle', fromlist=['x']).forward(small, sd),
+                'deeplab': lambda: __import__('oracle.deeplab_oracle', fromlist=['x']).forward(small, sd),
+                'yolox': lambda: __import__('oracle.yolox_oracle', fromlist=['x']).forward(small, sd)}[name]
+    cores = pick_cpu_threads(probe_fn)
+    torch.set_num_threads(cores)
+    step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, cores, dt / steps, f'{steps} steps x bs{batch} {H}x{W} forward+post-process, torch {torch.__version__} fp32, {cores} threads'
+
+
+def run_secondary_arm(args):
+    from cvpytorch_b200 import _lib
+    from cvpytorch_b200 import dist as cdist
+    name = args.config
+    cfg = SECONDARY[name]
+    dist, world, rank, local, dev, numa, barrier, max_over_ranks = _dist_setup()
+    B = args.batch or cfg['batch']
+    H, Wd = cfg['hw']
+    model = _secondary_model(name)
+    K, W = args.steps, max(3, args.warmup)
+    G = model.build_graph(B, H, Wd, dev)
+    g = G['g']
+    NBUF = 2
+    x_devs = [torch.randn(B, 3, H, Wd, generator=torch.Generator().manual_seed(1029 + rank + 97 * i)).to(dev) for i in range(NBUF)]
+    G['holder']['x'] = x_devs[0]
+
+    # results of one step + the collective of the configuration (dist.py helpers; eager NCCL call after the replay)
+    def results():
+        if name == 'fcos':
+            ws = G['ws']
+            return ws.out_scores, ws.out_classes, ws.out_boxes, ws.out_count
+        if name == 'deeplab':
+            return (G['labels'],)
+        return G['ws'].det, G['ws'].count
+
+    def gather():
+        if world == 1:
+            return
+        if name == 'fcos':
+            sc, cl, bx, cnt = results()
+            cdist.all_gather_fcos_detections(sc, cl, bx, cnt)
+        elif name == 'deeplab':
+            cdist.all_gather_label_maps(G['labels'], check=False)
+        else:
+            det, cnt = results()
+            out = torch.empty((world,) + tuple(det.shape), dtype=det.dtype, device=dev)
+            dist.all_gather_into_tensor(out, det.contiguous())
+            outc = torch.empty((world,) + tuple(cnt.shape), dtype=cnt.dtype, device=dev)
+            dist.all_gather_into_tensor(outc, cnt.contiguous())
+
+    graphs = []
+    for i in range(NBUF):
+        G['holder']['x'] = x_devs[i]
+        g._graph = None
+        graphs.append(g.capture(warmup=2 if i == 0 else 1))
+
+    def do_step(i):
+        graphs[i % NBUF].replay()
+        gather()
+
+    for i in range(W):
+        do_step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for i in range(K):
+        do_step(i)
+    t1.record()
+    barrier()
+    total_ms = max_over_ranks(t0.elapsed_time(t1))
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * K / (total_ms / 1e3)
+    n1 = _lib.launch_count()
+    g.run()
+    torch.cuda.synchronize()
+    launches = (_lib.launch_count() - n1) * K
+    conv_ms = time_conv_stack(g, K2=min(max(K, 3), 10))
+    status = int(G['ws'].status[0].item()) if name == 'fcos' else 0
+
+    # ---- end to end: pinned host fp32 frames -> device -> graph -> (gather) -> results to pinned host, every step
+    hosts = [torch.randn(B, 3, H, Wd, generator=torch.Generator().manual_seed(2000 + rank * 16 + i)).pin_memory() for i in range(2)]
+    x_in = x_devs[0]
+    G['holder']['x'] = x_in
+
+    def result_tensors():
+        r = results()
+        if name == 'deeplab':  # class ids < 256: the label maps travel as uint8 (2 MB / image instead of 16 MB), widened on the host if needed
+            return (r[0].to(torch.uint8),)
+        return r
+    outs_host = [torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in result_tensors()]
+    h2d = x_in.numel() * 4
+    d2h = sum(t.numel() * t.element_size() for t in outs_host)
+
+    def e2e_step(i):
+        x_in.copy_(hosts[i % 2], non_blocking=True)
+        graphs[0].replay()
+        gather()
+        for h, t in zip(outs_host, result_tensors()):
+            h.copy_(t, non_blocking=True)
+
+    for i in range(W):
+        e2e_step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * B * K / (e2e_ms / 1e3)
+
+    if rank == 0:
+        peaks = _peaks()
+        peak_tf = float(peaks.get('bf16_tflops_sustained', 1400.0))
+        hbm = float(peaks.get('hbm_gbs', 6500.0))
+        ach = g.flops / conv_ms / 1e9  # FLOP / ms / 1e9 == TFLOP/s
+        bound_ms = per_layer_bound_ms(g, B, peak_tf, hbm)
+        roof = {'bound': 'tensor', 'achieved': round(ach, 2), 'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': round(ach / peak_tf, 4), 'traffic': None,
+                'kernel': 'conv_tc_kernel<*> (all %d tensor-core conv launches of one step)' % g.n_convs, 'conv_ms_per_step': round(conv_ms, 4),
+                'algorithmic_gflop_per_image': round(g.flops / B / 1e9, 3), 'kernel_sources_sha1': csrc_sha1(),
+                'per_layer_roofline': {'bound_ms': round(bound_ms, 4), 'frac': round(bound_ms / conv_ms, 4)},
+                'note': 'algorithmic 2*M*N*K of the tensor-core convs (depthwise / GroupNorm / pooling / decode / NMS kernels excluded); three fp16 '
+                        'MMA products per fp32 product, so frac <= 1/3 by construction'}
+        cpu_v, cores, spt, sample = _secondary_cpu(name, args.cpu_steps) if (args.cpu_steps > 0 and world == 1) else (
+            None, 0, 0, 'skipped (timed at N=1 only)' if world > 1 else 'skipped')
+        line = {'metric': cfg['metric'], 'value': round(value, 2), 'unit': 'images/sec', 'n_gpus': world, 'steps': K, 'warmup': W,
+                'ms_per_step': round(total_ms / K, 4), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'fp16x3-split (fp32-equivalent, fp32 accumulate)', 'data': 'synthetic',
+                'config': {'workload': cfg['workload'], 'global_batch': world * B, 'per_gpu_batch': B, 'parallelism': f'dp{world}',
+                           'weights': 'synthetic, calibrated (tests/golden/*_calib.npz)', 'cuda_graph': True,
+                           'l2': 'inputs and activations of one step exceed the 126 MB L2 (no explicit flush needed)',
+                           'collective': cfg['collective'] if world > 1 else 'none (N=1)', 'numa_node': numa, 'nms_capacity_overflow': status},
+                'gpu_launches': int(launches),
+                'e2e': {'value': round(e2e_value, 2), 'unit': 'images/sec', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                        'ms_per_step': round(e2e_ms / K, 4),
+                        'api': 'pinned host fp32 frames -> model graph (== model.predict) -> results copied to pinned host memory, every step'},
+                'clocks': clocks, 'roofline': roof,
+                'cpu_baseline': {'value': round(cpu_v, 4) if cpu_v else None, 'unit': 'images/sec', 'cores': cores, 'kind': 'port', 'sample': sample}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_secondary_reference_arm(args):
+    if env_int('RANK', 0) != 0:
+        return
+    name = args.config
+    cfg = SECONDARY[name]
+    steps = max(1, args.steps)
+    v, cores, spt, sample = _secondary_cpu(name, steps)
+    line = {'impl': 'reference', 'metric': cfg['metric'], 'value': round(v, 4), 'unit': 'images/sec', 'n_gpus': args.gpus, 'steps': steps, 'warmup': 1,
+            'ms_per_step': round(spt * 1e3, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': cfg['workload'] + ', CPU sample bs1 per step', 'parallelism': 'cpu'},
+            'cpu_baseline': {'value': round(v, 4), 'unit': 'images/sec', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': round(v, 4), 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
 
 
 def main():
@@ -391,18 +685,30 @@ def main():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=64, help='images per GPU per step (BASELINE: 64)')
+    ap.add_argument('--config', default='yolov5s', choices=['yolov5s'] + sorted(SECONDARY),
+                    help='yolov5s (default) = the headline, BASELINE.json configs[1]; fcos / deeplab / yolox = the secondary configurations')
+    ap.add_argument('--batch', type=int, default=0, help='images per GPU per step (default: the configuration\'s own, 64 for yolov5s)')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'], help='weak: --batch images per GPU (default); strong: --batch images in total')
-    ap.add_argument('--graph', type=int, default=1, help='1 (default): the timed steps replay one captured CUDA graph (the conv-stack time for the roofline comes '
-                    'from an extra eager pass); 0: eager launches with per-conv-segment events inside the timed region')
-    ap.add_argument('--cpu-steps', type=int, default=3, help='bs8 CPU baseline steps timed on rank 0 (0 = skip)')
+    ap.add_argument('--graph', type=int, default=1, help='1 (default): the timed steps replay captured CUDA graphs (the conv-stack time for the roofline '
+                    'comes from the conv launches replayed as their own graph); 0: eager launches with per-conv-segment events inside the timed region')
+    ap.add_argument('--cpu-steps', type=int, default=3, help='CPU baseline steps timed on rank 0 (0 = skip)')
     args = ap.parse_args()
-    if args.impl == 'reference':
-        run_reference_arm(args)
+    if args.config == 'yolov5s':
+        args.batch = args.batch or 64
+        if args.impl == 'reference':
+            return run_reference_arm(args)
     else:
-        if not torch.cuda.is_available():
-            raise SystemExit('bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)')
+        if args.impl == 'reference':
+            return run_secondary_reference_arm(args)
+        if args.steps == 50:
+            args.steps = 10  # the secondary steps are 10-50 ms each
+        args.cpu_steps = min(args.cpu_steps, 2)
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)')
+    if args.config == 'yolov5s':
         run_b200_arm(args)
+    else:
+        run_secondary_arm(args)
 
 
 if __name__ == '__main__':

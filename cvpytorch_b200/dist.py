@@ -34,6 +34,27 @@ def unpack_detections(packed, max_det):
     return det, idx, cnt
 
 
+def packed_len(B, max_det):
+    """Length (floats) of the flat per-rank result buffer of ops.NmsWorkspace: [det B*M*6 | det_idx B*M | det_count B]."""
+    return B * max_det * 7 + B
+
+
+def all_gather_packed(packed, out, group=None):
+    """The one collective of the data path: `packed` = ops.NmsWorkspace.packed of this rank (the NMS kernels wrote it, nothing is
+    repacked), `out` = preallocated [world, len(packed)] on the same device.  Stream-ordered and CUDA-graph capturable (NCCL)."""
+    dist.all_gather_into_tensor(out.view(-1), packed, group=group)
+    return out
+
+
+def unpack_gathered(out, B, max_det):
+    """[world, B*M*7+B] (device or pinned host) -> (det [world*B,M,6] f32, det_idx [world*B,M] i32, det_count [world*B] i32), rank-major."""
+    W, M = out.shape[0], max_det
+    det = out[:, :B * M * 6].reshape(W * B, M, 6)
+    idx = out[:, B * M * 6:B * M * 7].contiguous().view(torch.int32).reshape(W * B, M)
+    cnt = out[:, B * M * 7:].contiguous().view(torch.int32).reshape(W * B)
+    return det, idx, cnt
+
+
 def all_gather_detections(det, det_idx, det_count, group=None, out=None):
     """Single collective: every rank ends up with the detections of the whole global batch (rank-major order).
     All ranks must hold the same local batch size (pad the last shard)."""
@@ -60,11 +81,11 @@ def all_gather_fcos_detections(scores, classes, boxes, counts, group=None):
             out[:, 6 * K:].contiguous().view(torch.int32).reshape(G))
 
 
-def all_gather_label_maps(labels, group=None):
+def all_gather_label_maps(labels, group=None, check=True):
     """Segmentation (BASELINE.json config 3): int64 label maps [B,H,W] (EncoderDecoder 'val' output) travel as uint8
     (class ids < 256; 2 MB per 1024x2048 image instead of 16 MB) in one all_gather_into_tensor and are widened to int64 again
     for API parity with encoder_decoder.py:133."""
-    if int(labels.numel()) and (int(labels.max()) > 255 or int(labels.min()) < 0):
+    if check and int(labels.numel()) and (int(labels.max()) > 255 or int(labels.min()) < 0):  # check=False: no host sync (argmax of <= 256 classes)
         raise ValueError('label ids must fit uint8 for the packed gather')
     u8 = labels.to(torch.uint8).contiguous()
     world = dist.get_world_size(group)

@@ -121,18 +121,24 @@ class GraphBuilder:
                 obj()
                 i += 1
 
-    def capture(self, warmup=2):
-        """Captures run() into a CUDA graph (kernels are launched on torch's current stream by the C ABI)."""
+    def capture(self, warmup=2, tail=None):
+        """Captures run() into a CUDA graph (kernels are launched on torch's current stream by the C ABI).
+        tail: optional callable appended to the captured step (e.g. the NCCL all-gather of the results: SURVEY.md 5 wants the
+        collective inside the graph, not an eager launch after every replay)."""
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(warmup):
                 self.run()
+                if tail is not None:
+                    tail()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self.run()
+            if tail is not None:
+                tail()
         self._graph = g
         return g
 

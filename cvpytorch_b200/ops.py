@@ -269,9 +269,13 @@ class NmsWorkspace:
         off = (-self.ws.data_ptr()) % 256
         self.ws_ptr = self.ws.data_ptr() + off
         self.ws_bytes = nbytes
-        self.det = torch.zeros((B, max_det, 6), dtype=torch.float32, device=device)
-        self.det_idx = torch.zeros((B, max_det), dtype=torch.int32, device=device)
-        self.det_count = torch.zeros((B,), dtype=torch.int32, device=device)
+        # ONE flat result buffer [det B*M*6 f32 | det_idx B*M i32 | det_count B i32]: the three outputs are views of it, so the NMS
+        # kernels write the wire format of the multi-GPU all-gather directly (dist.all_gather_packed; no packing kernels per step)
+        M = max_det
+        self.packed = torch.zeros((B * M * 7 + B,), dtype=torch.float32, device=device)
+        self.det = self.packed[:B * M * 6].view(B, M, 6)
+        self.det_idx = self.packed[B * M * 6:B * M * 7].view(torch.int32).view(B, M)
+        self.det_count = self.packed[B * M * 7:].view(torch.int32)
         self.status = torch.zeros((4,), dtype=torch.int32, device=device)
 
 

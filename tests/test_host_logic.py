@@ -152,6 +152,46 @@ def test_all_gather_detections_gloo_world2():
         assert int(i[3, 0]) == 1000 and int(i[0, 6]) == 6
 
 
+def _gloo_worker_packed(rank, world, port, q):
+    """the wire format the NMS kernels write (ops.NmsWorkspace.packed: [det B*M*6 | idx B*M | count B], views of ONE flat buffer)"""
+    import torch.distributed as dist
+    from cvpytorch_b200.dist import all_gather_packed, packed_len, unpack_gathered
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    B, M = 3, 7
+    packed = torch.zeros(packed_len(B, M))
+    det = packed[:B * M * 6].view(B, M, 6)
+    idx = packed[B * M * 6:B * M * 7].view(torch.int32).view(B, M)
+    cnt = packed[B * M * 7:].view(torch.int32)
+    det.copy_(torch.full((B, M, 6), float(rank)) + torch.arange(B).view(B, 1, 1))
+    idx.copy_(torch.arange(B * M, dtype=torch.int32).view(B, M) + 1000 * rank)
+    cnt.copy_(torch.tensor([rank + 1, 0, M], dtype=torch.int32))
+    out = torch.empty((world, packed.numel()))
+    all_gather_packed(packed, out)
+    d, i, c = unpack_gathered(out, B, M)
+    q.put((rank, d.clone(), i.clone(), c.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_all_gather_packed_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker_packed, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(2)]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    for rank, d, i, c in res:
+        assert d.shape == (6, 7, 6) and i.shape == (6, 7) and c.tolist() == [1, 0, 7, 2, 0, 7]
+        assert float(d[0, 0, 0]) == 0.0 and float(d[3, 0, 0]) == 1.0 and float(d[5, 0, 0]) == 3.0
+        assert int(i[3, 0]) == 1000 and int(i[0, 6]) == 6
+
+
 def _gloo_worker_fcos_seg(rank, world, port, q):
     import torch.distributed as dist
     from cvpytorch_b200.dist import all_gather_fcos_detections, all_gather_label_maps

@@ -1,6 +1,17 @@
 """Summarise an `ncu --csv` launch list (gpu__time_duration + dram bytes): per-kernel totals of ONE step of bench.py.
 Usage: python tools/launch_summary.py <csv> [first_kernel_substring=stem_s2d] [out.json batch]"""
-import csv, collections, json, sys
+import csv, collections, glob, hashlib, json, os, sys
+
+
+def _csrc_sha1():
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    h = hashlib.sha1()
+    for f in sorted(glob.glob(os.path.join(root, 'cvpytorch_b200', 'csrc', '*'))):
+        if f.endswith(('.cu', '.cuh', '.h')):
+            h.update(open(f, 'rb').read())
+    return h.hexdigest()[:12]
+
+
 path = sys.argv[1]
 anchor = sys.argv[2] if len(sys.argv) > 2 else 'stem_s2d'
 with open(path) as f:
@@ -34,5 +45,5 @@ if len(sys.argv) > 4:
     json.dump({'batch': int(sys.argv[4]), 'conv_dram_bytes_per_step': int(conv_b), 'conv_us_per_step_under_ncu': round(conv_t, 1),
                'step_us_under_ncu': round(tot, 1), 'kernels': {n: {'launches': a[0], 'us': round(a[1], 1), 'dram_read_MB': round(a[2] / 1e6, 1),
                                                                     'dram_write_MB': round(a[3] / 1e6, 1)} for n, a in agg.items()},
-               'source': path.split('/')[-1], 'how': 'ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none; one step of bench.py'},
+               'source': path.split('/')[-1], 'source_sha1': _csrc_sha1(), 'how': 'ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none; one step of bench.py'},
               open(sys.argv[3], 'w'), indent=1)
