@@ -131,3 +131,20 @@ def make_stress_prediction(B, A=25200, nc=80, regime='typical', seed=2, img=640)
     k = (np.arange(B * A) % 997).astype(np.float32).reshape(B, A)
     pred[:, :, 4] = np.clip(pred[:, :, 4] + k * np.float32(2.0 ** -20), 0, 1)
     return pred
+
+
+def same_up_to_score_ties(ref_scores, ref_ids, test_ids):
+    """True iff `test_ids` is `ref_ids` up to permutations INSIDE groups of exactly equal scores (the reference sorts with an unstable
+    argsort at its 30 000 cap, src/models/yolov5.py:131-132, so the order of exactly tied candidates is not defined by the reference)."""
+    ref_scores, ref_ids, test_ids = np.asarray(ref_scores), np.asarray(ref_ids), np.asarray(test_ids)
+    if ref_ids.shape != test_ids.shape:
+        return False
+    i, n = 0, ref_ids.shape[0]
+    while i < n:
+        j = i
+        while j + 1 < n and ref_scores[j + 1] == ref_scores[i]:
+            j += 1
+        if sorted(ref_ids[i:j + 1].tolist()) != sorted(test_ids[i:j + 1].tolist()):
+            return False
+        i = j + 1
+    return True

@@ -258,3 +258,55 @@ def test_full_size_bs64_properties(model):
     dp, ip, cp = model.predict(x[perm.cuda()].contiguous())
     torch.cuda.synchronize()
     assert torch.equal(cp.cpu(), cnt.cpu()[perm]) and torch.equal(ip.cpu(), idx.cpu()[perm]) and torch.equal(dp.cpu(), det.cpu()[perm])
+
+
+def test_headline_batch_vs_reference_rows_and_end_to_end_agreement(model, sd):
+    """The 8 reference-golden images of the headline batch (tests/golden/yolov5s_batch640.npz, incl. the exact-score-tie images 3 and 5):
+    (a) the CUDA NMS over the reference's candidates (the oracle's z when this host reproduces the build container's arithmetic, which
+        the fixture's z_sub decides) keeps the reference's SET, in the reference's ORDER up to exact-score ties, with bit-identical rows;
+    (b) end to end (B200 conv stack + decode + NMS vs the reference pipeline) the kept candidate ids are compared and the agreement is
+        RECORDED (printed, and asserted against the level measured in round 2) instead of a loose bound;
+    (c) the same 8 images inside the full bs64 batch give the same rows as the 8-image batch (two in-batch images vs the oracle)."""
+    from cvpytorch_b200 import models as M
+    from oracle import nms_oracle as NO
+    from oracle import yolov5_oracle as YO
+    g = np.load(os.path.join(GOLD, 'yolov5s_batch640.npz'))
+    torch.manual_seed(1029)
+    x64 = torch.randn(64, 3, 640, 640)
+    x = x64[:8].contiguous()
+    zo, _ = YO.forward(x, sd)
+    assert YO.rel_err(zo[:, ::16], torch.from_numpy(g['z_sub'])) < 1e-5
+    ref_arith = np.array_equal(zo[:, ::16].numpy(), g['z_sub'])
+    dets, idxs = M.non_max_suppression(zo.cuda(), 0.001, 0.6, multi_label=True, return_indices=True)
+    ores = NO.non_max_suppression(zo.numpy(), 0.001, 0.6, multi_label=True)
+    for i in range(8):
+        ci = idxs[i].cpu().numpy().astype(np.int64)
+        assert np.array_equal(ci, ores[i][1]) and np.array_equal(dets[i].cpu().numpy(), ores[i][0]), i   # bit-exact vs the oracle
+        if ref_arith:
+            rd, ri = g[f'det_{i}'], g[f'idx_{i}']
+            assert set(ci.tolist()) == set(ri.tolist()), i
+            assert NO.same_up_to_score_ties(rd[:, 4], ri, ci), i
+            assert np.array_equal(rd[np.argsort(ri, kind='stable')], dets[i].cpu().numpy()[np.argsort(ci, kind='stable')]), i
+    # (b) end to end
+    det, idx, cnt = [t.clone() for t in model.predict(x.cuda())]
+    torch.cuda.synchronize()
+    z = model._graph_for(x.cuda())['z'].cpu()
+    print('end-to-end decoded z rel err vs oracle:', _rel(z, zo))
+    assert _rel(z, zo) < TOL
+    common = []
+    for i in range(8):
+        k = int(cnt[i])
+        mine = set(idx[i, :k].cpu().numpy().astype(np.int64).tolist())
+        common.append(len(mine & set(g[f'idx_{i}'].tolist())))
+    print('end-to-end kept candidate ids in common with the REFERENCE pipeline, per image (of 300):', common)
+    assert min(common) >= 240 and sum(common) >= 8 * 270, common
+    # (c) two of these images inside the BASELINE-shaped bs64 batch equal the same image in the 8-image batch, and the oracle NMS over
+    #     the batch's own z reproduces the rows (bit-exact on identical candidates)
+    d64, i64, c64 = model.predict(x64.cuda())
+    torch.cuda.synchronize()
+    z64 = model._graph_for(x64.cuda())['z']
+    for b in (3, 5):
+        assert int(c64[b]) == int(cnt[b]) and torch.equal(i64[b], idx[b]) and torch.equal(d64[b], det[b])
+        od, oi = NO.non_max_suppression(z64[b:b + 1].cpu().numpy(), 0.001, 0.6, multi_label=True)[0]
+        k = int(c64[b])
+        assert np.array_equal(i64[b, :k].cpu().numpy().astype(np.int64), oi) and np.array_equal(d64[b, :k].cpu().numpy(), od)
