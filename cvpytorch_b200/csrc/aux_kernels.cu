@@ -1311,3 +1311,144 @@ extern "C" int cvb_confusion_matrix(const int64_t* gt, const int64_t* pred, int6
   count_launch();
   return CVB_OK;
 }
+
+// ------------------------------------------------------------------------------------------------ input side: letterbox
+// Resize(keep_ratio=True) of the reference (src/data/transforms/det_transforms.py:162-198): cv2.resize(INTER_LINEAR) of the uint8 HWC
+// frame to (oh, ow), then cv2.copyMakeBorder with a constant fill.  OpenCV's 8-bit bilinear kernel, restated (imgproc/resize.cpp):
+// per axis fx = (float)((d + 0.5) * scale - 0.5) with scale = 1 / (dst / src) in double, s = floor(fx), fx -= s; columns zero fx at the
+// borders, rows clip the index; 11-bit coefficients = round-to-nearest-even of (1 - fx) * 2048 and fx * 2048 in float; horizontal pass in
+// int32, vertical pass (((b0 * (S0 >> 4)) >> 16) + ((b1 * (S1 >> 4)) >> 16) + 2) >> 2.  Bit-identical to cv2 4.x (oracle/io_oracle.py,
+// tests/golden/letterbox.npz).  geom[b] = (h, w, oh, ow, top, left); one thread per output pixel.
+namespace cvb {
+__device__ __forceinline__ void lb_axis(int d, int dst, int src, bool zero_at_border, int* s0, int* s1, int* c0, int* c1) {
+  const double scale = 1.0 / ((double)dst / (double)src);
+  float f = (float)(((double)d + 0.5) * scale - 0.5);
+  int s = (int)floorf(f);
+  f -= (float)s;
+  if (zero_at_border) {
+    if (s < 0) {
+      f = 0.0f;
+      s = 0;
+    }
+    if (s >= src - 1) {
+      f = 0.0f;
+      s = src - 1;
+    }
+    *s0 = s;
+    *s1 = min(s + 1, src - 1);
+  } else {
+    *s0 = min(max(s, 0), src - 1);
+    *s1 = min(max(s + 1, 0), src - 1);
+  }
+  *c0 = __float2int_rn(__fmul_rn(__fsub_rn(1.0f, f), 2048.0f));
+  *c1 = __float2int_rn(__fmul_rn(f, 2048.0f));
+}
+
+__global__ void __launch_bounds__(256) letterbox_u8_kernel(const uint8_t* const* __restrict__ src, const int* __restrict__ geom, int B, int OH,
+                                                           int OW, int f0, int f1, int f2, uint8_t* __restrict__ dst) {
+  const long long n = (long long)B * OH * OW;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % OW);
+    const long long t = i / OW;
+    const int y = (int)(t % OH);
+    const int b = (int)(t / OH);
+    const int* g = geom + b * 6;
+    const int h = g[0], w = g[1], oh = g[2], ow = g[3], top = g[4], left = g[5];
+    const int dy = y - top, dx = x - left;
+    int r0 = f0, r1 = f1, r2 = f2;
+    if (dy >= 0 && dy < oh && dx >= 0 && dx < ow) {
+      const uint8_t* s = src[b];
+      if (h == oh && w == ow) {  // the reference skips cv2.resize when the size is unchanged
+        const uint8_t* p = s + ((size_t)dy * w + dx) * 3;
+        r0 = p[0];
+        r1 = p[1];
+        r2 = p[2];
+      } else {
+        int x0, x1, a0, a1, y0, y1, b0, b1;
+        lb_axis(dx, ow, w, true, &x0, &x1, &a0, &a1);
+        lb_axis(dy, oh, h, false, &y0, &y1, &b0, &b1);
+        const uint8_t* p00 = s + ((size_t)y0 * w + x0) * 3;
+        const uint8_t* p01 = s + ((size_t)y0 * w + x1) * 3;
+        const uint8_t* p10 = s + ((size_t)y1 * w + x0) * 3;
+        const uint8_t* p11 = s + ((size_t)y1 * w + x1) * 3;
+        int out[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const int h0 = (int)p00[c] * a0 + (int)p01[c] * a1;
+          const int h1 = (int)p10[c] * a0 + (int)p11[c] * a1;
+          const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+          out[c] = min(max(v, 0), 255);
+        }
+        r0 = out[0];
+        r1 = out[1];
+        r2 = out[2];
+      }
+    }
+    uint8_t* q = dst + (size_t)i * 3;
+    q[0] = (uint8_t)r0;
+    q[1] = (uint8_t)r1;
+    q[2] = (uint8_t)r2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ output side: COCO records
+// prepare_for_coco_detection + convert_to_xywh (src/evaluator/eval_coco.py:87-111, 200-202): one record per kept detection,
+// (image_id, category_id) and (x, y, xmax - xmin, ymax - ymin, score) -- same fp32 subtraction as the torch lines -- compacted over the
+// batch in image order.  One CTA per image; its offset is the sum of the preceding counts.
+__global__ void __launch_bounds__(128) coco_pack_kernel(const float* __restrict__ rows, int M, int row_stride, const int* __restrict__ count,
+                                                        const long long* __restrict__ image_ids, const int* __restrict__ id2cat, int nc,
+                                                        long long* __restrict__ rec_ids, float* __restrict__ rec_box, int* __restrict__ total) {
+  __shared__ int off_s;
+  const int b = blockIdx.x;
+  if (threadIdx.x < 32) {
+    int acc = 0;
+    for (int i = threadIdx.x; i < b; i += 32) acc += min(max(count[i], 0), M);
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (threadIdx.x == 0) off_s = acc;
+  }
+  __syncthreads();
+  const int off = off_s;
+  const int k = min(max(count[b], 0), M);
+  if (b == (int)gridDim.x - 1 && threadIdx.x == 0) *total = off + k;
+  const long long img = image_ids[b];
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const float* r = rows + ((size_t)b * M + j) * row_stride;
+    const float x1 = r[0], y1 = r[1], x2 = r[2], y2 = r[3];
+    int cls = (int)r[5];
+    if (id2cat != nullptr && cls >= 0 && cls < nc) cls = id2cat[cls];
+    const size_t o = (size_t)(off + j);
+    rec_ids[o * 2 + 0] = img;
+    rec_ids[o * 2 + 1] = cls;
+    float* q = rec_box + o * 5;
+    q[0] = x1;
+    q[1] = y1;
+    q[2] = __fsub_rn(x2, x1);
+    q[3] = __fsub_rn(y2, y1);
+    q[4] = r[4];
+  }
+}
+}  // namespace cvb
+
+extern "C" int cvb_letterbox_u8(const uint8_t* const* src_ptrs, const int32_t* geom, int32_t B, int32_t out_h, int32_t out_w, const int32_t* fill,
+                                uint8_t* dst, void* stream) {
+  using namespace cvb;
+  CVB_REQUIRE(src_ptrs && geom && fill && dst && B > 0 && out_h > 0 && out_w > 0, "letterbox: bad argument");
+  const long long n = (long long)B * out_h * out_w;
+  long long grid = (n + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  letterbox_u8_kernel<<<(int)grid, 256, 0, as_stream(stream)>>>(src_ptrs, geom, B, out_h, out_w, fill[0], fill[1], fill[2], dst);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}
+
+extern "C" int cvb_coco_pack(const float* rows, int32_t B, int32_t M, int32_t row_stride, const int32_t* count, const int64_t* image_ids,
+                             const int32_t* id2category, int32_t num_classes, int64_t* rec_ids, float* rec_box, int32_t* total, void* stream) {
+  using namespace cvb;
+  CVB_REQUIRE(rows && count && image_ids && rec_ids && rec_box && total && B > 0 && M > 0 && row_stride >= 6, "coco_pack: bad argument");
+  coco_pack_kernel<<<B, 128, 0, as_stream(stream)>>>(rows, M, row_stride, count, reinterpret_cast<const long long*>(image_ids), id2category,
+                                                     num_classes, reinterpret_cast<long long*>(rec_ids), rec_box, total);
+  CVB_CHECK_CUDA(cudaGetLastError());
+  count_launch();
+  return CVB_OK;
+}

@@ -448,4 +448,6 @@ class FCOS(_GraphCache):
             bn[:, [1, 3]] = bn[:, [1, 3]].clip(0, height)
             keep = sc[i, :k] > 0.05
             outputs.append({"boxes": torch.tensor(bn)[keep], "labels": cl[i, :k][keep].long(), "scores": sc[i, :k][keep]})
-        return {}, outputs
+        # fcos.py:124-166 returns the loss dict next to the outputs; a zero 'loss' entry keeps the unchanged trainer alive under
+        # cfg.distributed (trainer.py:216-219 -> reduce_dict -> torch.stack needs a non-empty dict)
+        return {'loss': torch.zeros((), dtype=torch.float32, device=imgs.device)}, outputs

@@ -388,7 +388,9 @@ class YOLOv5(_GraphCache):
         if mode != 'val':
             raise RuntimeError("YOLOv5 (B200): only mode='val' (inference) is implemented; training stays on the reference")
         det, _, cnt = self.predict(imgs)
-        losses = {}  # val-mode loss (yolov5.py:258) is a training diagnostic; not computed on the B200 path
+        losses = {'loss': torch.zeros((), dtype=torch.float32, device=imgs.device)}
+        # yolov5.py:258: the val-mode loss of the reference is a training diagnostic and is not computed on the B200 path; a zero 'loss' entry keeps
+        # the unchanged trainer alive (trainer.py:216-219 -> reduce_dict -> torch.stack needs a non-empty dict under cfg.distributed)
         # yolov5.py:267-282 on the device (cvb_rescale_clip_boxes: same fp32 subtract / divide / clip as the numpy lines), then ONE
         # device->host copy instead of one per image
         rows = det.clone()

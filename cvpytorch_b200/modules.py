@@ -49,7 +49,42 @@ class _EmitModule(nn.Module):
                            'backbone / neck / detect graph (call the parent module), not stand-alone')
 
 
-class ConvModule(_EmitModule):
+class _StandaloneBrick(_EmitModule):
+    """Brick-level drop-in (ConvModule(conv_cfg=dict(type='B200Conv2d'), ...) inside an otherwise unchanged reference
+    model): called on its own, the brick runs as a one-layer graph with the layout adapters at its boundary -- NCHW fp32 in, NCHW fp32
+    out, like the reference's ConvModule.forward (conv_module.py:201-214).  Inside a B200 parent it is emitted into the parent's graph
+    and this method is never used.  Inference only; one cached plan per input shape (invalidated by load_state_dict / train())."""
+
+    def forward(self, x):
+        from .engine import GraphBuilder
+        if self.training:
+            raise RuntimeError(f'{type(self).__name__} (B200): inference only; call .eval() first')
+        if not (isinstance(x, torch.Tensor) and x.is_cuda and x.dim() == 4):
+            raise ops._lib.CvbError(f'{type(self).__name__}: input must be a CUDA tensor [B,C,H,W]; there is no CPU fallback')
+        cache = self.__dict__.setdefault('_brick_graphs', {})
+        key = (tuple(x.shape), x.device.index)
+        if key not in cache:
+            B, C, H, W = x.shape
+            g = GraphBuilder(B, x.device)
+            cpad = (C + 15) // 16 * 16  # the tensor-core path wants cin % 16 == 0: zero channels are free
+            xin = g.new_act(H, W, cpad)
+            out = self._emit_padded(g, xin, C, cpad)
+            cache[key] = (g, xin, out)
+        g, xin, out = cache[key]
+        ops.nchw_to_split(x, xin.tensor.view(0, x.shape[1]))  # the padding channels of the zero-initialised buffer stay zero
+        g.run()
+        return ops.split_to_nchw(out.view())
+
+    def train(self, mode=True):
+        self.__dict__['_brick_graphs'] = {}
+        return super().train(mode)
+
+    def _load_from_state_dict(self, *a, **k):
+        self.__dict__['_brick_graphs'] = {}
+        return super()._load_from_state_dict(*a, **k)
+
+
+class ConvModule(_StandaloneBrick):
     """conv -> BN -> activation bundle.  Keys: ``conv.weight``, ``bn.{weight,bias,running_mean,running_var,num_batches_tracked}``."""
 
     def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1, bias='auto',
@@ -76,6 +111,13 @@ class ConvModule(_EmitModule):
             self.bn = nn.BatchNorm2d(out_channels, eps=norm_cfg.get('eps', 1e-5), momentum=norm_cfg.get('momentum', 0.1))
         self.act_name = _act_name(act_cfg)
         nn.init.kaiming_normal_(self.conv.weight, a=0, mode='fan_out', nonlinearity='relu')  # conv_module.py:181-199
+
+    def _emit_padded(self, g, xin, cin, cpad):
+        if self.groups != 1 or cpad == cin:
+            return self.emit(g, xin if cpad == cin else xin.slice(0, cin))
+        w, b = folded(self.conv, self.bn if self.with_norm else None)
+        w = torch.cat([w, torch.zeros((w.shape[0], cpad - cin) + tuple(w.shape[2:]), dtype=w.dtype)], 1)
+        return g.conv(xin, w, b, self.kernel_size, self.stride, self.padding, self.act_name, dilation=self.dilation)
 
     def emit(self, g, x, name='', **kw):
         w, b = folded(self.conv, self.bn if self.with_norm else None)
@@ -110,7 +152,7 @@ class DepthwiseSeparableConvModule(_EmitModule):
         return self.pointwise_conv.emit(g, d, name + '.pointwise_conv', out=out)
 
 
-class Conv(_EmitModule):
+class Conv(_StandaloneBrick):
     """Old-API conv block (yolo11_modules.py:27-39): keys ``conv.weight``, ``bn.*``; SiLU; autopad."""
 
     def __init__(self, c1, c2, k=1, s=1, p=None, g=1, act=True):
@@ -124,6 +166,12 @@ class Conv(_EmitModule):
         self.act_name = 'silu' if act is True else None
         if act is not True and act is not False and act is not None:
             raise NotImplementedError('custom activation module')
+
+    def _emit_padded(self, g, xin, cin, cpad):
+        w, b = folded(self.conv, self.bn)
+        if cpad != cin:
+            w = torch.cat([w, torch.zeros((w.shape[0], cpad - cin) + tuple(w.shape[2:]), dtype=w.dtype)], 1)
+        return g.conv(xin, w, b, self.k, self.s, self.p, self.act_name)
 
     def emit(self, g, x, name='', **kw):
         w, b = folded(self.conv, self.bn)

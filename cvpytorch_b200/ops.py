@@ -425,3 +425,58 @@ def confusion_matrix(gt, pred, num_classes, out=None):
     _lib.check(_lib.lib().cvb_confusion_matrix(gt.data_ptr(), pred.data_ptr(), gt.numel(), num_classes, out.data_ptr(), _stream()),
                'cvb_confusion_matrix')
     return out
+
+
+# --------------------------------------------------------------------------------------- input side: letterbox
+def letterbox_geometry(h, w, size=(640, 640), scaleup=True):
+    """(scale, oh, ow, top, left) of the reference's Resize(keep_ratio=True) (det_transforms.py:177-189; python round() = half to even)."""
+    scale = min(size[0] / h, size[1] / w)
+    if not scaleup:
+        scale = min(scale, 1.0)
+    oh, ow = int(round(h * scale)), int(round(w * scale))
+    padh, padw = (size[0] - oh) / 2, (size[1] - ow) / 2
+    return scale, oh, ow, int(round(padh - 0.1)), int(round(padw - 0.1))
+
+
+def letterbox_frames(frames, size=(640, 640), fill=(114, 114, 114), scaleup=True, out=None):
+    """frames: list of uint8 CUDA tensors [h_i, w_i, 3] (camera frames of different sizes).  Returns (uint8 [B,size0,size1,3] letterboxed
+    batch, pads [B,2] (top, left), scales [B,2]) -- the image and the `target["pads"]` / `target["scales"]` entries of the reference's
+    Resize transform; the batch feeds YOLOv5.predict_frames (ToTensor + Normalize are fused into the stem loader)."""
+    B = len(frames)
+    dev = frames[0].device
+    geom, pads, scales = [], [], []
+    for f in frames:
+        _require_cuda(f, 'letterbox_frames')
+        assert f.dtype == torch.uint8 and f.dim() == 3 and f.shape[2] == 3 and f.is_contiguous()
+        h, w = int(f.shape[0]), int(f.shape[1])
+        scale, oh, ow, top, left = letterbox_geometry(h, w, size, scaleup)
+        geom.append([h, w, oh, ow, top, left])
+        pads.append([top, left])
+        scales.append([scale, scale])
+    ptrs = torch.tensor([f.data_ptr() for f in frames], dtype=torch.int64).to(dev)
+    g = torch.tensor(geom, dtype=torch.int32).to(dev)
+    if out is None:
+        out = torch.empty((B, size[0], size[1], 3), dtype=torch.uint8, device=dev)
+    fl = (ctypes.c_int32 * 3)(*[int(v) for v in fill])
+    _lib.check(_lib.lib().cvb_letterbox_u8(ptrs.data_ptr(), g.data_ptr(), B, size[0], size[1], fl, out.data_ptr(), _stream()), 'cvb_letterbox_u8')
+    return out, torch.tensor(pads, dtype=torch.float32), torch.tensor(scales, dtype=torch.float32)
+
+
+# --------------------------------------------------------------------------------------- output side (SURVEY.md 8 f-2): COCO records
+def coco_pack(rows, count, image_ids, id2category=None):
+    """rows [B,M,>=6] fp32 CUDA (x1,y1,x2,y2,score,class; already rescaled / clipped), count [B] int32, image_ids [B] int64 (CUDA or list),
+    id2category: optional list / tensor (dataset.id2category).  Returns (rec_ids [B*M,2] int64, rec_box [B*M,5] f32, total [1] int32) on
+    the device: the first `total` records are valid -- eval_coco.py:87-111 without the per-image .tolist() loop."""
+    _require_cuda(rows, 'coco_pack')
+    assert rows.dtype == torch.float32 and rows.is_contiguous() and rows.dim() == 3 and count.dtype == torch.int32
+    B, M, S = rows.shape
+    dev = rows.device
+    ids = torch.as_tensor(image_ids, dtype=torch.int64).to(dev).contiguous()
+    cat = torch.as_tensor(id2category, dtype=torch.int32).to(dev).contiguous() if id2category is not None else None
+    rec_ids = torch.zeros((B * M, 2), dtype=torch.int64, device=dev)
+    rec_box = torch.zeros((B * M, 5), dtype=torch.float32, device=dev)
+    total = torch.zeros((1,), dtype=torch.int32, device=dev)
+    _lib.check(_lib.lib().cvb_coco_pack(rows.data_ptr(), B, M, S, count.data_ptr(), ids.data_ptr(), cat.data_ptr() if cat is not None else None,
+                                        int(cat.numel()) if cat is not None else 0, rec_ids.data_ptr(), rec_box.data_ptr(), total.data_ptr(), _stream()),
+               'cvb_coco_pack')
+    return rec_ids, rec_box, total

@@ -354,7 +354,9 @@ class YOLOX(_GraphCache):
         if isinstance(imgs, (list, tuple)):
             imgs = torch.stack(list(imgs))
         det, cnt = self.predict(imgs)
-        losses = {}  # val-mode loss (yolox.py:156) is a training diagnostic; not computed on the B200 path
+        losses = {'loss': torch.zeros((), dtype=torch.float32, device=imgs.device)}
+        # yolox.py:156: the val-mode loss of the reference is a training diagnostic and is not computed on the B200 path; a zero 'loss' entry keeps
+        # the unchanged trainer alive (trainer.py:216-219 -> reduce_dict -> torch.stack needs a non-empty dict under cfg.distributed)
         # yolox.py:165-178 on the device (cvb_rescale_clip_boxes), then ONE device->host copy of the kept prefix
         kmax = max(int(cnt.max()), 1)
         rows = det[:, :kmax].contiguous()

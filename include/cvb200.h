@@ -279,6 +279,27 @@ int cvb_rescale_clip_boxes(float* rows, int32_t B, int32_t M, int32_t row_stride
                            const float* wh, void* stream);
 int cvb_confusion_matrix(const int64_t* gt, const int64_t* pred, int64_t n, int32_t num_classes, int64_t* cm, void* stream);
 
+/*
+ * Input side of the path: the reference's Resize(size=[640,640], keep_ratio=True, fill=[114,114,114]) transform
+ * (src/data/transforms/det_transforms.py:162-198, conf/coco_yolov5_s.yml:56) on the device: cv2.resize(INTER_LINEAR) of each uint8 HWC
+ * frame to (oh, ow) -- OpenCV's 11-bit fixed-point 8-bit bilinear kernel restated, bit-identical to cv2 4.x -- and the constant border of
+ * cv2.copyMakeBorder, for a batch of frames of DIFFERENT sizes.  The output [B,out_h,out_w,3] uint8 is what cvb_stem_s2d_u8 consumes.
+ *   src_ptrs: device array of B device pointers (frame b = uint8 [h_b, w_b, 3]); geom: device int32 [B,6] = (h, w, oh, ow, top, left) as
+ *   det_transforms.py:177-189 computes them (host side: python round(), see cvpytorch_b200.ops.letterbox_geometry); fill: host int32[3].
+ */
+int cvb_letterbox_u8(const uint8_t* const* src_ptrs, const int32_t* geom, int32_t B, int32_t out_h, int32_t out_w, const int32_t* fill,
+                     uint8_t* dst, void* stream);
+
+/*
+ * Output side, COCO records on the device: replaces CocoEvaluator.prepare_for_coco_detection + convert_to_xywh
+ * (src/evaluator/eval_coco.py:87-111, 200-202) for the fixed-capacity detections of a batch.  rows [B, M, row_stride] fp32 =
+ * (x1, y1, x2, y2, score, class, ...) after cvb_rescale_clip_boxes, count [B]; image_ids device int64 [B]; id2category device int32
+ * [num_classes] or NULL (dataset.id2category).  Writes, compacted in image order, rec_ids [n,2] int64 = (image_id, category_id) and
+ * rec_box [n,5] fp32 = (x, y, x2 - x1, y2 - y1, score) (the fp32 subtraction of the torch lines), and *total = n (device int32).
+ */
+int cvb_coco_pack(const float* rows, int32_t B, int32_t M, int32_t row_stride, const int32_t* count, const int64_t* image_ids,
+                  const int32_t* id2category, int32_t num_classes, int64_t* rec_ids, float* rec_box, int32_t* total, void* stream);
+
 /* Library info / errors */
 const char* cvb_last_error_string(void);
 int cvb_version(void);

@@ -278,3 +278,32 @@ def test_focus_and_window_formulation_equivalence():
     win = torch.stack([xp[..., j:j + 8] for j in range(4)], 1).reshape(2, 64, 6, 8)   # channel = kx*16 + c of pixel (w - 1 + kx)
     got = F.conv2d(win, ww, None, 1, (1, 0))
     assert float((got - ref).abs().max()) < 1e-12
+
+
+def test_brick_registration_hook():
+    """cvpytorch_b200.bricks.register() against a stand-in with the reference registry's interface
+    (src/utils/registry.py:293-346: register_module(name=, module=), KeyError on duplicates)."""
+    import types
+
+    from cvpytorch_b200 import bricks
+
+    class Registry:
+        def __init__(self):
+            self.module_dict = {}
+
+        def register_module(self, name=None, force=False, module=None):
+            if name in self.module_dict and not force:
+                raise KeyError(f'{name} is already registered')
+            self.module_dict[name] = module
+
+        def get(self, k):
+            return self.module_dict.get(k)
+
+    reg = types.SimpleNamespace(CONV_LAYERS=Registry(), PLUGIN_LAYERS=Registry())
+    bricks.register(reg)
+    bricks.register(reg)  # idempotent
+    assert reg.CONV_LAYERS.get('B200Conv2d') is bricks.B200Conv2d and reg.PLUGIN_LAYERS.get('B200ConvModule') is bricks.B200ConvModule
+    m = reg.PLUGIN_LAYERS.get('B200ConvModule')(16, 32, 3, padding=1, conv_cfg=dict(type='B200Conv2d'), norm_cfg=dict(type='BN'), act_cfg=dict(type='SiLU'))
+    assert set(m.state_dict().keys()) == {'conv.weight', 'bn.weight', 'bn.bias', 'bn.running_mean', 'bn.running_var', 'bn.num_batches_tracked'}
+    with pytest.raises(Exception):
+        m.eval()(torch.zeros(1, 16, 8, 8))  # CPU tensor: no fallback

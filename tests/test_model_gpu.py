@@ -310,3 +310,65 @@ def test_headline_batch_vs_reference_rows_and_end_to_end_agreement(model, sd):
         od, oi = NO.non_max_suppression(z64[b:b + 1].cpu().numpy(), 0.001, 0.6, multi_label=True)[0]
         k = int(c64[b])
         assert np.array_equal(i64[b, :k].cpu().numpy().astype(np.int64), oi) and np.array_equal(d64[b, :k].cpu().numpy(), od)
+
+
+def test_brick_level_convmodule_standalone(cuda):
+    """ConvModule / Conv called on their own (brick-level drop-in): NCHW fp32 in / out == conv -> BN(eval) -> act of torch."""
+    from cvpytorch_b200.bricks import B200ConvModule
+    from cvpytorch_b200.modules import Conv
+    torch.manual_seed(3)
+    for (cin, cout, k, s, p, act) in [(32, 64, 3, 1, 1, 'SiLU'), (3, 16, 3, 2, 1, 'ReLU'), (64, 40, 1, 1, 0, None)]:
+        m = B200ConvModule(cin, cout, k, stride=s, padding=p, conv_cfg=dict(type='B200Conv2d'), norm_cfg=dict(type='BN', eps=1e-3),
+                           act_cfg=dict(type=act) if act else None).cuda().eval()
+        with torch.no_grad():
+            m.bn.running_mean.normal_(0, 0.3)
+            m.bn.running_var.uniform_(0.5, 1.5)
+            m.bn.weight.uniform_(0.5, 1.5)
+            m.bn.bias.normal_(0, 0.2)
+        x = torch.randn(2, cin, 24, 40, device='cuda')
+        y = m(x)
+        ref = torch.nn.functional.batch_norm(torch.nn.functional.conv2d(x, m.conv.weight, None, s, p), m.bn.running_mean, m.bn.running_var,
+                                             m.bn.weight, m.bn.bias, False, 0.0, m.bn.eps)
+        ref = torch.nn.functional.silu(ref) if act == 'SiLU' else (torch.relu(ref) if act == 'ReLU' else ref)
+        assert _rel(y, ref) < 2e-5, (cin, cout, k)
+        assert _rel(m(x), ref) < 2e-5  # cached plan
+    c = Conv(32, 32, 3, 1).cuda().eval()
+    x = torch.randn(1, 32, 16, 16, device='cuda')
+    ref = torch.nn.functional.silu(torch.nn.functional.batch_norm(torch.nn.functional.conv2d(x, c.conv.weight, None, 1, 1), c.bn.running_mean,
+                                                                  c.bn.running_var, c.bn.weight, c.bn.bias, False, 0.0, c.bn.eps))
+    assert _rel(c(x), ref) < 2e-5
+
+
+def test_drop_in_through_the_reference_trainer_val_step(model):
+    """The val branch of the reference's Trainer.run_step (trainer.py:209-231) restated around the drop-in model, including the
+    `cfg.distributed` path: reduce_dict(losses) stacks the loss values (src/utils/distributed.py:108-125) and must not see an empty dict."""
+    class Logger:
+        def __init__(self):
+            self.seen = {}
+
+        def update(self, *a, **k):
+            self.seen.update(k)
+            self.args = a
+
+    def reduce_dict_distributed(d):  # the world_size >= 2 branch of src/utils/distributed.py:112-125 (mean over the stacked values)
+        names = sorted(d.keys())
+        values = torch.stack([d[k] for k in names], dim=0)
+        return {k: torch.mean(v) for k, v in zip(names, values)}
+
+    torch.manual_seed(4)
+    imgs = torch.randn(2, 3, 128, 128).cuda()
+    targets = [{'labels': torch.zeros(1), 'boxes': torch.zeros(1, 4), 'scales': torch.tensor([1.0, 1.0]), 'pads': torch.tensor([0.0, 0.0]),
+                'height': torch.tensor(128), 'width': torch.tensor(128)} for _ in range(2)]
+    for distributed in (False, True):
+        loss_logger, perf_logger = Logger(), Logger()
+        out = model(imgs, targets, 'val')                      # trainer.py:209
+        if not isinstance(out, tuple):                         # :210-213
+            losses, predicts = None, out
+        else:
+            losses, predicts = out
+        if losses is not None:                                 # :215-222
+            loss_logger.update(**(reduce_dict_distributed(losses) if distributed else losses))
+        if predicts is not None:                               # :224-231 (the reference's reduce_dict of a LIST of dicts is its own bug)
+            perf_logger.update(targets, predicts)
+        assert 'loss' in loss_logger.seen and float(loss_logger.seen['loss']) == 0.0
+        assert len(perf_logger.args[1]) == 2 and set(perf_logger.args[1][0].keys()) == {'boxes', 'labels', 'scores'}

@@ -126,3 +126,57 @@ def test_output_side_rescale_clip_and_confusion_matrix(cuda):
         mask = (g >= 0) & (g < nc)
         return np.bincount(nc * g[mask].astype('int') + p[mask], minlength=nc ** 2).reshape(nc, nc)
     assert np.array_equal(cm.cpu().numpy(), ref_matrix(gt, pr) + ref_matrix(gt[:1], pr[:1]))
+
+
+def test_letterbox_on_device_equals_reference_resize(cuda):
+    """cvb_letterbox_u8 (frames of different sizes in one launch) == the reference's Resize(keep_ratio=True) fixture, bit for bit
+    (tests/golden/letterbox.npz: cv2.resize INTER_LINEAR + copyMakeBorder through the reference's own class), pads / scales included."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from test_oracle_golden import _letterbox_cases
+    from cvpytorch_b200 import ops
+    cases = _letterbox_cases()
+    for size in sorted({c[1] for c in cases}):
+        group = [c for c in cases if c[1] == size]
+        frames = [torch.from_numpy(c[0]).cuda() for c in group]
+        out, pads, scales = ops.letterbox_frames(frames, size=size, fill=(114, 114, 114))
+        torch.cuda.synchronize()
+        for i, (frame, _, p, s, check) in enumerate(group):
+            assert check(out[i].cpu().numpy()), (size, frame.shape)
+            assert tuple(int(v) for v in pads[i]) == p and abs(float(scales[i, 0]) - s) < 1e-6 * s
+
+
+def test_letterbox_feeds_predict_frames(cuda):
+    """camera frames of two sizes -> device letterbox -> YOLOv5.predict_frames == the reference-order pipeline on the oracle-letterboxed batch"""
+    from cvpytorch_b200 import ops, synth
+    from oracle import io_oracle as IO
+    m = synth.build_yolov5s(True)
+    rng = np.random.default_rng(9)
+    frames = [rng.integers(0, 256, size=(96, 128, 3), dtype=np.uint8), rng.integers(0, 256, size=(150, 100, 3), dtype=np.uint8)]
+    lb, pads, scales = ops.letterbox_frames([torch.from_numpy(f).cuda() for f in frames], size=(128, 128))
+    ref = np.stack([IO.letterbox(f, (128, 128))[0] for f in frames])
+    assert np.array_equal(lb.cpu().numpy(), ref)
+    d0, i0, c0 = [t.clone() for t in m.predict_frames(lb)]
+    d1, i1, c1 = m.predict_frames(torch.from_numpy(ref).cuda())
+    assert torch.equal(c0, c1) and torch.equal(i0, i1) and torch.equal(d0, d1)
+
+
+def test_coco_pack_on_device(cuda):
+    from cvpytorch_b200 import ops
+    from oracle import io_oracle as IO
+    g = torch.Generator().manual_seed(12)
+    B, M = 5, 300
+    xy = torch.rand(B, M, 2, generator=g) * 500
+    wh = torch.rand(B, M, 2, generator=g) * 120
+    rows = torch.cat([xy, xy + wh, torch.rand(B, M, 1, generator=g), torch.randint(0, 80, (B, M, 1), generator=g).float()], 2).contiguous()
+    count = torch.tensor([300, 0, 17, 1, 250], dtype=torch.int32)
+    image_ids = [581929, 42, 139, 7, 100000]
+    id2cat = list(range(1, 81))
+    rec_ids, rec_box, total = ops.coco_pack(rows.cuda(), count.cuda(), image_ids, id2cat)
+    torch.cuda.synchronize()
+    n = int(total[0])
+    ids, cats, xywh, sc = IO.coco_records(rows[:, :, :4].numpy(), rows[:, :, 4].numpy(), rows[:, :, 5].numpy(), count.tolist(), image_ids, id2cat)
+    assert n == int(count.sum()) == ids.shape[0]
+    assert np.array_equal(rec_ids[:n, 0].cpu().numpy(), ids) and np.array_equal(rec_ids[:n, 1].cpu().numpy(), cats)
+    assert np.array_equal(rec_box[:n, :4].cpu().numpy(), xywh) and np.array_equal(rec_box[:n, 4].cpu().numpy(), sc)
