@@ -59,6 +59,7 @@ struct alignas(64) ConvKArgs {
   int mma_pair;        // 1: A_hi x [B_hi | B_lo] as one MMA of N = 2 * BLOCK_N (needs n_main == 1 and BLOCK_N <= 128)
   int resid_tma;       // 1: the residual tile arrives by TMA (issued one group ahead by the epilogue), 0: per-thread loads
   int resid_first;     // 1: out = act(conv + bias + residual) (ResNet bottleneck); 0: out = act(conv + bias) + residual (Darknet)
+  float resid_scale;   // weight of the residual operand (1 for the Darknet / ResNet shortcuts, alpha of the YOLOv6 BottleRep)
   float rz_gain;       // 1 + (MMAs per hi*hi chain) * c: undoes the mean shrink of round-toward-zero accumulation
   int out_bufs;        // 1 or 2 output staging tiles (2: the TMA store of group g overlaps the conversion of g+1)
   int8_t tap_map[kMaxTaps];
@@ -505,6 +506,7 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
     uint32_t res_phase = 0;
     grid_dep_wait();  // residual / up-partial reads and the output stores must not pass the previous kernel(s)
     const int n_main = a.n_main;
+    const float rscale = a.resid_scale;
     constexpr int kGroups = BLOCK_N / OUT_GROUP_CH;
     // residual tile of (tile, group): two TMA boxes (hi, lo) with the output tile's geometry; OOB parts are zero-filled
     auto issue_residual = [&](int tile_i, int g) {
@@ -644,8 +646,8 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
               for (int e = 0; e < 4; ++e) {
                 const float2 hf = __half22float2(h2[e]);
                 const float2 lf = __half22float2(l2[e]);
-                rsum[8 * j + 2 * e + 0] = hf.x + lf.x;
-                rsum[8 * j + 2 * e + 1] = hf.y + lf.y;
+                rsum[8 * j + 2 * e + 0] = (hf.x + lf.x) * rscale;
+                rsum[8 * j + 2 * e + 1] = (hf.y + lf.y) * rscale;
               }
             }
           }
@@ -1302,6 +1304,7 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
       a.resid_tma = 1;
     }
     a.resid_first = d->residual_before_act ? 1 : 0;
+    a.resid_scale = d->residual_scale != 0.0f ? d->residual_scale : 1.0f;
   }
   if (d->up_partial.base) {
     const CvbView& u = d->up_partial;

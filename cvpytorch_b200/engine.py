@@ -71,7 +71,7 @@ class GraphBuilder:
 
     # ---------------------------------------------------------------- ops
     def conv(self, x, w64, b64, k, stride=1, pad=0, act='silu', out=None, residual=None, up_partial=None,
-             f32_out=None, dilation=1, name='', block_n=0, w_window=0, residual_before_act=False):
+             f32_out=None, dilation=1, name='', block_n=0, w_window=0, residual_before_act=False, residual_scale=1.0):
         """x: Val.  w64: [O,I,k,k] float64 (BN already folded), b64: [O] float64.
         out: Val (split16) or None (allocate).  f32_out: F32Tensor -> plain fp32 output."""
         O, I = w64.shape[0], w64.shape[1]
@@ -96,7 +96,7 @@ class GraphBuilder:
         plan = ops.ConvPlan(x.view(), out_view, wp, bp, k, stride, pad, dilation, act,
                             residual=residual.view() if residual is not None else None,
                             up_partial=up_partial.view(0, O) if up_partial is not None else None, block_n=block_n,
-                            w_window=w_window, residual_before_act=1 if residual_before_act else 0)
+                            w_window=w_window, residual_before_act=1 if residual_before_act else 0, residual_scale=residual_scale)
         self.steps.append(('conv', plan))
         self.n_convs += 1
         self.flops += 2 * self.B * Ho * Wo * O * I * k * k

@@ -138,7 +138,7 @@ class ConvPlan:
     """Owns a CvbConvPlan handle (host-side TMA descriptors + launch shape) and keeps its tensors alive."""
 
     def __init__(self, inp, out, weights, bias, k, stride=1, pad=0, dilation=1, act=None, residual=None,
-                 up_partial=None, block_n=0, sm_limit=0, keepalive=(), w_window=0, no_resident=0, residual_before_act=0, halo=0):
+                 up_partial=None, block_n=0, sm_limit=0, keepalive=(), w_window=0, no_resident=0, residual_before_act=0, halo=0, residual_scale=1.0):
         d = CvbConvDesc()
         d.inp, d.out = inp, out
         d.weights = weights.data_ptr()
@@ -155,6 +155,7 @@ class ConvPlan:
         d.no_resident = no_resident
         d.residual_before_act = residual_before_act
         d.halo = halo
+        d.residual_scale = float(residual_scale)
         self._keep = (weights, bias) + tuple(keepalive)
         self.handle = c_void_p()
         _lib.check(_lib.lib().cvb_conv_plan_create(byref(d), byref(self.handle)), 'cvb_conv_plan_create')

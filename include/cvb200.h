@@ -89,6 +89,8 @@ typedef struct CvbConvDesc {
                            1 / 2 = force "halo" mode where the layer allows it: the 8x16-pixel tile is loaded once per K chunk including
                            the filter halo (2: one box per input map; 1: one box per horizontal tap offset) and every tap is a
                            row-shifted shared-memory descriptor view of it -- up to 6x less L2->SM fill traffic for 3x3 layers. */
+  float residual_scale; /* out = act(...) + residual_scale * residual (0 is read as 1): the learnable shortcut weight `alpha` of the YOLOv6
+                           BottleRep block (src/models/modules/yolo_modules.py:474-492) */
 } CvbConvDesc;
 
 typedef struct CvbConvPlan CvbConvPlan;

@@ -372,3 +372,26 @@ def test_drop_in_through_the_reference_trainer_val_step(model):
             perf_logger.update(targets, predicts)
         assert 'loss' in loss_logger.seen and float(loss_logger.seen['loss']) == 0.0
         assert len(perf_logger.args[1]) == 2 and set(perf_logger.args[1][0].keys()) == {'boxes', 'labels', 'scores'}
+
+
+def test_yolov6_yolov7_blocks_vs_reference_golden(cuda):
+    """RepVGGBlock (training form and re-parameterised), BepC3 (BottleRep chain with learnable shortcut weights) and E-ELAN mirrors load the
+    REFERENCE's state_dict (identical key lists) and reproduce the reference outputs (tools/make_golden_blocks.py) within 1e-3 -- measured
+    ~1e-5: every RepVGG block is one folded 3x3 tcgen05 conv, every torch.cat is buffer aliasing."""
+    from cvpytorch_b200 import yolo_blocks as YB
+    g = np.load(os.path.join(GOLD, 'yolo_blocks.npz'))
+    ctors = {'rep_id': lambda: YB.RepVGGBlock(32, 32), 'rep_s2': lambda: YB.RepVGGBlock(32, 64, stride=2), 'rep_deploy': lambda: YB.RepVGGBlock(32, 32),
+             'bepc3': lambda: YB.BepC3(64, 64, n=4), 'eelan': lambda: YB.EELAN(64, 32, 128)}
+    for name, ctor in ctors.items():
+        m = ctor()
+        keys = [str(k) for k in g[f'{name}_keys']]
+        assert list(m.state_dict().keys()) == keys, name
+        m.load_state_dict({k: torch.from_numpy(g[f'{name}_sd_{k}']) for k in keys}, strict=True)
+        m = m.cuda().eval()
+        if name == 'rep_deploy':
+            m.switch_to_deploy()
+            assert list(m.state_dict().keys()) == ['rbr_reparam.weight', 'rbr_reparam.bias']
+        y = m(torch.from_numpy(g[f'{name}_x']).cuda())
+        err = _rel(y, g[f'{name}_y'])
+        print(name, 'rel err vs reference', err)
+        assert err < TOL and err < 1e-4, (name, err)
