@@ -23,6 +23,7 @@
 #include <cstdlib>
 #include <mutex>
 #include <new>
+#include <type_traits>
 
 #include "internal.h"
 #include "ptx.cuh"
@@ -382,94 +383,116 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
       const bool pair = a.mma_pair != 0 && 2 * BLOCK_N <= 256, resident = a.b_resident != 0, kskip = a.kskip != 0;
       const int ksteps = KSTEPS - a.kskip;
       const int chunks = a.chunks;
-      // one tap with the loop-invariant mode flags resolved at compile time inside (the branches are uniform and cheap, the MMA
-      // sequences themselves are straight-line code)
-      auto tap = [&](uint32_t a16, uint32_t lo16, uint32_t a_hi, uint32_t b16, uint32_t d_base, uint32_t d_main, uint32_t d_cross,
-                     uint32_t nz, uint32_t main_nz) {
-        if (pair) {
-          if (!kskip) issue_tap<BLOCK_N, KSTEPS, true, false>(a16, lo16, a_hi, b16, kB16, kHiStd, d_base, d_main, d_cross, nz, main_nz, ksteps);
-          else issue_tap<BLOCK_N, KSTEPS, true, true>(a16, lo16, a_hi, b16, kB16, kHiStd, d_base, d_main, d_cross, nz, main_nz, ksteps);
-        } else {
-          if (!kskip) issue_tap<BLOCK_N, KSTEPS, false, false>(a16, lo16, a_hi, b16, kB16, kHiStd, d_base, d_main, d_cross, nz, main_nz, ksteps);
-          else issue_tap<BLOCK_N, KSTEPS, false, true>(a16, lo16, a_hi, b16, kB16, kHiStd, d_base, d_main, d_cross, nz, main_nz, ksteps);
-        }
-      };
-      if (resident && (int)blockIdx.x < total_tiles) mbar_wait(bfull, 0, 250);
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        if (!(a.dbg & 8)) CVB_PROF_WAIT(0, mbar_wait(&tempty[acc], acc_phase ^ 1, 200 + acc));
-        tc_fence_after();
-        // The tensor core's fp32 adder rounds toward zero, so a long accumulation chain shrinks |sum| by ~1.6e-8 per
-        // MMA (measured, tools/precision_probe.py).  Chains are kept short: the hi*hi products rotate over n_main
-        // accumulators, the (2^-11 smaller) hi*lo + lo*hi cross terms go to their own; the epilogue adds them in RN fp32.
-        const uint32_t d_base = tmem_base + (uint32_t)acc * set_cols;
-        const uint32_t d_cross = d_base + (uint32_t)(n_main * BLOCK_N);
-        int r = 0;
-        int it = 0;
-        if (a.halo) {
-          // copy / tap mode: every tap is a row-shifted descriptor view of the copy in the current A slot; weight tiles come from
-          // the resident slab or from their own ring.  The taps of a copy form an ny x nx grid (filter rows x filter columns) whose
-          // view offsets and weight indices are affine in (y, x), so the loop needs no per-tap table.
-          const uint32_t wstep16 = (uint32_t)chunks * 2u * kB16;  // resident slab: distance between consecutive weight taps
-          for (int ck = 0; ck < chunks; ++ck) {
-            for (int c = 0; c < a.n_copies; ++c) {
-              const int ny = a.cp_ny[c], nx = a.cp_nx[c];
-              const uint32_t row16 = a.cp_row16[c], lo16 = a.cp_lo_off[c] >> 4;
-              const uint32_t a_hi = (a.cp_sbo[c] >> 4) | (1u << 14) | (kLayout << 29);
-              const uint32_t wy16 = (uint32_t)a.cp_wy[c] * wstep16, wx16 = (uint32_t)a.cp_wx[c] * wstep16;
-              uint32_t brow16 = bres16 + (uint32_t)a.cp_w0[c] * wstep16 + (uint32_t)ck * 2u * kB16;
-              if (!(a.dbg & 8)) CVB_PROF_WAIT(1, mbar_wait(&full[stage], phase, 300 + stage));
-              tc_fence_after();
-              uint32_t arow16 = ring16 + (uint32_t)stage * stage16;
-              for (int y = 0; y < ny; ++y, arow16 += row16, brow16 += wy16) {
-                uint32_t a16 = arow16, bx16 = brow16;
-                for (int x = 0; x < nx; ++x, a16 += (SWZ >> 4), bx16 += wx16) {
-                  uint32_t b16 = bx16;
-                  if (!resident) {
-                    CVB_PROF_WAIT(2, mbar_wait(&fullB[hb], hphase_b, 350 + hb));
-                    tc_fence_after();
-                    b16 = bres16 + (uint32_t)hb * 2u * kB16;
-                  }
-                  tap(a16, lo16, a_hi, b16, d_base, d_base + (uint32_t)(r * BLOCK_N), d_cross, it != 0 ? 1u : 0u, it >= n_main ? 1u : 0u);
-                  if (!resident) {
-                    umma_commit(&emptyB[hb]);
-                    if (++hb == SB) {
-                      hb = 0;
-                      hphase_b ^= 1;
+      const bool nowait = (a.dbg & 8) != 0;
+      // The issuing thread is instruction-latency bound (~7 cycles per dependent instruction, one warp): a K chunk of a narrow tile is
+      // only 4-8 MMAs of ~50 cycles each, so the loop around them must stay within a few dozen instructions.  The loop nest is
+      // therefore instantiated per mode (PAIR / KSKIP / single main accumulator) instead of branching per tap, ring positions are
+      // running descriptor words, and the "first MMA of the tile overwrites" flag is a register that flips after the first tap.
+      auto run_tiles = [&](auto PAIR_T, auto KSKIP_T, auto ONEMAIN_T) {
+        constexpr bool PAIR = decltype(PAIR_T)::value, KSKIP = decltype(KSKIP_T)::value, ONEMAIN = decltype(ONEMAIN_T)::value;
+        uint32_t a_ring16 = ring16;  // descriptor low word of the current A slot / stage
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+          if (!nowait) CVB_PROF_WAIT(0, mbar_wait(&tempty[acc], acc_phase ^ 1, 200 + acc));
+          tc_fence_after();
+          // The tensor core's fp32 adder rounds toward zero, so a long accumulation chain shrinks |sum| by ~1.6e-8 per MMA (measured,
+          // tools/precision_probe.py).  Chains are kept short: the hi*hi products rotate over n_main accumulators, the (2^-11
+          // smaller) hi*lo + lo*hi cross terms go to their own; the epilogue adds them in RN fp32.
+          const uint32_t d_base = tmem_base + (uint32_t)acc * set_cols;
+          const uint32_t d_cross = d_base + (uint32_t)(n_main * BLOCK_N);
+          uint32_t nz = 0;   // 0 until the first tap of the tile has been issued
+          int r = 0, it = 0;
+          if (a.halo) {
+            // copy / tap mode: every tap is a row-shifted descriptor view of the copy in the current A slot; weight tiles come from
+            // the resident slab or from their own ring.  The taps of a copy form an ny x nx grid (filter rows x filter columns) whose
+            // view offsets and weight indices are affine in (y, x): two running descriptor words, no per-tap table.
+            const uint32_t wstep16 = (uint32_t)chunks * 2u * kB16;  // resident slab: distance between consecutive weight taps
+            for (int ck = 0; ck < chunks; ++ck) {
+              for (int c = 0; c < a.n_copies; ++c) {
+                const int ny = a.cp_ny[c], nx = a.cp_nx[c];
+                const uint32_t row16 = a.cp_row16[c], lo16 = a.cp_lo_off[c] >> 4;
+                const uint32_t a_hi = (a.cp_sbo[c] >> 4) | (1u << 14) | (kLayout << 29);
+                const uint32_t wy16 = (uint32_t)a.cp_wy[c] * wstep16, wx16 = (uint32_t)a.cp_wx[c] * wstep16;
+                uint32_t brow16 = bres16 + (uint32_t)a.cp_w0[c] * wstep16 + (uint32_t)ck * 2u * kB16;
+                if (!nowait) CVB_PROF_WAIT(1, mbar_wait(&full[stage], phase, 300 + stage));
+                tc_fence_after();
+                uint32_t arow16 = a_ring16;
+                for (int y = 0; y < ny; ++y, arow16 += row16, brow16 += wy16) {
+                  uint32_t a16 = arow16, b16 = brow16;
+                  for (int x = 0; x < nx; ++x, a16 += (SWZ >> 4), b16 += wx16) {
+                    uint32_t bb = b16;
+                    if (!resident) {
+                      if (!nowait) CVB_PROF_WAIT(2, mbar_wait(&fullB[hb], hphase_b, 350 + hb));
+                      tc_fence_after();
+                      bb = bres16 + (uint32_t)hb * 2u * kB16;
+                    }
+                    const uint32_t d_main = ONEMAIN ? d_base : d_base + (uint32_t)(r * BLOCK_N);
+                    issue_tap<BLOCK_N, KSTEPS, PAIR, KSKIP>(a16, lo16, a_hi, bb, kB16, kHiStd, d_base, d_main, d_cross, nz,
+                                                           ONEMAIN ? nz : (it >= n_main ? 1u : 0u), ksteps);
+                    nz = 1u;
+                    if (!resident) {
+                      umma_commit(&emptyB[hb]);
+                      if (++hb == SB) {
+                        hb = 0;
+                        hphase_b ^= 1;
+                      }
+                    }
+                    if constexpr (!ONEMAIN) {
+                      if (++r == n_main) r = 0;
+                      ++it;
                     }
                   }
-                  if (++r == n_main) r = 0;
-                  ++it;
+                }
+                umma_commit(&empty[stage]);  // all taps of this copy have been issued: the slot is free once they complete
+                a_ring16 += stage16;
+                if (++stage == STAGES) {
+                  stage = 0;
+                  phase ^= 1;
+                  a_ring16 = ring16;
                 }
               }
-              umma_commit(&empty[stage]);  // all taps of this copy have been issued: the slot is free once they complete
+            }
+          } else {
+            const uint32_t lo16 = a.a_lo_off >> 4;
+            uint32_t bres_it16 = bres16;
+            for (int i = 0; i < k_iters; ++i, bres_it16 += 2u * kB16) {
+              if (!nowait) CVB_PROF_WAIT(1, mbar_wait(&full[stage], phase, 300 + stage));
+              tc_fence_after();
+              const uint32_t b16 = resident ? bres_it16 : a_ring16 + ((2u * A_BYTES) >> 4);
+              const uint32_t d_main = ONEMAIN ? d_base : d_base + (uint32_t)(r * BLOCK_N);
+              issue_tap<BLOCK_N, KSTEPS, PAIR, KSKIP>(a_ring16, lo16, kHiStd, b16, kB16, kHiStd, d_base, d_main, d_cross, nz,
+                                                     ONEMAIN ? nz : (it >= n_main ? 1u : 0u), ksteps);
+              nz = 1u;
+              umma_commit(&empty[stage]);  // frees this smem stage once the MMAs above have read it
+              a_ring16 += stage16;
               if (++stage == STAGES) {
                 stage = 0;
                 phase ^= 1;
+                a_ring16 = ring16;
+              }
+              if constexpr (!ONEMAIN) {
+                if (++r == n_main) r = 0;
+                ++it;
               }
             }
           }
-        } else {
-          const uint32_t lo16 = a.a_lo_off >> 4;
-          uint32_t bres_it16 = bres16;
-          for (; it < k_iters; ++it, bres_it16 += 2u * kB16) {
-            if (!(a.dbg & 8)) CVB_PROF_WAIT(1, mbar_wait(&full[stage], phase, 300 + stage));
-            tc_fence_after();
-            const uint32_t a16 = ring16 + (uint32_t)stage * stage16;
-            const uint32_t b16 = resident ? bres_it16 : a16 + ((2u * A_BYTES) >> 4);
-            tap(a16, lo16, kHiStd, b16, d_base, d_base + (uint32_t)(r * BLOCK_N), d_cross, it != 0 ? 1u : 0u, it >= n_main ? 1u : 0u);
-            umma_commit(&empty[stage]);  // frees this smem stage once the MMAs above have read it
-            if (++stage == STAGES) {
-              stage = 0;
-              phase ^= 1;
-            }
-            if (++r == n_main) r = 0;
+          umma_commit(&tfull[acc]);  // accumulators complete -> epilogue
+          if (++acc == a.nbuf) {
+            acc = 0;
+            acc_phase ^= 1;
           }
         }
-        umma_commit(&tfull[acc]);  // accumulators complete -> epilogue
-        if (++acc == a.nbuf) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
+      };
+      if (resident && (int)blockIdx.x < total_tiles && !nowait) mbar_wait(bfull, 0, 250);
+      using T_ = std::true_type;
+      using F_ = std::false_type;
+      if (pair) {  // pair mode implies a single main accumulator
+        if (!kskip) run_tiles(T_{}, F_{}, T_{});
+        else run_tiles(T_{}, T_{}, T_{});
+      } else if (n_main == 1) {
+        if (!kskip) run_tiles(F_{}, F_{}, T_{});
+        else run_tiles(F_{}, T_{}, T_{});
+      } else {
+        run_tiles(F_{}, std::integral_constant<bool, false>{}, F_{});
       }
       if (a.dbg & 8) {  // diagnostics: the issuer ran without waiting for anybody; drain the tensor pipe before the teardown
         umma_commit(rfull);
