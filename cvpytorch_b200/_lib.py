@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libcvb200.so')
 
 CVB_ACT_NONE, CVB_ACT_SILU, CVB_ACT_RELU = 0, 1, 2
-CVB_OUT_SPLIT16, CVB_OUT_F32 = 0, 1
+CVB_OUT_SPLIT16, CVB_OUT_F32, CVB_OUT_YOLO = 0, 1, 2
 
 
 class CvbView(ctypes.Structure):
@@ -20,11 +20,16 @@ class CvbView(ctypes.Structure):
                 ('c_pitch', c_int32), ('plane_stride', c_int64)]
 
 
+class CvbYoloDecode(ctypes.Structure):
+    _fields_ = [('na', c_int32), ('no', c_int32), ('anchors_px', c_float * 8), ('stride', c_float), ('z', c_void_p), ('z_rows', c_int64),
+                ('z_off', c_int64), ('nms_workspace', c_void_p), ('conf_thres', c_float), ('multi_label', c_int32)]
+
+
 class CvbConvDesc(ctypes.Structure):
     _fields_ = [('inp', CvbView), ('out', CvbView), ('weights', c_void_p), ('cout_pad', c_int32),
                 ('bias', c_void_p), ('kh', c_int32), ('kw', c_int32), ('stride', c_int32), ('pad', c_int32),
                 ('dilation', c_int32), ('act', c_int32), ('out_kind', c_int32), ('residual', CvbView),
-                ('up_partial', CvbView), ('block_n', c_int32), ('sm_limit', c_int32), ('no_resident', c_int32), ('residual_before_act', c_int32), ('w_window', c_int32), ('halo', c_int32), ('residual_scale', c_float)]
+                ('up_partial', CvbView), ('block_n', c_int32), ('sm_limit', c_int32), ('no_resident', c_int32), ('residual_before_act', c_int32), ('w_window', c_int32), ('halo', c_int32), ('yolo', POINTER(CvbYoloDecode)), ('residual_scale', c_float)]
 
 
 class CvbNmsParams(ctypes.Structure):

@@ -19,6 +19,7 @@
 //   warp 1      MMA issuer     (one lane)   TMEM accumulators double buffered: tfull[]/tempty[]
 //   warps 2..9  epilogue (two warps per TMEM lane quarter): tcgen05.ld -> +partial +bias -> act -> +residual -> hi/lo split -> swizzled smem -> TMA store
 #include <cuda_fp16.h>
+#include <math_constants.h>
 
 #include <cstdlib>
 #include <mutex>
@@ -34,6 +35,9 @@ constexpr int kTileM = 128;
 constexpr int kMaxTaps = 9;
 constexpr int kEpiThreads = 256;          // 8 epilogue warps
 constexpr int kThreads = 64 + kEpiThreads;  // + TMA producer warp + MMA issuer warp
+constexpr int kYoloEpiThreads = 384;      // fused-decode kernels: 12 epilogue warps (three per TMEM lane quarter, two 16-column chunks each)
+constexpr int kYoloBiasBytes = 4 * 128 * 4;  // fused decode: bias of all (<= 4) anchors, loaded once per CTA
+constexpr int kYoloStageBytes = 45056;  // fused decode: [128][85] fp32 staging tile + 3 x 128 partial row maxima, rounded to 1 KB
 constexpr int kSmemBudget = 232448;  // 227 KB opt-in limit per CTA on sm_100
 constexpr int kSmemBudget2 = 115712;  // per CTA when two share an SM: (228 KB - 2 x 1 KB reserved) / 2
 
@@ -90,7 +94,18 @@ struct alignas(64) ConvKArgs {
   // the taps of copy c form an ny x nx grid: view offset = y * cp_row16 + x * (row bytes >> 4) (16-byte units), weight tap = w0 + y*wy + x*wx
   uint32_t cp_row16[6];
   int8_t cp_ny[6], cp_nx[6], cp_w0[6], cp_wy[6], cp_wx[6];
-  int dbg;                     // diagnostics (CVB_DBG, results are WRONG): bit 0 = no TMA stores, bit 1 = activations loaded only for the first ring pass, bit 2 = epilogue skips the math / staging
+  // ---- fused YOLOv5 decode epilogue (YOLO kernels): n-tile = anchor (85 of 128 columns used), z rows / NMS histogram / rowmax written directly
+  int tile_contig;             // 1: every CTA owns a contiguous run of tiles (image-major), so its shared-memory histogram belongs to <= 2 images
+  float* yz;                   // z [B, y_zrows, y_no] fp32
+  long long y_zrows, y_zoff;
+  int y_no, y_multi;
+  int y_nx;                    // level width (the conv itself runs on the flattened level: Wo = ny * nx, Ho = 1)
+  uint32_t y_nx_magic;         // ceil(2^32 / nx): pixel -> row by multiply-high
+  float y_stride, y_conf;
+  float y_anchor[8];           // anchor sizes in pixels: [a * 2 + 0] = w, [a * 2 + 1] = h
+  unsigned int* y_hist;        // NMS workspace histogram [B][kNmsBins] (or NULL)
+  float* y_rowmax;             // NMS workspace per-row best score [B][y_zrows] (or NULL)
+  int dbg;                     // diagnostics (CVB_DBG, results are WRONG): bit 0 = no TMA stores, bit 1 = activations loaded only for the first ring pass, bit 2 = epilogue skips the math / staging, bit 5 = fused decode without histogram atomics, bit 6 = without the z copy-out
   long long* prof;             // diagnostics (cvb_conv_plan_set_profile): per-CTA cycle counters of the three pipeline roles, or NULL
 };
 
@@ -126,6 +141,16 @@ __device__ __forceinline__ void split_pair(float x0, float x1, uint32_t& hi, uin
       stmt;                                    \
     }                                          \
   } while (0)
+
+// NMS score histogram in shared memory: ++hist[min(bits(sc) >> 17, kNmsBins - 1)] iff `on` -- one predicated red.shared, no branch
+// (a C++ `if (on) atomicAdd(...)` compiles to a ~14-instruction divergent region per score, which dominated the fused-decode epilogue)
+__device__ __forceinline__ void hist_inc_if(uint32_t hist_smem_addr, float sc, bool on) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b32 t;\n\tsetp.ne.b32 p, %2, 0;\n\tshr.b32 t, %1, 17;\n\tmin.u32 t, t, %3;\n\tmad.lo.u32 t, t, 4, %0;\n\t"
+      "@p red.shared.add.u32 [t], 1;\n\t}\n"
+      ::"r"(hist_smem_addr), "r"(__float_as_uint(sc)), "r"((uint32_t)on), "n"(kNmsBins - 1)
+      : "memory");
+}
 
 template <int CW>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&v)[CW]) {
@@ -176,8 +201,8 @@ struct ConvCfg {
   static constexpr int TAIL_BYTES = BLOCK_N * 4 + 64 * 8 + 16;  // bias + barriers + tmem slot
 };
 
-template <int BLOCK_N, int BLOCK_K, bool OUT_F32>
-__global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_kernel(const __grid_constant__ ConvKArgs a) {
+template <int BLOCK_N, int BLOCK_K, bool OUT_F32, bool YOLO>
+__global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_kernel(const __grid_constant__ ConvKArgs a) {
   using Cfg = ConvCfg<BLOCK_N, BLOCK_K, OUT_F32>;
   constexpr int SWZ = Cfg::SWZ;
   constexpr int A_BYTES = Cfg::A_BYTES;
@@ -186,6 +211,7 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
   constexpr int OUT_GROUP_CH = Cfg::OUT_GROUP_CH;
   constexpr int OUT_ROW_BYTES = Cfg::OUT_ROW_BYTES;
   constexpr uint32_t IDESC = make_idesc_f16_f32(kTileM, BLOCK_N);
+  constexpr int EPI_THREADS = YOLO ? kYoloEpiThreads : kEpiThreads;
 
   // the kernel has no static shared memory, so the dynamic window starts at offset 0 of the CTA's (1024-byte aligned)
   // allocation; checked once instead of spending 1 KB of slack (which is what lets some two-CTA plans fit in 113 KB)
@@ -200,8 +226,8 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
   uint8_t* stage_base = smem;
   uint8_t* b_res = smem + STAGES * stage_bytes;                                  // resident weights: k_iters x {hi, lo} tiles (halo mode: or the weight ring)
   uint8_t* out_stage0 = b_res + (a.b_resident ? a.taps * a.chunks * 2 * B_BYTES : (a.halo ? a.sb_stages * 2 * B_BYTES : 0));
-  uint8_t* res_stage = out_stage0 + a.out_bufs * Cfg::OUT_STAGE_BYTES;           // residual tile (same layout as an output tile)
-  float* bias_s = reinterpret_cast<float*>(res_stage + (a.resid_tma ? Cfg::OUT_STAGE_BYTES : 0));
+  uint8_t* res_stage = out_stage0 + (YOLO ? kYoloStageBytes + kNmsBins * 4 + kYoloBiasBytes : a.out_bufs * Cfg::OUT_STAGE_BYTES);  // residual tile (same layout as an output tile)
+  float* bias_s = reinterpret_cast<float*>(res_stage + (a.resid_tma ? Cfg::OUT_STAGE_BYTES : 0));  // (fused decode: staging tile + histogram instead of output tiles)
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + BLOCK_N);
   const int SB = a.halo ? a.sb_stages : 0;
   uint64_t* full = bars;
@@ -220,7 +246,7 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&a.tmA[0]);
     tma_prefetch_desc(&a.tmB);
-    tma_prefetch_desc(&a.tmO);
+    if constexpr (!YOLO) tma_prefetch_desc(&a.tmO);
     if (a.resid_tma) tma_prefetch_desc(&a.tmR);
   }
   if (warp == 1) {
@@ -235,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
       }
       for (int s = 0; s < 2; ++s) {
         mbar_init(&tfull[s], 1);
-        mbar_init(&tempty[s], kEpiThreads / 32);
+        mbar_init(&tempty[s], EPI_THREADS / 32);
       }
       mbar_init(bfull, 1);
       mbar_init(rfull, 1);
@@ -256,6 +282,15 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
   const int m_tiles = a.tiles_w * a.tiles_h * a.tiles_b;
   const int total_tiles = m_tiles * a.tiles_n;
   const int k_iters = a.taps * a.chunks;
+  // tiles of this CTA: strided over the grid (default), or one contiguous run (fused-decode kernels: image-major order keeps the CTA's
+  // shared-memory NMS histogram on one or two images)
+  int t_begin = (int)blockIdx.x, t_end = total_tiles, t_step = (int)gridDim.x;
+  if (a.tile_contig) {
+    const int per = (total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    t_begin = (int)blockIdx.x * per;
+    t_end = min(total_tiles, t_begin + per);
+    t_step = 1;
+  }
   // Tile order: tile = mt * tiles_n + nt.  Every CTA strides by gridDim.x; in resident mode gridDim.x is a multiple of
   // tiles_n, so nt = tile % tiles_n is the same for all tiles of a CTA and its weight slab is loaded exactly once.
 
@@ -268,7 +303,7 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t tx_bytes = 2 * a.a_box_bytes + (a.b_resident ? 0 : 2 * B_BYTES);
-      if (a.b_resident && (int)blockIdx.x < total_tiles) {
+      if (a.b_resident && t_begin < t_end) {
         const int n0r = ((int)blockIdx.x % a.tiles_n) * BLOCK_N;
         mbar_expect_tx(bfull, (uint32_t)(k_iters * 2 * B_BYTES));
         for (int it = 0; it < k_iters; ++it) {
@@ -282,7 +317,7 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
         // chunk), then the weight tiles of the copy's taps in the order the MMA warp consumes them
         int sb = 0;
         uint32_t phase_b = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = t_begin; tile < t_end; tile += t_step) {
           const int nt = tile % a.tiles_n;
           const int mt = tile / a.tiles_n;
           const int wt = mt % a.tiles_w;
@@ -294,7 +329,7 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
             int t = 0;
             for (int c = 0; c < a.n_copies; ++c) {
               CVB_PROF_WAIT(0, mbar_wait(&empty[stage], phase ^ 1, 100 + stage));
-              if ((a.dbg & 2) && (tile != (int)blockIdx.x)) {
+              if ((a.dbg & 2) && (tile != t_begin)) {
                 mbar_arrive(&full[stage]);  // diagnostics: no data movement after the first tile
               } else {
               mbar_expect_tx(&full[stage], 2 * a.cp_bytes[c]);
@@ -322,7 +357,7 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
           }
         }
       } else
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = t_begin; tile < t_end; tile += t_step) {
         const int nt = tile % a.tiles_n;
         const int mt = tile / a.tiles_n;
         const int wt = mt % a.tiles_w;
@@ -391,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
       auto run_tiles = [&](auto PAIR_T, auto KSKIP_T, auto ONEMAIN_T) {
         constexpr bool PAIR = decltype(PAIR_T)::value, KSKIP = decltype(KSKIP_T)::value, ONEMAIN = decltype(ONEMAIN_T)::value;
         uint32_t a_ring16 = ring16;  // descriptor low word of the current A slot / stage
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int tile = t_begin; tile < t_end; tile += t_step) {
           if (!nowait) CVB_PROF_WAIT(0, mbar_wait(&tempty[acc], acc_phase ^ 1, 200 + acc));
           tc_fence_after();
           // The tensor core's fp32 adder rounds toward zero, so a long accumulation chain shrinks |sum| by ~1.6e-8 per MMA (measured,
@@ -482,7 +517,7 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
           }
         }
       };
-      if (resident && (int)blockIdx.x < total_tiles && !nowait) mbar_wait(bfull, 0, 250);
+      if (resident && t_begin < t_end && !nowait) mbar_wait(bfull, 0, 250);
       using T_ = std::true_type;
       using F_ = std::false_type;
       if (pair) {  // pair mode implies a single main accumulator
@@ -520,7 +555,7 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
     constexpr int CW = OUT_GROUP_CH / 2;  // columns per warp per group (32, or 16 for 32-wide groups)
     constexpr int SUB = (BLOCK_N <= 64 && CW > 16) ? 16 : CW;  // columns held in registers at a time
     const bool prof_on = a.prof != nullptr;
-    long long prof_acc[1] = {0};
+    long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
     const long long prof_t0 = prof_on ? clock64() : 0;
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -541,8 +576,33 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
       tma_load_5d(&a.tmR, rfull, res_stage, c0, wt_ * a.TW, ht_ * a.TH, bt_ * a.NB, 0);
       tma_load_5d(&a.tmR, rfull, res_stage + Cfg::OUT_PLANE_BYTES, c0, wt_ * a.TW, ht_ * a.TH, bt_ * a.NB, 1);
     };
-    if (a.resid_tma && tid_e == 0 && (int)blockIdx.x < total_tiles) issue_residual(blockIdx.x, 0);
-    for (int tile = (a.dbg & 16) ? total_tiles : (int)blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    // fused YOLOv5 decode (YOLO kernels): staging tile [128 rows][85] fp32 + per-row partial best scores + per-image NMS histogram
+    float* y_stage = reinterpret_cast<float*>(out_stage0);
+    float* y_part = y_stage + kTileM * 85;
+    uint32_t* hist_s = reinterpret_cast<uint32_t*>(out_stage0 + kYoloStageBytes);
+    int cur_img = -1;
+    auto flush_hist = [&](int img) {  // all epilogue threads: add the CTA's counts of image `img` to the workspace histogram
+      named_bar_sync(1, EPI_THREADS);
+      if (img >= 0 && a.y_hist != nullptr) {
+        unsigned int* gh = a.y_hist + (size_t)img * kNmsBins;
+        for (int i = tid_e; i < kNmsBins; i += EPI_THREADS) {
+          const uint32_t c = hist_s[i];
+          if (c) {
+            atomicAdd(&gh[i], c);
+            hist_s[i] = 0;
+          }
+        }
+      }
+      named_bar_sync(1, EPI_THREADS);
+    };
+    float* y_bias = reinterpret_cast<float*>(out_stage0 + kYoloStageBytes + kNmsBins * 4);  // [anchor][128]; -inf in the padding columns: sigmoid = 0, never a candidate
+    if constexpr (YOLO) {
+      for (int i = tid_e; i < kNmsBins; i += EPI_THREADS) hist_s[i] = 0;
+      for (int i = tid_e; i < a.tiles_n * BLOCK_N; i += EPI_THREADS)
+        y_bias[i] = ((i & (BLOCK_N - 1)) < a.y_no && i < a.bias_len) ? a.bias[i] : -CUDART_INF_F;
+    }
+    if (a.resid_tma && tid_e == 0 && t_begin < t_end) issue_residual(t_begin, 0);
+    for (int tile = (a.dbg & 16) ? t_end : t_begin; tile < t_end; tile += t_step) {
       const int nt = tile % a.tiles_n;
       const int mt = tile / a.tiles_n;
       const int wt = mt % a.tiles_w;
@@ -553,10 +613,13 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
       const int ow = w0 + tw, oh = h0 + th, ob = b0 + nb;
       const bool valid = (row < a.rows_valid) && (ow < a.Wo) && (oh < a.Ho) && (ob < a.Bn);
 
-      if (n0 != cur_n0) {
-        named_bar_sync(1, kEpiThreads);
-        for (int i = tid_e; i < BLOCK_N; i += kEpiThreads) bias_s[i] = (n0 + i < a.bias_len) ? a.bias[n0 + i] : 0.0f;
-        named_bar_sync(1, kEpiThreads);
+      if (!YOLO && n0 != cur_n0) {
+        named_bar_sync(1, EPI_THREADS);
+        for (int i = tid_e; i < BLOCK_N; i += EPI_THREADS) {
+          float bv = (n0 + i < a.bias_len) ? a.bias[n0 + i] : 0.0f;
+          bias_s[i] = bv;
+        }
+        named_bar_sync(1, EPI_THREADS);
         cur_n0 = n0;
       }
       const float* up_row = nullptr;
@@ -567,6 +630,144 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
 
       const uint32_t t_set = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (n_main + 1) * BLOCK_N);
 
+      if constexpr (YOLO) {
+        // ---- conv -> sigmoid -> box decode -> z rows + NMS histogram + per-row best score, straight from the accumulator
+        // (replaces the fp32 raw tensor round trip + cvb_yolo_decode: yolov5_detect.py:42-55; same arithmetic, bit-identical z).
+        // n-tile nt == anchor; accumulator column o < y_no is output o of that anchor; thread == pixel row of the tile.  The level is
+        // seen as ONE row of ny*nx pixels (the planner flattens the 1x1 conv), so a tile's 128 pixels are 128 consecutive z rows.
+        // Twelve epilogue warps: three per TMEM lane quarter (`part` = 0..2), each converting two of the six 16-column chunks -- the
+        // conversion is issue / latency bound, so it wants more warps than the 8 of the plain epilogue.  They form two independent
+        // groups (accumulator rows 0-63 / 64-127) with their own staging half, barrier and TMA bulk store, so one group's copy-out
+        // overlaps the other's conversion.
+        if (b0 != cur_img) {  // (NB == 1 in this mode: one image per tile; b0 is uniform over the CTA)
+          flush_hist(cur_img);
+          cur_img = b0;
+        }
+        const int an = nt, no = a.y_no;
+        const float gain = a.rz_gain, conf = a.y_conf;
+        const float* bias_a = y_bias + an * BLOCK_N;
+        const int grp = q >> 1;                                  // rows 64 * grp .. + 63
+        const int part = half;                                   // (warp - 2) >> 2 = 0..2
+        constexpr int GT = EPI_THREADS / 2;                      // threads per group
+        const int gtid = ((q & 1) * 3 + part) * 32 + lane;        // thread index inside the group
+        const int npix = a.Wo;                                   // pixels of the level (flattened)
+        const int py = (int)__umulhi((uint32_t)ow, a.y_nx_magic), px = ow - py * a.y_nx;  // ow = flat pixel index
+        const size_t lvl_row0 = (size_t)b0 * (size_t)a.y_zrows + (size_t)a.y_zoff + (size_t)an * npix;  // z row of the level's pixel 0
+        CVB_PROF_WAIT(0, mbar_wait(&tfull[acc], acc_phase, 400 + acc));
+        tc_fence_after();
+        const uint32_t obj_m = tmem_ld_32x1(t_set + 4u), obj_c = tmem_ld_32x1(t_set + (uint32_t)BLOCK_N + 4u);  // (n_main == 1: checked by the planner)
+        tmem_ld_wait();
+        // objectness of this thread's row; 0 for rows outside the level, so that none of their scores passes the threshold
+        const float obj = valid ? sigmoid_fast(fmaf(__uint_as_float(obj_m), gain, __uint_as_float(obj_c)) + bias_a[4]) : 0.0f;
+        // the group's staging half was last read by the bulk store its thread 0 issued for the previous tile
+        long long pt0 = prof_on ? clock64() : 0;
+        if (gtid == 0) tma_store_wait_read0();
+        named_bar_sync(2 + grp, GT);
+        if (prof_on) {
+          const long long t = clock64();
+          prof_acc[1] += t - pt0;  // waiting for the staging half (previous bulk store + group barrier)
+          pt0 = t;
+        }
+        float rbest = 0.0f;
+        float* srow = y_stage + row * 85;
+        const uint32_t hist_s32 = smem_u32(hist_s);
+        const bool any_live = __any_sync(0xffffffffu, obj > conf);  // background-only warps skip the score pass
+        const bool multi = a.y_multi != 0 && !(a.dbg & 32);
+#pragma unroll 1
+        for (int cg = 0; cg < 2; ++cg) {  // this warp's 16-column chunks: part and part + 3 (columns >= 96 are padding)
+          const int col = (part + 3 * cg) * 16;
+          if (col >= no || (a.dbg & 4)) break;
+          uint32_t vc[16], vm[16];
+          tmem_ld_32x16(t_set + (uint32_t)(BLOCK_N + col), vc);
+          tmem_ld_32x16(t_set + (uint32_t)col, vm);
+          tmem_ld_wait();
+          float yv[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)  // 16 independent sigmoids: the MUFU pipe stays busy (bias_s is -inf beyond the anchor's outputs: y = 0)
+            yv[j] = sigmoid_fast(fmaf(__uint_as_float(vm[j]), gain, __uint_as_float(vc[j])) + bias_a[col + j]);
+          int j0 = 0;
+          if (col == 0) {  // (warp-uniform) xy = (y*2 - 0.5 + grid) * stride; wh = (y*2)^2 * anchor  (yolov5_detect.py:50-53)
+            const float t0 = __fmul_rn(yv[0], 2.0f), t1 = __fmul_rn(yv[1], 2.0f), t2 = __fmul_rn(yv[2], 2.0f), t3 = __fmul_rn(yv[3], 2.0f);
+            srow[0] = __fmul_rn(__fadd_rn(__fsub_rn(t0, 0.5f), (float)px), a.y_stride);
+            srow[1] = __fmul_rn(__fadd_rn(__fsub_rn(t1, 0.5f), (float)py), a.y_stride);
+            srow[2] = __fmul_rn(__fmul_rn(t2, t2), a.y_anchor[an * 2]);
+            srow[3] = __fmul_rn(__fmul_rn(t3, t3), a.y_anchor[an * 2 + 1]);
+            srow[4] = yv[4];
+            yv[0] = yv[1] = yv[2] = yv[3] = yv[4] = 0.0f;  // not class scores
+            j0 = 5;
+          }
+          if (col + 16 <= no) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j >= j0) srow[col + j] = yv[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (j >= j0 && col + j < no) srow[col + j] = yv[j];
+          }
+          if (any_live) {
+            // scores: the fp32 product the NMS kernels recompute from z (yolov5.py:106).  y = 0 in the padding columns and obj = 0 in
+            // rows outside the level, so `sc > conf` alone decides; the histogram update sits behind a warp vote (a uniform branch):
+            // background pixels cost four instructions per score
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float sc = __fmul_rn(yv[j], obj);
+              const bool pass = sc > conf;
+              rbest = fmaxf(rbest, sc);
+              if (multi && __any_sync(0xffffffffu, pass)) hist_inc_if(hist_s32, sc, pass);
+            }
+          }
+        }
+        // all tcgen05.ld of this accumulator set are complete -> hand it back to the MMA warp before the global stores
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[acc]);
+        if (++acc == a.nbuf) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        y_part[part * kTileM + row] = rbest;
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the bulk-copy engine (async proxy)
+        if (prof_on) {
+          const long long t = clock64();
+          prof_acc[2] += t - pt0;  // conversion
+          pt0 = t;
+        }
+        named_bar_sync(2 + grp, GT);
+        if (prof_on) {
+          const long long t = clock64();
+          prof_acc[3] += t - pt0;  // group barrier after the conversion
+          pt0 = t;
+        }
+        {
+          // the group's valid tile rows [r0, r1) are consecutive z rows: one bulk copy
+          const int r0 = grp * 64;
+          const int r1 = min(min(r0 + 64, a.rows_valid), npix - w0);
+          if (r1 > r0 && !(a.dbg & 64)) {
+            float* gdst = a.yz + (lvl_row0 + (size_t)(w0 + r0)) * (size_t)no;
+            const float* ssrc = y_stage + (size_t)r0 * 85;
+            const int nfl = (r1 - r0) * no;
+            if (no == 85 && (reinterpret_cast<uintptr_t>(gdst) & 15) == 0 && (nfl & 3) == 0 && !(a.dbg & 128)) {
+              if (gtid == 0) {
+                bulk_store_1d(gdst, ssrc, (uint32_t)nfl * 4u);
+                tma_store_commit();
+              }
+            } else if (no == 85) {  // generic paths (odd geometry / fewer classes): staged rows have pitch 85, z rows pitch `no`
+              for (int i = gtid; i < nfl; i += GT) gdst[i] = ssrc[i];
+            } else {
+              for (int i = gtid; i < nfl; i += GT) gdst[i] = ssrc[(i / no) * 85 + (i % no)];
+            }
+          }
+          if (a.y_rowmax != nullptr && part == 0 && valid) {
+            float rm = fmaxf(fmaxf(y_part[row], y_part[kTileM + row]), y_part[2 * kTileM + row]);
+            if (!(rm > conf)) rm = 0.0f;
+            a.y_rowmax[lvl_row0 + (size_t)ow] = rm;
+            if (!a.y_multi && rm > conf) atomicAdd(&hist_s[min(__float_as_uint(rm) >> 17, (uint32_t)(kNmsBins - 1))], 1u);
+          }
+        }
+        if (prof_on) prof_acc[4] += clock64() - pt0;  // copy-out issue + rowmax
+        continue;
+      }
 #pragma unroll 1
       for (int g = 0; g < BLOCK_N / OUT_GROUP_CH; ++g) {
         const int col0 = g * OUT_GROUP_CH + half * CW;
@@ -611,7 +812,7 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
           if (a.out_bufs == 2) tma_store_wait_read1();
           else tma_store_wait_read0();
         }
-        named_bar_sync(1, kEpiThreads);
+        named_bar_sync(1, EPI_THREADS);
         uint8_t* out_stage = out_stage0 + (gcount & (a.out_bufs - 1)) * Cfg::OUT_STAGE_BYTES;
         ++gcount;
 #pragma unroll
@@ -718,7 +919,7 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
           }
         }
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-        named_bar_sync(1, kEpiThreads);
+        named_bar_sync(1, EPI_THREADS);
         if (tid_e == 0) {
           const int c0 = n0 + g * OUT_GROUP_CH;
           if (c0 < a.cout && !(a.dbg & 1)) {
@@ -728,7 +929,7 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
           tma_store_commit();
           if (a.resid_tma) {  // every epilogue thread has consumed the residual tile (barrier above): fetch the next one
             if (g + 1 < kGroups) issue_residual(tile, g + 1);
-            else if (tile + (int)gridDim.x < total_tiles) issue_residual(tile + (int)gridDim.x, 0);
+            else if (tile + t_step < t_end) issue_residual(tile + t_step, 0);
           }
         }
       }
@@ -741,10 +942,15 @@ __global__ void __launch_bounds__(kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_ker
         acc_phase ^= 1;
       }
     }
+    if constexpr (YOLO) {
+      flush_hist(cur_img);
+      if (lane == 0 && half == 0 && (q & 1) == 0) tma_store_wait_all0();  // thread 0 of each decode group: its bulk stores
+    }
     if (tid_e == 0) tma_store_wait_all0();
     if (prof_on && tid_e == 0) {  // epilogue: total cycles, waiting for a finished accumulator
       a.prof[blockIdx.x * 16 + 8] = clock64() - prof_t0;
       a.prof[blockIdx.x * 16 + 9] = prof_acc[0];
+      for (int i = 1; i < 5; ++i) a.prof[blockIdx.x * 16 + 9 + i] = prof_acc[i];
     }
   }
 
@@ -763,14 +969,19 @@ struct KernelEntry {
   int stage_bytes, out_stage_bytes, tail_bytes;
 };
 
-template <int BN, int BK, bool F32>
+template <int BN, int BK, bool F32, bool YOLO = false>
 static KernelEntry entry() {
   using Cfg = ConvCfg<BN, BK, F32>;
-  return KernelEntry{reinterpret_cast<const void*>(&conv_tc_kernel<BN, BK, F32>), Cfg::STAGE_BYTES, Cfg::OUT_STAGE_BYTES,
+  return KernelEntry{reinterpret_cast<const void*>(&conv_tc_kernel<BN, BK, F32, YOLO>), Cfg::STAGE_BYTES, Cfg::OUT_STAGE_BYTES,
                      Cfg::TAIL_BYTES};
 }
 
-static bool lookup_kernel(int bn, int bk, bool f32, KernelEntry* e) {
+static bool lookup_kernel(int bn, int bk, bool f32, KernelEntry* e, bool yolo = false) {
+  if (yolo) {  // fused-decode epilogue: one anchor per 128-wide n-tile
+    if (bn == 128 && bk == 32) { *e = entry<128, 32, true, true>(); return true; }
+    if (bn == 128 && bk == 64) { *e = entry<128, 64, true, true>(); return true; }
+    return false;
+  }
 #define CVB_CASE(BN, BK)                               \
   if (bn == BN && bk == BK) {                          \
     *e = f32 ? entry<BN, BK, true>() : entry<BN, BK, false>(); \
@@ -791,6 +1002,7 @@ struct CvbConvPlan {
   const void* fn;
   int grid;
   int smem;
+  int threads;
 };
 
 namespace cvb {
@@ -854,9 +1066,23 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   using namespace cvb;
   CVB_REQUIRE(d != nullptr && out_plan != nullptr, "null argument");
   *out_plan = nullptr;
+  CvbConvDesc flat;
+  int yolo_nx = 0;
+  if (d->out_kind == CVB_OUT_YOLO) {
+    // fused decode: a 1x1 / stride 1 conv does not care about the image geometry, so the level is planned as ONE row of H * W pixels.
+    // A tile is then 128 consecutive pixels = 128 consecutive z rows (one contiguous 43 KB store) and no accumulator row is wasted
+    // on partial boxes (80x80: 50 full tiles per image and anchor).
+    CVB_REQUIRE(d->in.H >= 1 && d->in.W >= 1 && d->in.H == d->out.H && d->in.W == d->out.W && (long long)d->in.H * d->in.W < (1 << 24),
+                "conv(yolo): bad level geometry");
+    flat = *d;
+    yolo_nx = d->in.W;
+    flat.in.W = flat.out.W = d->in.H * d->in.W;
+    flat.in.H = flat.out.H = 1;
+    d = &flat;
+  }
   const CvbView& in = d->in;
   const CvbView& out = d->out;
-  CVB_REQUIRE(in.base && out.base && d->weights && d->bias, "conv: null tensor pointer");
+  CVB_REQUIRE(in.base && (out.base || d->out_kind == CVB_OUT_YOLO) && d->weights && d->bias, "conv: null tensor pointer");
   CVB_REQUIRE(d->kh >= 1 && d->kw >= 1 && (d->w_window > 0 ? d->kh : d->kh * d->kw) <= kMaxTaps,
               "conv: kernel %dx%d unsupported (max %d taps)", d->kh, d->kw, kMaxTaps);
   CVB_REQUIRE(d->stride == 1 || d->stride == 2, "conv: stride %d unsupported", d->stride);
@@ -869,10 +1095,19 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
     CVB_REQUIRE(in.W > win - 1, "conv: padded input too narrow");
   }
   const int cin = win > 0 ? win * in.C : in.C;  // K per tap as seen by the GEMM
+  const bool yolo = d->out_kind == CVB_OUT_YOLO;
+  if (yolo) {
+    CVB_REQUIRE(d->yolo != nullptr && d->yolo->z != nullptr, "conv: out_kind CVB_OUT_YOLO needs CvbConvDesc.yolo with a z pointer");
+    CVB_REQUIRE(d->yolo->na >= 1 && d->yolo->na <= 4 && d->yolo->no >= 6 && d->yolo->no <= 85, "conv(yolo): na <= 4 and 6 <= no <= 85 supported");
+    CVB_REQUIRE(d->kh == 1 && d->kw == 1 && d->stride == 1 && d->pad == 0 && win == 0, "conv(yolo): the detect conv is 1x1 / stride 1");
+    CVB_REQUIRE(out.C == d->yolo->na * 128 && d->cout_pad == out.C, "conv(yolo): weights must be packed one anchor per 128-wide n-tile (C = na*128)");
+    CVB_REQUIRE(!d->residual.base && !d->up_partial.base && d->act == CVB_ACT_NONE, "conv(yolo): no residual / partial / activation");
+    CVB_REQUIRE((reinterpret_cast<uintptr_t>(d->yolo->z) & 3) == 0, "conv(yolo): z must be 4-byte aligned");
+  }
   const int cout = out.C;
   CVB_REQUIRE(cin % 16 == 0, "conv: cin=%d must be a multiple of 16", cin);
-  CVB_REQUIRE(in.c_pitch % 8 == 0 && out.c_pitch % 8 == 0, "conv: channel pitch must be a multiple of 8");
-  CVB_REQUIRE((reinterpret_cast<uintptr_t>(in.base) & 15) == 0 && (reinterpret_cast<uintptr_t>(out.base) & 15) == 0 &&
+  CVB_REQUIRE(in.c_pitch % 8 == 0 && (yolo || out.c_pitch % 8 == 0), "conv: channel pitch must be a multiple of 8");
+  CVB_REQUIRE((reinterpret_cast<uintptr_t>(in.base) & 15) == 0 && (yolo || (reinterpret_cast<uintptr_t>(out.base) & 15) == 0) &&
                   (reinterpret_cast<uintptr_t>(d->weights) & 15) == 0,
               "conv: pointers must be 16-byte aligned");
   // window mode: the caller fixes the output height (asymmetric vertical padding is expressed by `pad` = rows above; rows
@@ -882,7 +1117,7 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   CVB_REQUIRE(Ho == out.H && Wo == out.W && in.B == out.B, "conv: output view %dx%dx%d does not match computed %dx%dx%d", out.B, out.H,
               out.W, in.B, Ho, Wo);
   CVB_REQUIRE(d->cout_pad >= cout && d->cout_pad % 8 == 0, "conv: bad cout_pad");
-  const bool f32 = d->out_kind == CVB_OUT_F32;
+  const bool f32 = d->out_kind == CVB_OUT_F32 || yolo;
   if (f32) CVB_REQUIRE(out.c_pitch % 4 == 0, "conv: fp32 output pitch must be a multiple of 4");
 
   int bn = d->block_n;
@@ -897,7 +1132,12 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
     if (split128 && !f32 && d->kh * d->kw == 1 && cout == 128 && cin <= 128 && cin % 64 == 0) bn = 64;
   }
   int bk = (cin % 64 == 0) ? 64 : (cin % 32 == 0 ? 32 : 16);
-  {
+  if (yolo) {
+    bn = 128;  // one anchor per n-tile
+    CVB_REQUIRE(cin % 32 == 0, "conv(yolo): cin must be a multiple of 32");
+    bk = 32;   // the 64 KB NMS histogram + 44 KB staging tile leave room for three 32 KB stages
+  }
+  if (!yolo) {
     static const int bk_small = [] {
       const char* e = getenv("CVB_BK_SMALLN");  // tuning knob: K chunk of the block_n <= 64 kernels for 64-channel inputs (default 32)
       const int v = e ? atoi(e) : 0;
@@ -1164,7 +1404,7 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   }
   if (use_halo) bk = hc.bk;
   KernelEntry ke;
-  CVB_REQUIRE(lookup_kernel(bn, bk, f32, &ke), "conv: no kernel for block_n=%d block_k=%d", bn, bk);
+  CVB_REQUIRE(lookup_kernel(bn, bk, f32, &ke, yolo), "conv: no kernel for block_n=%d block_k=%d yolo=%d", bn, bk, (int)yolo);
 
   CvbConvPlan* p = new (std::nothrow) CvbConvPlan();
   CVB_REQUIRE(p != nullptr, "out of host memory");
@@ -1173,6 +1413,11 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
 
   int TW, TH, NB;
   choose_box(out.B, Ho, Wo, &TW, &TH, &NB);
+  if (yolo) {  // one image per tile (the epilogue keeps a per-image histogram), 128 consecutive pixels of the flattened level
+    TW = Wo < kTileM ? Wo : kTileM;
+    TH = 1;
+    NB = 1;
+  }
   if (use_halo) {
     TW = HTW;
     TH = HTH;
@@ -1282,7 +1527,7 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
     rc = encode_map(&a.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(d->weights), dims, str, box, swizzle_for_bytes(bk * 2));
   }
   // ---- output map: 5D (C, W, H, B, plane)
-  if (rc == CVB_OK) {
+  if (rc == CVB_OK && !yolo) {
     if (f32) {
       const long long pix = (long long)out.c_pitch * 4;
       const cuuint64_t dims[5] = {(cuuint64_t)cout, (cuuint64_t)Wo, (cuuint64_t)Ho, (cuuint64_t)out.B, 1};
@@ -1375,7 +1620,26 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
     return (budget - base - ke.out_stage_bytes) / (a_stage + b_stage);
   };
   int stages = 0, ctas_per_sm = 1;
-  if (use_halo) {
+  if (yolo) {
+    const CvbYoloDecode& y = *d->yolo;
+    stages = (kSmemBudget - ke.tail_bytes - kYoloStageBytes - kNmsBins * 4 - kYoloBiasBytes) / (a_stage + b_stage);
+    if (stages > 4) stages = 4;
+    a.b_resident = 0;
+    a.out_bufs = 1;
+    a.tile_contig = 1;
+    a.yz = y.z;
+    a.y_zrows = y.z_rows;
+    a.y_zoff = y.z_off;
+    a.y_no = y.no;
+    a.y_nx = yolo_nx;
+    a.y_nx_magic = (uint32_t)((0x100000000ULL + (unsigned long long)yolo_nx - 1) / (unsigned long long)yolo_nx);
+    a.y_multi = y.multi_label ? 1 : 0;
+    a.y_stride = y.stride;
+    a.y_conf = y.conf_thres;
+    for (int i = 0; i < 8; ++i) a.y_anchor[i] = y.anchors_px[i];
+    a.y_hist = static_cast<unsigned int*>(y.nms_workspace);
+    a.y_rowmax = y.nms_workspace ? reinterpret_cast<float*>(static_cast<uint8_t*>(y.nms_workspace) + nms_ws_rowmax_offset(out.B)) : nullptr;
+  } else if (use_halo) {
     stages = hc.sa;
     a.b_resident = hc.resident;
     a.out_bufs = hc.out_bufs;
@@ -1415,6 +1679,7 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
     int n_main = (chain + max_chain - 1) / max_chain;
     if (n_main > 3) n_main = 3;
     while ((n_main + 1) * bn > 512) --n_main;
+    if (yolo) n_main = 1;  // the fused-decode epilogue reads one main + one cross accumulator (chains of the 1x1 head convs are <= 64 MMAs anyway)
     if (n_main < 1) {
       delete p;
       return set_error(CVB_ERR_INVALID, "conv: block_n=%d leaves no room for the split accumulators", bn);
@@ -1445,7 +1710,9 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   }
   p->smem = base + stages * (a_stage + (a.b_resident ? 0 : b_stage)) + (a.b_resident ? k_iters * b_stage : 0) + a.out_bufs * ke.out_stage_bytes;
   if (use_halo) p->smem = hc.smem;
+  if (yolo) p->smem = ke.tail_bytes + kYoloStageBytes + kNmsBins * 4 + kYoloBiasBytes + stages * (a_stage + b_stage);
   p->fn = ke.fn;
+  p->threads = yolo ? 64 + kYoloEpiThreads : kThreads;
   {
     const char* e = getenv("CVB_DBG");  // diagnostics only (tools/conv_pipeline_profile.py): results are wrong when set
     a.dbg = e ? atoi(e) : 0;
@@ -1504,7 +1771,7 @@ extern "C" int cvb_conv_plan_run(const CvbConvPlan* p, void* stream) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(p->grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(p->threads);
   cfg.dynamicSmemBytes = (size_t)p->smem;
   cfg.stream = as_stream(stream);
   cudaLaunchAttribute attr[1];

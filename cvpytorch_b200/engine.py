@@ -103,6 +103,20 @@ class GraphBuilder:
         self.layer_log.append((name, I, O, k, stride, Ho, Wo))
         return ret
 
+    def conv_yolo_head(self, x, w64, b64, na, no, anchors_px, stride, z, z_rows, z_off, nms_ws=None, conf_thres=0.001, multi_label=True, name=''):
+        """Detect-head 1x1 conv with the YOLOv5 decode as its epilogue (CVB_OUT_YOLO): writes this level's rows of z (and the NMS
+        histogram / per-row best scores) straight from the accumulator; no raw [B,ny,nx,na*no] tensor exists."""
+        O, I = w64.shape[0], w64.shape[1]
+        assert I == x.c and O == na * no, (name, I, x.c, O)
+        wp, bp = ops.pack_yolo_head_weights(w64, b64, na, no, device=self.device)
+        out_view = ops.CvbView(z.data_ptr(), self.B, x.H, x.W, na * 128, na * 128, 0)
+        y = ops.yolo_decode_desc(na, no, anchors_px, stride, z, z_rows, z_off, nms_ws, conf_thres, multi_label)
+        plan = ops.ConvPlan(x.view(), out_view, wp, bp, 1, 1, 0, 1, None, yolo=y, keepalive=(z,))
+        self.steps.append(('conv', plan))
+        self.n_convs += 1
+        self.flops += 2 * self.B * x.H * x.W * O * I
+        self.layer_log.append((name, I, O, 1, 1, x.H, x.W))
+
     def fn(self, f):
         self.steps.append(('fn', f))
 

@@ -11,6 +11,7 @@ Component modules accept/return the reference's NCHW fp32 tensors (adapter kerne
 model-level module runs ONE fused graph end to end (split-NHWC internally, decode + batched NMS on device).
 """
 import math
+import os
 from copy import deepcopy
 
 import torch
@@ -208,7 +209,16 @@ class YOLOv5Detect(_GraphCache):
         off = 0
         if nms_ws is not None:
             g.fn(lambda: ops.nms_reset(nms_ws))
+        fused = (not want_raw) and no <= 85 and na <= 4 and all(f.c % 32 == 0 for f in feats) and os.environ.get('CVB_FUSED_DECODE', '1') != '0'
         for i, f in enumerate(feats):
+            if fused:
+                # the decode IS the conv's epilogue: z rows + NMS histogram / rowmax straight from the accumulator (no raw tensor, one launch)
+                w, b = folded(self.m[i])
+                anchors_px = self.anchors[i].detach().float().cpu() * float(self.stride[i])
+                g.conv_yolo_head(f, w, b, na, no, anchors_px, float(self.stride[i]), z, A, off, nms_ws, conf_thres, multi_label,
+                                 name=f'{name}.m.{i}')
+                off += na * f.H * f.W
+                continue
             cpitch = (na * no + 31) // 32 * 32
             raw = g.new_f32(f.H, f.W, cpitch)
             w, b = folded(self.m[i])

@@ -9,7 +9,8 @@ from ctypes import byref, c_void_p
 import torch
 
 from . import _lib
-from ._lib import CVB_ACT_NONE, CVB_ACT_RELU, CVB_ACT_SILU, CVB_OUT_F32, CVB_OUT_SPLIT16, CvbConvDesc, CvbNmsParams, CvbView
+from ._lib import (CVB_ACT_NONE, CVB_ACT_RELU, CVB_ACT_SILU, CVB_OUT_F32, CVB_OUT_SPLIT16, CVB_OUT_YOLO, CvbConvDesc, CvbNmsParams, CvbView,
+                   CvbYoloDecode)
 
 ACTS = {None: CVB_ACT_NONE, 'none': CVB_ACT_NONE, 'silu': CVB_ACT_SILU, 'swish': CVB_ACT_SILU, 'relu': CVB_ACT_RELU}
 
@@ -106,6 +107,35 @@ def pack_conv_weights(w64, b64, cin_pad=None, device='cuda'):
     return packed.to(device), bias.to(device)
 
 
+def pack_yolo_head_weights(w64, b64, na, no, device='cuda'):
+    """Detect-head 1x1 conv [na*no, I, 1, 1] -> the CVB_OUT_YOLO layout: ONE ANCHOR PER 128-WIDE N-TILE (row a*128 + o = output channel
+    a*no + o, the other rows zero), so that the fused-decode epilogue finds all `no` outputs of an (anchor, pixel) row in one accumulator tile."""
+    O, I, kh, kw = w64.shape
+    assert O == na * no and kh == 1 and kw == 1 and no <= 128
+    w = torch.zeros((na * 128, I, 1, 1), dtype=torch.float64)
+    b = torch.zeros((na * 128,), dtype=torch.float64)
+    for a in range(na):
+        w[a * 128:a * 128 + no] = w64[a * no:(a + 1) * no]
+        b[a * 128:a * 128 + no] = b64[a * no:(a + 1) * no]
+    return pack_conv_weights(w, b, device=device)
+
+
+def yolo_decode_desc(na, no, anchors_px, stride, z, z_rows, z_off, nms_ws=None, conf_thres=0.001, multi_label=True):
+    y = CvbYoloDecode()
+    y.na, y.no = na, no
+    ap = [float(v) for v in anchors_px.detach().float().cpu().reshape(-1).tolist()]
+    assert len(ap) == 2 * na and na <= 4
+    for i in range(8):
+        y.anchors_px[i] = ap[i] if i < len(ap) else 0.0
+    y.stride = float(stride)
+    y.z = z.data_ptr()
+    y.z_rows, y.z_off = int(z_rows), int(z_off)
+    y.nms_workspace = nms_ws.ws_ptr if nms_ws is not None else None
+    y.conf_thres = float(conf_thres)
+    y.multi_label = 1 if (multi_label and no - 5 > 1) else 0
+    return y
+
+
 def window_weights(w64, window):
     """[O,C,kh,kw] -> [O, window*C, kh, 1]: the kw taps of a filter row laid side by side (zeros for kx >= kw), matching
     CvbConvDesc.w_window (k = ky*window*C + kx*C + c)."""
@@ -138,7 +168,10 @@ class ConvPlan:
     """Owns a CvbConvPlan handle (host-side TMA descriptors + launch shape) and keeps its tensors alive."""
 
     def __init__(self, inp, out, weights, bias, k, stride=1, pad=0, dilation=1, act=None, residual=None,
-                 up_partial=None, block_n=0, sm_limit=0, keepalive=(), w_window=0, no_resident=0, residual_before_act=0, halo=0, residual_scale=1.0):
+                 up_partial=None, block_n=0, sm_limit=0, keepalive=(), w_window=0, no_resident=0, residual_before_act=0, halo=0, residual_scale=1.0,
+                 yolo=None):
+        """yolo: a CvbYoloDecode -> the conv's epilogue is the YOLOv5 decode (out_kind CVB_OUT_YOLO, see include/cvb200.h); `out` then only
+        carries B/H/W with C = na * 128 and `weights` / `bias` must come from pack_yolo_head_weights."""
         d = CvbConvDesc()
         d.inp, d.out = inp, out
         d.weights = weights.data_ptr()
@@ -148,6 +181,10 @@ class ConvPlan:
         d.stride, d.pad, d.dilation = stride, pad, dilation
         d.act = ACTS[act]
         d.out_kind = CVB_OUT_F32 if out.plane_stride == 0 else CVB_OUT_SPLIT16
+        if yolo is not None:
+            d.out_kind = CVB_OUT_YOLO
+            d.yolo = ctypes.pointer(yolo)
+            self._yolo = yolo  # (the plan copies what it needs at creation; kept for introspection)
         d.residual = residual if residual is not None else null_view()
         d.up_partial = up_partial if up_partial is not None else null_view()
         d.block_n, d.sm_limit = block_n, sm_limit

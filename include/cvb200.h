@@ -40,6 +40,7 @@ extern "C" {
 
 #define CVB_OUT_SPLIT16 0 /* two fp16 planes (hi, lo)          */
 #define CVB_OUT_F32 1     /* plain fp32 NHWC (partials / heads) */
+#define CVB_OUT_YOLO 2    /* fused YOLOv5 decode: the conv writes z rows + NMS histogram / per-row best scores (CvbConvDesc.yolo) */
 
 /* A channel-slice view of an NHWC tensor. */
 typedef struct CvbView {
@@ -62,6 +63,26 @@ typedef struct CvbView {
  *           BN folding algebra src/utils/fuse.py:33-54 (done by the caller when packing weights).
  * Weights: device fp16 [2 planes][cout_pad][kh*kw*cin] with k = (ky*kw + kx)*cin + c  (K-major).
  */
+/*
+ * Fused head: 1x1 detect conv + sigmoid + box decode + NMS pre-pass in ONE kernel (out_kind = CVB_OUT_YOLO).  The conv's epilogue turns
+ * the accumulator of (anchor a, pixel) into the z row the reference builds with permute + sigmoid + two slice writes + cat
+ * (src/models/detects/yolov5_detect.py:42-55) and, when nms_workspace is given, accumulates what cvb_yolo_decode would have (score
+ * histogram, per-row best score) -- the fp32 raw tensor [B,ny,nx,na*no] is never written or re-read.  Same arithmetic as
+ * CVB_OUT_F32 conv + cvb_yolo_decode: bit-identical z.
+ *   weights / bias: packed with ONE ANCHOR PER 128-WIDE N-TILE: row a*128 + o = output channel a*no + o of nn.Conv2d (o < no <= 96, the
+ *   rest zero), i.e. cout_pad = na * 128; `out` only carries B/H/W (C = na * 128); base may be the z pointer.
+ */
+typedef struct CvbYoloDecode {
+  int32_t na, no;          /* anchors per level (<= 4), outputs per anchor (5 + classes, <= 96) */
+  float anchors_px[8];     /* anchor (w, h) in pixels = anchors * stride                        */
+  float stride;
+  float* z;                /* [B, z_rows, no] fp32; this level's rows start at z_off (a * ny * nx + y * nx + x inside the level) */
+  int64_t z_rows, z_off;
+  void* nms_workspace;     /* prepared with cvb_nms_workspace_reset (sized for A = z_rows), or NULL */
+  float conf_thres;
+  int32_t multi_label;
+} CvbYoloDecode;
+
 typedef struct CvbConvDesc {
   CvbView in;           /* split16 input view, C = cin (multiple of 16)              */
   CvbView out;          /* output view, C = cout                                     */
@@ -89,6 +110,7 @@ typedef struct CvbConvDesc {
                            1 / 2 = force "halo" mode where the layer allows it: the 8x16-pixel tile is loaded once per K chunk including
                            the filter halo (2: one box per input map; 1: one box per horizontal tap offset) and every tap is a
                            row-shifted shared-memory descriptor view of it -- up to 6x less L2->SM fill traffic for 3x3 layers. */
+  const CvbYoloDecode* yolo; /* required iff out_kind == CVB_OUT_YOLO */
   float residual_scale; /* out = act(...) + residual_scale * residual (0 is read as 1): the learnable shortcut weight `alpha` of the YOLOv6
                            BottleRep block (src/models/modules/yolo_modules.py:474-492) */
 } CvbConvDesc;

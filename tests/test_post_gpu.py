@@ -180,3 +180,89 @@ def test_coco_pack_on_device(cuda):
     assert n == int(count.sum()) == ids.shape[0]
     assert np.array_equal(rec_ids[:n, 0].cpu().numpy(), ids) and np.array_equal(rec_ids[:n, 1].cpu().numpy(), cats)
     assert np.array_equal(rec_box[:n, :4].cpu().numpy(), xywh) and np.array_equal(rec_box[:n, 4].cpu().numpy(), sc)
+
+
+def _ws_regions(ws, B, A):
+    """(histogram u32 [B,16384], rowmax f32 [B,A]) views of an NmsWorkspace (layout: csrc/internal.h)."""
+    al = lambda x, a: (x + a - 1) // a * a
+    head = al(B * 16384 * 4, 256) + 6 * al(B * 4, 256)
+    rm_off = head + B * (65536 + 4096) * 8
+    off = ws.ws_ptr - ws.ws.data_ptr()
+    raw = ws.ws[off:]
+    hist = raw[:B * 16384 * 4].view(torch.int32).view(B, 16384)
+    rowmax = raw[rm_off:rm_off + B * A * 4].view(torch.float32).view(B, A)
+    return hist, rowmax
+
+
+@pytest.mark.parametrize('B,ny,nx,cin,na,nc,z_off,multi', [
+    (2, 12, 20, 64, 3, 80, 4, True),     # vector copy-out path (16-byte aligned runs)
+    (3, 7, 13, 32, 3, 80, 3, False),     # odd map, misaligned z rows -> scalar copy-out, best-class histogram
+    (2, 20, 20, 128, 3, 80, 0, True),    # the 20x20 level geometry (tile 20x6)
+    (2, 9, 16, 96, 2, 3, 8, True),       # small `no` (8), two anchors
+    (1, 80, 80, 128, 3, 80, 0, True),    # 80x80 level: tile 16x8, several tiles per CTA
+])
+def test_fused_head_conv_decode_equals_conv_then_decode(cuda, B, ny, nx, cin, na, nc, z_off, multi):
+    """CVB_OUT_YOLO (decode as the conv epilogue) == fp32-out conv + cvb_yolo_decode, bit for bit: z rows, NMS histogram and per-row
+    best scores; then the NMS that consumes them returns identical rows."""
+    from cvpytorch_b200 import ops
+    no = nc + 5
+    g = torch.Generator().manual_seed(11 + cin + nx)
+    x = torch.randn(B, cin, ny, nx, generator=g)
+    w = (torch.randn(na * no, cin, 1, 1, generator=g) * (2.5 / cin ** 0.5)).double()
+    b = (torch.randn(na * no, generator=g) * 0.5).double()
+    tin = ops.SplitTensor(B, ny, nx, cin)
+    ops.nchw_to_split(x.cuda(), tin.view())
+    anchors_px = torch.tensor([[10., 13.], [16., 30.], [33., 23.]][:na])
+    A = na * ny * nx + z_off + 7
+    conf = 0.05
+    # (a) two steps
+    ws_a = ops.NmsWorkspace(B, A, nc)
+    ops.nms_reset(ws_a)
+    z_a = torch.zeros(B, A, no, device='cuda')
+    cp = (na * no + 31) // 32 * 32
+    raw = ops.F32Tensor(B, ny, nx, cp)
+    wp, bp = ops.pack_conv_weights(w, b)
+    ops.ConvPlan(tin.view(), raw.view(0, na * no), wp, bp, 1, 1, 0, 1, None).run()
+    ops.yolo_decode(raw.view(0, na * no), na, no, anchors_px.cuda().contiguous(), 8.0, z_a, A, z_off, None, ws_a, conf, multi)
+    # (b) fused
+    ws_b = ops.NmsWorkspace(B, A, nc)
+    ops.nms_reset(ws_b)
+    z_b = torch.zeros(B, A, no, device='cuda')
+    wy, by = ops.pack_yolo_head_weights(w, b, na, no)
+    y = ops.yolo_decode_desc(na, no, anchors_px, 8.0, z_b, A, z_off, ws_b, conf, multi)
+    ops.ConvPlan(tin.view(), ops.CvbView(z_b.data_ptr(), B, ny, nx, na * 128, na * 128, 0), wy, by, 1, 1, 0, 1, None, yolo=y).run()
+    torch.cuda.synchronize()
+    bad = (z_a != z_b).nonzero()
+    assert bad.shape[0] == 0, (bad.shape[0], bad[:8].tolist(), bad[-4:].tolist())
+    assert float(z_b[:, :z_off].abs().max() if z_off else 0.0) == 0.0 and float(z_b[:, z_off + na * ny * nx:].abs().max()) == 0.0
+    ha, ra = _ws_regions(ws_a, B, A)
+    hb, rb = _ws_regions(ws_b, B, A)
+    assert int(ha.sum()) > 0
+    assert torch.equal(ha, hb)
+    assert torch.equal(ra[:, z_off:z_off + na * ny * nx], rb[:, z_off:z_off + na * ny * nx])
+    da = [t.clone() for t in ops.yolo_nms(z_a, ws_a, conf, 0.6, multi, hist_ready=True)]
+    db = [t.clone() for t in ops.yolo_nms(z_b, ws_b, conf, 0.6, multi, hist_ready=True)]
+    torch.cuda.synchronize()
+    for ta, tb in zip(da, db):
+        assert torch.equal(ta, tb)
+    assert int(da[2].sum()) > 0
+
+
+def test_predict_fused_decode_equals_unfused(cuda, monkeypatch):
+    """model.predict with the decode fused into the head convs (default) == the conv + cvb_yolo_decode graph (CVB_FUSED_DECODE=0)."""
+    from cvpytorch_b200 import synth
+    torch.manual_seed(5)
+    x = torch.randn(3, 3, 160, 192).cuda()
+    m1 = synth.build_yolov5s(calibrated=True)
+    det1, idx1, cnt1 = [t.clone() for t in m1.predict(x)]
+    z1 = m1._graph_for(x)['z'].clone()
+    n1 = m1._graph_for(x)['g'].n_convs
+    monkeypatch.setenv('CVB_FUSED_DECODE', '0')
+    m2 = synth.build_yolov5s(calibrated=True)
+    det2, idx2, cnt2 = [t.clone() for t in m2.predict(x)]
+    z2 = m2._graph_for(x)['z'].clone()
+    torch.cuda.synchronize()
+    assert n1 == m2._graph_for(x)['g'].n_convs
+    assert sum(1 for s in m1._graph_for(x)['g'].steps if s[0] == 'fn') + 3 == sum(1 for s in m2._graph_for(x)['g'].steps if s[0] == 'fn')
+    assert torch.equal(z1, z2) and torch.equal(cnt1, cnt2) and torch.equal(idx1, idx2) and torch.equal(det1, det2)
+    assert int(cnt1.sum()) > 0
