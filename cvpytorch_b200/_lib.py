@@ -9,7 +9,8 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int32, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libcvb200.so')
+# CVB_DIAG_LIB=1 (developer tools only) loads the diagnostics build of the same sources (csrc/build.sh diag: cycle counters + CVB_DBG switches)
+LIB_PATH = os.path.join(_HERE, 'libcvb200_diag.so' if os.environ.get('CVB_DIAG_LIB') == '1' else 'libcvb200.so')
 
 CVB_ACT_NONE, CVB_ACT_SILU, CVB_ACT_RELU = 0, 1, 2
 CVB_OUT_SPLIT16, CVB_OUT_F32, CVB_OUT_YOLO = 0, 1, 2

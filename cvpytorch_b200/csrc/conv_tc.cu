@@ -31,6 +31,10 @@
 
 namespace cvb {
 
+#ifndef CVB_DIAG
+#define CVB_DIAG 0  // 1: the per-role cycle counters (cvb_conv_plan_set_profile) and the CVB_DBG switches are compiled in (tools build: libcvb200_diag.so)
+#endif
+constexpr bool kDiag = CVB_DIAG != 0;
 constexpr int kTileM = 128;
 constexpr int kMaxTaps = 9;
 constexpr int kEpiThreads = 256;          // 8 epilogue warps
@@ -47,6 +51,7 @@ struct alignas(64) ConvKArgs {
   CUtensorMap tmO;     // output (5D; plane dim = 1 for fp32)
   CUtensorMap tmR;     // residual (same box as the output tile), loaded by TMA into a staging tile
   int tiles_w, tiles_h, tiles_b, tiles_n;
+  uint32_t mg_n, mg_w, mg_h;   // ceil(2^32 / tiles_{n,w,h}): tile index -> coordinates by multiply-high (0: use a real division)
   int TW, TH, NB;
   int Ho, Wo, Bn;
   int cout;
@@ -105,9 +110,14 @@ struct alignas(64) ConvKArgs {
   float y_anchor[8];           // anchor sizes in pixels: [a * 2 + 0] = w, [a * 2 + 1] = h
   unsigned int* y_hist;        // NMS workspace histogram [B][kNmsBins] (or NULL)
   float* y_rowmax;             // NMS workspace per-row best score [B][y_zrows] (or NULL)
+  uint32_t wait_hint;          // suspend-time hint (ns) of the producer's free-slot waits (CVB_WAIT_HINT, 0 = spin)
   int dbg;                     // diagnostics (CVB_DBG, results are WRONG): bit 0 = no TMA stores, bit 1 = activations loaded only for the first ring pass, bit 2 = epilogue skips the math / staging, bit 5 = fused decode without histogram atomics, bit 6 = without the z copy-out
   long long* prof;             // diagnostics (cvb_conv_plan_set_profile): per-CTA cycle counters of the three pipeline roles, or NULL
 };
+
+// x / d for 0 <= x with x * d < 2^32 (checked on the host, else magic = 0; magic = 1 means d == 1): one multiply-high instead of a
+// ~20-instruction division
+__device__ __forceinline__ int fast_div(int x, int d, uint32_t magic) { return magic == 1u ? x : (magic ? (int)__umulhi((uint32_t)x, magic) : x / d); }
 
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == CVB_ACT_SILU) return __fdividef(x, 1.0f + __expf(-x));
@@ -201,7 +211,10 @@ struct ConvCfg {
   static constexpr int TAIL_BYTES = BLOCK_N * 4 + 64 * 8 + 16;  // bias + barriers + tmem slot
 };
 
-template <int BLOCK_N, int BLOCK_K, bool OUT_F32, bool YOLO>
+// EPI selects a compile-time specialisation of the epilogue (the hot layers run a compact, branch-free instruction stream; the generic
+// stream with its run-time mode checks costs ~40 % more issue slots per tile, and the HBM-bound layers are issue bound in the epilogue):
+//   0 generic   1 act = SiLU, no residual, no up-partial   2 act = SiLU, residual tile by TMA added after the activation
+template <int BLOCK_N, int BLOCK_K, bool OUT_F32, bool YOLO, int EPI = 0>
 __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_kernel(const __grid_constant__ ConvKArgs a) {
   using Cfg = ConvCfg<BLOCK_N, BLOCK_K, OUT_F32>;
   constexpr int SWZ = Cfg::SWZ;
@@ -212,6 +225,10 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
   constexpr int OUT_ROW_BYTES = Cfg::OUT_ROW_BYTES;
   constexpr uint32_t IDESC = make_idesc_f16_f32(kTileM, BLOCK_N);
   constexpr int EPI_THREADS = YOLO ? kYoloEpiThreads : kEpiThreads;
+  static_assert(EPI == 0 || (!OUT_F32 && !YOLO), "epilogue specialisations exist for the split16 output only");
+  // run-time mode flags, folded to constants in the specialised kernels
+  const bool resid_tma = EPI == 2 ? true : (EPI == 1 ? false : a.resid_tma != 0);
+  const int act_mode = EPI != 0 ? CVB_ACT_SILU : a.act;
 
   // the kernel has no static shared memory, so the dynamic window starts at offset 0 of the CTA's (1024-byte aligned)
   // allocation; checked once instead of spending 1 KB of slack (which is what lets some two-CTA plans fit in 113 KB)
@@ -221,13 +238,14 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
     printf("conv_tc_kernel: dynamic shared memory is not 1024-byte aligned\n");
     __trap();
   }
+  const int dbg = kDiag ? a.dbg : 0;  // diagnostics switches: compiled out of the product library
   const int STAGES = a.stages;
   const int stage_bytes = a.halo ? (int)a.a_slot_bytes : (a.b_resident ? 2 * A_BYTES : STAGE_BYTES);
   uint8_t* stage_base = smem;
   uint8_t* b_res = smem + STAGES * stage_bytes;                                  // resident weights: k_iters x {hi, lo} tiles (halo mode: or the weight ring)
   uint8_t* out_stage0 = b_res + (a.b_resident ? a.taps * a.chunks * 2 * B_BYTES : (a.halo ? a.sb_stages * 2 * B_BYTES : 0));
   uint8_t* res_stage = out_stage0 + (YOLO ? kYoloStageBytes + kNmsBins * 4 + kYoloBiasBytes : a.out_bufs * Cfg::OUT_STAGE_BYTES);  // residual tile (same layout as an output tile)
-  float* bias_s = reinterpret_cast<float*>(res_stage + (a.resid_tma ? Cfg::OUT_STAGE_BYTES : 0));  // (fused decode: staging tile + histogram instead of output tiles)
+  float* bias_s = reinterpret_cast<float*>(res_stage + (resid_tma ? Cfg::OUT_STAGE_BYTES : 0));  // (fused decode: staging tile + histogram instead of output tiles)
   uint64_t* bars = reinterpret_cast<uint64_t*>(bias_s + BLOCK_N);
   const int SB = a.halo ? a.sb_stages : 0;
   uint64_t* full = bars;
@@ -247,7 +265,7 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
     tma_prefetch_desc(&a.tmA[0]);
     tma_prefetch_desc(&a.tmB);
     if constexpr (!YOLO) tma_prefetch_desc(&a.tmO);
-    if (a.resid_tma) tma_prefetch_desc(&a.tmR);
+    if (resid_tma) tma_prefetch_desc(&a.tmR);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -296,8 +314,8 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (elect_one() && !(a.dbg & 16)) {
-      const bool prof_on = a.prof != nullptr;
+    if (elect_one() && !(dbg & 16)) {
+      const bool prof_on = kDiag && a.prof != nullptr;
       long long prof_acc[4] = {0, 0, 0, 0};
       const long long prof_t0 = prof_on ? clock64() : 0;
       int stage = 0;
@@ -318,18 +336,15 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
         int sb = 0;
         uint32_t phase_b = 0;
         for (int tile = t_begin; tile < t_end; tile += t_step) {
-          const int nt = tile % a.tiles_n;
-          const int mt = tile / a.tiles_n;
-          const int wt = mt % a.tiles_w;
-          const int t2 = mt / a.tiles_w;
-          const int ht = t2 % a.tiles_h;
-          const int bt = t2 / a.tiles_h;
+          const int mt = fast_div(tile, a.tiles_n, a.mg_n), nt = tile - mt * a.tiles_n;
+          const int t2 = fast_div(mt, a.tiles_w, a.mg_w), wt = mt - t2 * a.tiles_w;
+          const int bt = fast_div(t2, a.tiles_h, a.mg_h), ht = t2 - bt * a.tiles_h;
           const int w0 = wt * a.TW, h0 = ht * a.TH, b0 = bt * a.NB, n0 = nt * BLOCK_N;
           for (int ck = 0; ck < a.chunks; ++ck) {
             int t = 0;
             for (int c = 0; c < a.n_copies; ++c) {
-              CVB_PROF_WAIT(0, mbar_wait(&empty[stage], phase ^ 1, 100 + stage));
-              if ((a.dbg & 2) && (tile != t_begin)) {
+              CVB_PROF_WAIT(0, mbar_wait(&empty[stage], phase ^ 1, 100 + stage, a.wait_hint));
+              if ((dbg & 2) && (tile != t_begin)) {
                 mbar_arrive(&full[stage]);  // diagnostics: no data movement after the first tile
               } else {
               mbar_expect_tx(&full[stage], 2 * a.cp_bytes[c]);
@@ -344,7 +359,7 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
               }
               if (!a.b_resident) {
                 for (int j = 0; j < a.cp_ntaps[c]; ++j, ++t) {
-                  CVB_PROF_WAIT(1, mbar_wait(&emptyB[sb], phase_b ^ 1, 150 + sb));
+                  CVB_PROF_WAIT(1, mbar_wait(&emptyB[sb], phase_b ^ 1, 150 + sb, a.wait_hint));
                   mbar_expect_tx(&fullB[sb], 2 * B_BYTES);
                   tma_load_3d(&a.tmB, &fullB[sb], b_res + sb * 2 * B_BYTES, a.tap_w[t] * a.cin + ck * BLOCK_K, n0, 0);
                   if (++sb == SB) {
@@ -358,19 +373,16 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
         }
       } else
       for (int tile = t_begin; tile < t_end; tile += t_step) {
-        const int nt = tile % a.tiles_n;
-        const int mt = tile / a.tiles_n;
-        const int wt = mt % a.tiles_w;
-        const int t2 = mt / a.tiles_w;
-        const int ht = t2 % a.tiles_h;
-        const int bt = t2 / a.tiles_h;
+        const int mt = fast_div(tile, a.tiles_n, a.mg_n), nt = tile - mt * a.tiles_n;
+        const int t2 = fast_div(mt, a.tiles_w, a.mg_w), wt = mt - t2 * a.tiles_w;
+        const int bt = fast_div(t2, a.tiles_h, a.mg_h), ht = t2 - bt * a.tiles_h;
         const int w0 = wt * a.TW, h0 = ht * a.TH, b0 = bt * a.NB, n0 = nt * BLOCK_N;
         for (int tap = 0; tap < a.taps; ++tap) {
           const CUtensorMap* mapA = &a.tmA[a.tap_map[tap]];
           const int cw = w0 + a.tap_dw[tap];
           const int ch = h0 + a.tap_dh[tap];
           for (int ck = 0; ck < a.chunks; ++ck) {
-            CVB_PROF_WAIT(0, mbar_wait(&empty[stage], phase ^ 1, 100 + stage));
+            CVB_PROF_WAIT(0, mbar_wait(&empty[stage], phase ^ 1, 100 + stage, a.wait_hint));
             mbar_expect_tx(&full[stage], tx_bytes);
             uint8_t* sb = stage_base + stage * stage_bytes;
             tma_load_5d(mapA, &full[stage], sb, ck * BLOCK_K, cw, ch, b0, 0);  // fused: both planes in one box
@@ -395,7 +407,7 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     if (elect_one()) {
-      const bool prof_on = a.prof != nullptr;
+      const bool prof_on = kDiag && a.prof != nullptr;
       long long prof_acc[4] = {0, 0, 0, 0};
       const long long prof_t0 = prof_on ? clock64() : 0;
       int stage = 0;
@@ -418,7 +430,7 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
       const bool pair = a.mma_pair != 0 && 2 * BLOCK_N <= 256, resident = a.b_resident != 0, kskip = a.kskip != 0;
       const int ksteps = KSTEPS - a.kskip;
       const int chunks = a.chunks;
-      const bool nowait = (a.dbg & 8) != 0;
+      const bool nowait = (dbg & 8) != 0;
       // The issuing thread is instruction-latency bound (~7 cycles per dependent instruction, one warp): a K chunk of a narrow tile is
       // only 4-8 MMAs of ~50 cycles each, so the loop around them must stay within a few dozen instructions.  The loop nest is
       // therefore instantiated per mode (PAIR / KSKIP / single main accumulator) instead of branching per tap, ring positions are
@@ -529,7 +541,7 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
       } else {
         run_tiles(F_{}, std::integral_constant<bool, false>{}, F_{});
       }
-      if (a.dbg & 8) {  // diagnostics: the issuer ran without waiting for anybody; drain the tensor pipe before the teardown
+      if (dbg & 8) {  // diagnostics: the issuer ran without waiting for anybody; drain the tensor pipe before the teardown
         umma_commit(rfull);
         mbar_wait(rfull, 0, 999);
       }
@@ -554,7 +566,7 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
     const int nb = r2 / a.TH;
     constexpr int CW = OUT_GROUP_CH / 2;  // columns per warp per group (32, or 16 for 32-wide groups)
     constexpr int SUB = (BLOCK_N <= 64 && CW > 16) ? 16 : CW;  // columns held in registers at a time
-    const bool prof_on = a.prof != nullptr;
+    const bool prof_on = kDiag && a.prof != nullptr;
     long long prof_acc[6] = {0, 0, 0, 0, 0, 0};
     const long long prof_t0 = prof_on ? clock64() : 0;
     int acc = 0;
@@ -568,9 +580,9 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
     constexpr int kGroups = BLOCK_N / OUT_GROUP_CH;
     // residual tile of (tile, group): two TMA boxes (hi, lo) with the output tile's geometry; OOB parts are zero-filled
     auto issue_residual = [&](int tile_i, int g) {
-      const int nt_ = tile_i % a.tiles_n, mt_ = tile_i / a.tiles_n;
-      const int wt_ = mt_ % a.tiles_w, t2_ = mt_ / a.tiles_w;
-      const int ht_ = t2_ % a.tiles_h, bt_ = t2_ / a.tiles_h;
+      const int mt_ = fast_div(tile_i, a.tiles_n, a.mg_n), nt_ = tile_i - mt_ * a.tiles_n;
+      const int t2_ = fast_div(mt_, a.tiles_w, a.mg_w), wt_ = mt_ - t2_ * a.tiles_w;
+      const int bt_ = fast_div(t2_, a.tiles_h, a.mg_h), ht_ = t2_ - bt_ * a.tiles_h;
       const int c0 = nt_ * BLOCK_N + g * OUT_GROUP_CH;
       mbar_expect_tx(rfull, (uint32_t)(2 * a.rows_valid * OUT_ROW_BYTES));
       tma_load_5d(&a.tmR, rfull, res_stage, c0, wt_ * a.TW, ht_ * a.TH, bt_ * a.NB, 0);
@@ -601,17 +613,20 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
       for (int i = tid_e; i < a.tiles_n * BLOCK_N; i += EPI_THREADS)
         y_bias[i] = ((i & (BLOCK_N - 1)) < a.y_no && i < a.bias_len) ? a.bias[i] : -CUDART_INF_F;
     }
-    if (a.resid_tma && tid_e == 0 && t_begin < t_end) issue_residual(t_begin, 0);
-    for (int tile = (a.dbg & 16) ? t_end : t_begin; tile < t_end; tile += t_step) {
-      const int nt = tile % a.tiles_n;
-      const int mt = tile / a.tiles_n;
-      const int wt = mt % a.tiles_w;
-      const int t2 = mt / a.tiles_w;
-      const int ht = t2 % a.tiles_h;
-      const int bt = t2 / a.tiles_h;
+    if (resid_tma && tid_e == 0 && t_begin < t_end) issue_residual(t_begin, 0);
+    // per-thread pixel coordinates are needed only by the operands read with per-thread loads (up-partial, non-TMA residual) and by the
+    // fused decode; the plain path knows its tile through the TMA store coordinates alone
+    const bool need_rows = EPI != 0 ? false : (YOLO || a.up != nullptr || (a.resid != nullptr && !resid_tma));
+    for (int tile = (dbg & 16) ? t_end : t_begin; tile < t_end; tile += t_step) {
+      const int mt = fast_div(tile, a.tiles_n, a.mg_n);
+      const int nt = tile - mt * a.tiles_n;
+      const int t2 = fast_div(mt, a.tiles_w, a.mg_w);
+      const int wt = mt - t2 * a.tiles_w;
+      const int bt = fast_div(t2, a.tiles_h, a.mg_h);
+      const int ht = t2 - bt * a.tiles_h;
       const int w0 = wt * a.TW, h0 = ht * a.TH, b0 = bt * a.NB, n0 = nt * BLOCK_N;
       const int ow = w0 + tw, oh = h0 + th, ob = b0 + nb;
-      const bool valid = (row < a.rows_valid) && (ow < a.Wo) && (oh < a.Ho) && (ob < a.Bn);
+      const bool valid = need_rows && (row < a.rows_valid) && (ow < a.Wo) && (oh < a.Ho) && (ob < a.Bn);
 
       if (!YOLO && n0 != cur_n0) {
         named_bar_sync(1, EPI_THREADS);
@@ -623,10 +638,10 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
         cur_n0 = n0;
       }
       const float* up_row = nullptr;
-      if (a.up != nullptr && valid)
+      if (EPI == 0 && a.up != nullptr && valid)
         up_row = a.up + ((size_t)((size_t)ob * a.up_H + (oh >> 1)) * a.up_W + (ow >> 1)) * a.up_pitch + n0;
       const __half* res_row = nullptr;
-      if (a.resid != nullptr && valid) res_row = a.resid + ((size_t)((size_t)ob * a.Ho + oh) * a.Wo + ow) * a.resid_pitch + n0;
+      if (EPI == 0 && a.resid != nullptr && valid) res_row = a.resid + ((size_t)((size_t)ob * a.Ho + oh) * a.Wo + ow) * a.resid_pitch + n0;
 
       const uint32_t t_set = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * (n_main + 1) * BLOCK_N);
 
@@ -672,11 +687,11 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
         float* srow = y_stage + row * 85;
         const uint32_t hist_s32 = smem_u32(hist_s);
         const bool any_live = __any_sync(0xffffffffu, obj > conf);  // background-only warps skip the score pass
-        const bool multi = a.y_multi != 0 && !(a.dbg & 32);
+        const bool multi = a.y_multi != 0 && !(dbg & 32);
 #pragma unroll 1
         for (int cg = 0; cg < 2; ++cg) {  // this warp's 16-column chunks: part and part + 3 (columns >= 96 are padding)
           const int col = (part + 3 * cg) * 16;
-          if (col >= no || (a.dbg & 4)) break;
+          if (col >= no || (dbg & 4)) break;
           uint32_t vc[16], vm[16];
           tmem_ld_32x16(t_set + (uint32_t)(BLOCK_N + col), vc);
           tmem_ld_32x16(t_set + (uint32_t)col, vm);
@@ -743,11 +758,11 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
           // the group's valid tile rows [r0, r1) are consecutive z rows: one bulk copy
           const int r0 = grp * 64;
           const int r1 = min(min(r0 + 64, a.rows_valid), npix - w0);
-          if (r1 > r0 && !(a.dbg & 64)) {
+          if (r1 > r0 && !(dbg & 64)) {
             float* gdst = a.yz + (lvl_row0 + (size_t)(w0 + r0)) * (size_t)no;
             const float* ssrc = y_stage + (size_t)r0 * 85;
             const int nfl = (r1 - r0) * no;
-            if (no == 85 && (reinterpret_cast<uintptr_t>(gdst) & 15) == 0 && (nfl & 3) == 0 && !(a.dbg & 128)) {
+            if (no == 85 && (reinterpret_cast<uintptr_t>(gdst) & 15) == 0 && (nfl & 3) == 0 && !(dbg & 128)) {
               if (gtid == 0) {
                 bulk_store_1d(gdst, ssrc, (uint32_t)nfl * 4u);
                 tma_store_commit();
@@ -772,8 +787,8 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
       for (int g = 0; g < BLOCK_N / OUT_GROUP_CH; ++g) {
         const int col0 = g * OUT_GROUP_CH + half * CW;
         const bool ch_ok = (n0 + col0 + CW <= a.cout);
-        const bool has_up = (up_row != nullptr) && ch_ok;
-        const bool has_res = a.resid_tma ? true : ((res_row != nullptr) && ch_ok);
+        const bool has_up = EPI != 0 ? false : ((up_row != nullptr) && ch_ok);
+        const bool has_res = EPI == 1 ? false : (resid_tma ? true : ((res_row != nullptr) && ch_ok));
         // the thread's CW columns are processed in sub-chunks of SUB columns (SUB < CW only for the small-N kernels that must
         // stay within the two-CTAs-per-SM register budget).  Epilogue operands that do not depend on the accumulator are
         // requested first, so their latency hides behind the accumulator wait / barrier / tcgen05.ld below
@@ -786,7 +801,7 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
 #pragma unroll
             for (int j = 0; j < SUB / 4; ++j) upv[j] = __ldg(p + j);
           }
-          if (has_res && !a.resid_tma) {
+          if (has_res && !resid_tma) {
             const uint4* ph = reinterpret_cast<const uint4*>(res_row + col);
             const uint4* pl = reinterpret_cast<const uint4*>(res_row + a.resid_plane + col);
 #pragma unroll
@@ -798,7 +813,7 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
         };
         load_extras(0);
         if constexpr (!OUT_F32) {
-          if (a.resid_tma) {
+          if (resid_tma) {
             mbar_wait(rfull, res_phase, 500);
             res_phase ^= 1;
           }
@@ -808,20 +823,26 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
           tc_fence_after();
         }
         // the staging tile written now was last read by the TMA store issued out_bufs groups ago
+        long long pt0 = prof_on ? clock64() : 0;
         if (tid_e == 0) {
           if (a.out_bufs == 2) tma_store_wait_read1();
           else tma_store_wait_read0();
         }
         named_bar_sync(1, EPI_THREADS);
+        if (prof_on) {
+          const long long t = clock64();
+          prof_acc[1] += t - pt0;  // staging tile free (TMA store read + barrier)
+          pt0 = t;
+        }
         uint8_t* out_stage = out_stage0 + (gcount & (a.out_bufs - 1)) * Cfg::OUT_STAGE_BYTES;
         ++gcount;
 #pragma unroll
         for (int sc = 0; sc < CW / SUB; ++sc) {
-          if (a.dbg & 4) break;  // diagnostics: no tcgen05.ld / math / staging
+          if (dbg & 4) break;  // diagnostics: no tcgen05.ld / math / staging
           const int col = col0 + sc * SUB;
           if (sc > 0) load_extras(sc);
           if constexpr (!OUT_F32) {
-            if (a.resid_tma) {  // same swizzled chunk addressing as the output staging tile below
+            if (resid_tma) {  // same swizzled chunk addressing as the output staging tile below
               const uint8_t* rh = res_stage + row * OUT_ROW_BYTES;
 #pragma unroll
               for (int j = 0; j < SUB / 8; ++j) {
@@ -836,19 +857,31 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
           }
           float f[SUB];
           {
-            uint32_t v[SUB];
-            tmem_ld_cols<SUB>(t_set + (uint32_t)(n_main * BLOCK_N + col), v);  // cross terms first (smallest magnitude)
+            uint32_t v[SUB], vx[SUB];
+            const float gain = a.rz_gain;
+            tmem_ld_cols<SUB>(t_set + (uint32_t)(n_main * BLOCK_N + col), vx);  // cross terms (smallest magnitude: added first)
+            tmem_ld_cols<SUB>(t_set + (uint32_t)col, v);                         // both loads in flight, one wait
             tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < SUB; ++j) f[j] = __uint_as_float(v[j]);
-            const float gain = a.rz_gain;
-            for (int r = 0; r < n_main; ++r) {
+            for (int j = 0; j < SUB; ++j) f[j] = fmaf(__uint_as_float(v[j]), gain, __uint_as_float(vx[j]));
+#pragma unroll 1
+            for (int r = 1; r < n_main; ++r) {  // long accumulation chains only (n_main > 1)
               tmem_ld_cols<SUB>(t_set + (uint32_t)(r * BLOCK_N + col), v);
               tmem_ld_wait();
 #pragma unroll
               for (int j = 0; j < SUB; ++j) f[j] = fmaf(__uint_as_float(v[j]), gain, f[j]);
             }
           }
+          float bv[SUB];  // bias of this thread's columns: 16-byte shared-memory loads
+#pragma unroll
+          for (int j = 0; j < SUB / 4; ++j) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + col + 4 * j);
+            bv[4 * j] = b4.x;
+            bv[4 * j + 1] = b4.y;
+            bv[4 * j + 2] = b4.z;
+            bv[4 * j + 3] = b4.w;
+          }
+          if (dbg & 256) continue;  // diagnostics: tcgen05.ld only
           if (has_up) {
 #pragma unroll
             for (int j = 0; j < SUB / 4; ++j) {
@@ -875,22 +908,29 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
               }
             }
           }
-          const bool rf = a.resid_first != 0;
-          if (a.act == CVB_ACT_SILU) {
+          const bool rf = EPI != 0 ? false : (a.resid_first != 0);
+          if (act_mode == CVB_ACT_SILU) {
 #pragma unroll
             for (int j = 0; j < SUB; ++j) {
-              const float t = f[j] + bias_s[col + j];
+              const float t = f[j] + bv[j];
               f[j] = rf ? silu_fast(t + rsum[j]) : silu_fast(t) + rsum[j];
             }
-          } else if (a.act == CVB_ACT_RELU) {
+          } else if (act_mode == CVB_ACT_RELU) {
 #pragma unroll
             for (int j = 0; j < SUB; ++j) {
-              const float t = f[j] + bias_s[col + j];
+              const float t = f[j] + bv[j];
               f[j] = rf ? fmaxf(t + rsum[j], 0.0f) : fmaxf(t, 0.0f) + rsum[j];
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < SUB; ++j) f[j] = f[j] + bias_s[col + j] + rsum[j];
+            for (int j = 0; j < SUB; ++j) f[j] = f[j] + bv[j] + rsum[j];
+          }
+          if (dbg & 512) {  // diagnostics: no conversion / staging stores (the results stay live through a dummy dependency)
+            float acc_d = 0.0f;
+#pragma unroll
+            for (int j = 0; j < SUB; ++j) acc_d += f[j];
+            if (acc_d == 123.456f) bias_s[0] = acc_d;
+            continue;
           }
           if constexpr (OUT_F32) {
             // row = 32 fp32 = 128 B = 8 chunks of 16 B, 128B swizzle: chunk ^= row & 7; this warp owns chunks half*4 .. +3
@@ -919,19 +959,30 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
           }
         }
         fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+        if (prof_on) {
+          const long long t = clock64();
+          prof_acc[2] += t - pt0;  // tcgen05.ld + conversion + staging
+          pt0 = t;
+        }
         named_bar_sync(1, EPI_THREADS);
+        if (prof_on) {
+          const long long t = clock64();
+          prof_acc[3] += t - pt0;  // barrier after the conversion
+          pt0 = t;
+        }
         if (tid_e == 0) {
           const int c0 = n0 + g * OUT_GROUP_CH;
-          if (c0 < a.cout && !(a.dbg & 1)) {
+          if (c0 < a.cout && !(dbg & 1)) {
             tma_store_5d(&a.tmO, out_stage, c0, w0, h0, b0, 0);
             if constexpr (!OUT_F32) tma_store_5d(&a.tmO, out_stage + Cfg::OUT_PLANE_BYTES, c0, w0, h0, b0, 1);
           }
           tma_store_commit();
-          if (a.resid_tma) {  // every epilogue thread has consumed the residual tile (barrier above): fetch the next one
+          if (resid_tma) {  // every epilogue thread has consumed the residual tile (barrier above): fetch the next one
             if (g + 1 < kGroups) issue_residual(tile, g + 1);
             else if (tile + t_step < t_end) issue_residual(tile + t_step, 0);
           }
         }
+        if (prof_on) prof_acc[4] += clock64() - pt0;  // store issue
       }
       // all tcgen05.ld of this accumulator set are complete -> hand it back to the MMA warp
       tc_fence_before();
@@ -969,23 +1020,24 @@ struct KernelEntry {
   int stage_bytes, out_stage_bytes, tail_bytes;
 };
 
-template <int BN, int BK, bool F32, bool YOLO = false>
+template <int BN, int BK, bool F32, bool YOLO = false, int EPI = 0>
 static KernelEntry entry() {
   using Cfg = ConvCfg<BN, BK, F32>;
-  return KernelEntry{reinterpret_cast<const void*>(&conv_tc_kernel<BN, BK, F32, YOLO>), Cfg::STAGE_BYTES, Cfg::OUT_STAGE_BYTES,
+  return KernelEntry{reinterpret_cast<const void*>(&conv_tc_kernel<BN, BK, F32, YOLO, EPI>), Cfg::STAGE_BYTES, Cfg::OUT_STAGE_BYTES,
                      Cfg::TAIL_BYTES};
 }
 
-static bool lookup_kernel(int bn, int bk, bool f32, KernelEntry* e, bool yolo = false) {
+static bool lookup_kernel(int bn, int bk, bool f32, KernelEntry* e, bool yolo = false, int epi = 0) {
   if (yolo) {  // fused-decode epilogue: one anchor per 128-wide n-tile
     if (bn == 128 && bk == 32) { *e = entry<128, 32, true, true>(); return true; }
     if (bn == 128 && bk == 64) { *e = entry<128, 64, true, true>(); return true; }
     return false;
   }
-#define CVB_CASE(BN, BK)                               \
-  if (bn == BN && bk == BK) {                          \
-    *e = f32 ? entry<BN, BK, true>() : entry<BN, BK, false>(); \
-    return true;                                       \
+#define CVB_CASE(BN, BK)                                                                                          \
+  if (bn == BN && bk == BK) {                                                                                     \
+    *e = f32 ? entry<BN, BK, true>()                                                                              \
+             : (epi == 1 ? entry<BN, BK, false, false, 1>() : (epi == 2 ? entry<BN, BK, false, false, 2>() : entry<BN, BK, false>())); \
+    return true;                                                                                                  \
   }
   CVB_CASE(32, 16) CVB_CASE(32, 32) CVB_CASE(32, 64)
   CVB_CASE(64, 16) CVB_CASE(64, 32) CVB_CASE(64, 64)
@@ -1430,6 +1482,17 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   a.tiles_h = ceil_div(Ho, TH);
   a.tiles_b = ceil_div(out.B, NB);
   a.tiles_n = ceil_div(cout, bn);
+  {
+    const unsigned long long total_t = (unsigned long long)a.tiles_w * a.tiles_h * a.tiles_b * a.tiles_n;
+    auto magic = [&](int dv) -> uint32_t {  // exact for 0 <= x <= total_t when x * dv < 2^32
+      if (dv <= 1) return 1u;  // sentinel: x / 1
+      if (total_t * (unsigned long long)dv >= 0xFFFFFFFFULL) return 0u;
+      return (uint32_t)((0x100000000ULL + (unsigned long long)dv - 1) / (unsigned long long)dv);
+    };
+    a.mg_n = magic(a.tiles_n);
+    a.mg_w = magic(a.tiles_w);
+    a.mg_h = magic(a.tiles_h);
+  }
   a.Ho = Ho;
   a.Wo = Wo;
   a.Bn = out.B;
@@ -1712,10 +1775,28 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
   if (use_halo) p->smem = hc.smem;
   if (yolo) p->smem = ke.tail_bytes + kYoloStageBytes + kNmsBins * 4 + kYoloBiasBytes + stages * (a_stage + b_stage);
   p->fn = ke.fn;
+  {
+    // compile-time specialised epilogues for the two hot modes (same tile / smem geometry as the generic kernel picked above)
+    static const bool spec_on = [] { const char* e = getenv("CVB_EPI_SPEC"); return !(e && atoi(e) == 0); }();  // A/B knob
+    int epi = 0;
+    if (spec_on && !f32 && !yolo && d->act == CVB_ACT_SILU && !d->up_partial.base) {
+      if (!d->residual.base) epi = 1;
+      else if (a.resid_tma && !a.resid_first) epi = 2;
+    }
+    if (epi) {
+      KernelEntry k2;
+      if (lookup_kernel(bn, bk, f32, &k2, false, epi)) p->fn = k2.fn;
+    }
+  }
   p->threads = yolo ? 64 + kYoloEpiThreads : kThreads;
   {
     const char* e = getenv("CVB_DBG");  // diagnostics only (tools/conv_pipeline_profile.py): results are wrong when set
     a.dbg = e ? atoi(e) : 0;
+    static const int hint = [] {
+      const char* h = getenv("CVB_WAIT_HINT");  // tuning knob: ns the producer may sleep per free-slot wait (default 0 = spin)
+      return h ? atoi(h) : 0;
+    }();
+    a.wait_hint = (uint32_t)(hint > 0 ? hint : 0);
   }
 
   static std::mutex mu;

@@ -44,13 +44,24 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity
       : "memory");
   return ok;
 }
+// same with a suspend-time hint (ns): the thread may sleep in hardware up to that long before the instruction returns false
+__device__ __forceinline__ uint32_t mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(hint)
+      : "memory");
+  return ok;
+}
 // `tag` identifies the waiter in the watchdog message (printed only when built with -DCVB_WATCHDOG=2: the printf call site costs
 // ~30 instructions and a stack frame per inlined wait, and the single-thread producer / MMA loops are instruction-latency bound).
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+// `hint` > 0: long waits (a producer waiting for a free ring slot) sleep in hardware instead of spinning on the issue port.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag, uint32_t hint = 0) {
 #if CVB_WATCHDOG
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!(hint ? mbar_try_wait_hint(bar, parity, hint) : mbar_try_wait(bar, parity))) {
     if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz: trap instead of hanging the GPU
 #if CVB_WATCHDOG >= 2
       printf("[cvb200] mbarrier watchdog: block %d thread %d tag %d parity %u\n", (int)blockIdx.x, (int)threadIdx.x, tag, parity);
@@ -59,7 +70,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int ta
     }
   }
 #else
-  while (!mbar_try_wait(bar, parity)) {
+  while (!(hint ? mbar_try_wait_hint(bar, parity, hint) : mbar_try_wait(bar, parity))) {
   }
 #endif
   (void)tag;

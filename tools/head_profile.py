@@ -6,6 +6,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+os.environ['CVB_DIAG_LIB'] = '1'  # the diagnostics build (csrc/build.sh diag)
 import torch  # noqa: E402
 
 from cvpytorch_b200 import _lib, ops  # noqa: E402
