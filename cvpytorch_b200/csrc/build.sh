@@ -14,5 +14,5 @@ fi
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC,-O3 --shared
        -I"$HERE/../../include" -lcudart)
-"$NVCC" "${FLAGS[@]}" "${EXTRA[@]}" "$@" -o "$OUT" "$HERE/api.cu" "$HERE/conv_tc.cu" "$HERE/aux_kernels.cu" "$HERE/nms.cu"
+"$NVCC" "${FLAGS[@]}" "${EXTRA[@]}" "$@" -o "$OUT" "$HERE/api.cu" "$HERE/conv_tc.cu" "$HERE/aux_kernels.cu" "$HERE/nms.cu" "$HERE/train_kernels.cu"
 echo "built $OUT"

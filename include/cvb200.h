@@ -324,6 +324,35 @@ int cvb_letterbox_u8(const uint8_t* const* src_ptrs, const int32_t* geom, int32_
 int cvb_coco_pack(const float* rows, int32_t B, int32_t M, int32_t row_stride, const int32_t* count, const int64_t* image_ids,
                   const int32_t* id2category, int32_t num_classes, int64_t* rec_ids, float* rec_box, int32_t* total, void* stream);
 
+/*
+ * Training step of the YOLOX C3 block (BASELINE.json configs[3]): one  BaseConv = nn.Conv2d(bias=False) ->
+ * nn.BatchNorm2d (batch statistics) -> SiLU  (src/models/modules/yolox_modules.py:35-55) forward and backward, i.e. what
+ * trainer.py:177-207 gets from cuDNN / ATen autograd, as bf16 tcgen05 implicit GEMMs + element-wise passes (csrc/train_kernels.cu).
+ * All activations / gradients: device bf16 NHWC, dense ([B,H,W,C], C a multiple of 64); convolutions k = 1 or 3, stride 1, pad k/2.
+ *
+ * cvb_train_pack_weights: fp32 master weights [cout,cin,k,k] -> w_fwd bf16 [cout][k*k][cin] and w_bwd bf16 [cin][k*k][cout] (taps rotated
+ *   by 180 degrees: the operand of the backward-data convolution).
+ * cvb_train_conv: out[B,H,W,cout] = conv(x[B,H,W,cin], w_packed [cout][k*k][cin]).  Forward: (x, w_fwd).  Backward-data: (dy, w_bwd) with
+ *   cin/cout swapped.  y_prev / bn_stat_prev != NULL: SiLU' epilogue -- the result is multiplied by silu'(y_prev * scale + shift) of the
+ *   layer that produced this conv's input (bn_stat layout below), giving dz of that layer directly.
+ * cvb_train_conv_wgrad: dw[cout][k*k][cin] (fp32, ZEROED BY THE CALLER, accumulated with atomics) += sum over pixels of dy x (shifted x).
+ * cvb_train_bn_stats: batch mean / biased variance of y over npix = B*H*W -> stat [4][C] fp32 = (mean, rstd, scale = gamma*rstd,
+ *   shift = beta - mean*scale); running_mean / running_var (may be NULL) updated like nn.BatchNorm2d (momentum, unbiased variance).
+ *   sums_scratch: [2][C] fp32.
+ * cvb_train_bn_silu_fwd: out = silu(y * scale + shift).
+ * cvb_train_bn_silu_bwd: g = d(loss)/d(out) (or, g_is_dz != 0, already multiplied by silu'): sums [2][C] = (dbeta, dgamma) and
+ *   dy = gamma * rstd * (dz - dbeta / N - xhat * dgamma / N)   (the batch-norm backward of torch.autograd).
+ */
+int cvb_train_pack_weights(const float* w, int32_t cout, int32_t cin, int32_t k, void* w_fwd, void* w_bwd, void* stream);
+int cvb_train_conv(const void* x, int32_t B, int32_t H, int32_t W, int32_t cin, const void* w_packed, int32_t cout, int32_t k, void* out,
+                   const void* y_prev, const float* bn_stat_prev, void* stream);
+int cvb_train_conv_wgrad(const void* x, const void* dy, int32_t B, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t k, float* dw, void* stream);
+int cvb_train_bn_stats(const void* y, int64_t npix, int32_t C, const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
+                       float* running_var, float* sums_scratch, float* stat, void* stream);
+int cvb_train_bn_silu_fwd(const void* y, int64_t npix, int32_t C, const float* stat, void* out, void* stream);
+int cvb_train_bn_silu_bwd(const void* g, int32_t g_is_dz, const void* y, int64_t npix, int32_t C, const float* stat, const float* gamma, float* sums,
+                          void* dy, void* stream);
+
 /* Library info / errors */
 const char* cvb_last_error_string(void);
 int cvb_version(void);

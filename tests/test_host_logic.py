@@ -307,3 +307,20 @@ def test_brick_registration_hook():
     assert set(m.state_dict().keys()) == {'conv.weight', 'bn.weight', 'bn.bias', 'bn.running_mean', 'bn.running_var', 'bn.num_batches_tracked'}
     with pytest.raises(Exception):
         m.eval()(torch.zeros(1, 16, 8, 8))  # CPU tensor: no fallback
+
+
+def test_training_dropin_mirrors_reference_block_and_fails_loudly_on_cpu():
+    """cvpytorch_b200.train.CSPLayer has the reference block's parameter names (tests/golden/c3_train.npz key list, dumped from the reference)
+    and no CPU fallback."""
+    from cvpytorch_b200 import _lib, train as T
+    g = np.load(os.path.join(ROOT, 'tests', 'golden', 'c3_train.npz'))
+    m = T.CSPLayer(128, 128, n=2)
+    assert list(m.state_dict().keys()) == [str(k) for k in g['c3_n2_keys']]
+    m.train()
+    with pytest.raises(_lib.CvbError):
+        m(torch.zeros(1, 128, 8, 8))
+    m.eval()
+    with pytest.raises(RuntimeError):
+        m.conv1(torch.zeros(1, 8, 8, 128, dtype=torch.bfloat16))
+    with pytest.raises(NotImplementedError):
+        T.BaseConv(48, 64, 1, 1)
