@@ -677,6 +677,266 @@ def run_secondary_arm(args):
         dist.destroy_process_group()
 
 
+TRAIN_CFG = dict(cin=128, cout=128, n=3, hw=(80, 80), batch=16,
+                 metric='images/sec YOLOX-s dark3 C3 block (CSPLayer 128->128, n=3, 80x80) training step fwd+bwd+SGD, bf16, bs16 per GPU',
+                 workload='one C3 block of the YOLOX-s backbone (dark3: CSPLayer(128,128,n=3) on the 80x80 map of a 640x640 image), training step: forward + backward '
+                          '+ gradient all-reduce + SGD(momentum) update, bf16 activations / gradients, fp32 master weights; bs16 per GPU = BASELINE.json configs[3] '
+                          "(batch 128 over 8 GPUs); the block is the part of configs[3] built so far (SURVEY.md 8(f) rank 3)")
+
+
+def _train_flops(B, H, W, cin, cout, n):
+    hid = cout // 2
+    npix = B * H * W
+    convs = [(cin, hid, 1), (cin, hid, 1), (2 * hid, cout, 1)] + [(hid, hid, 1), (hid, hid, 3)] * n
+    fwd = sum(2.0 * npix * ci * co * k * k for ci, co, k in convs)
+    return 3.0 * fwd  # forward + backward-data + backward-weight
+
+
+def _train_cpu(steps, B=2):
+    """The oracle's training step (reference block restated, torch.autograd backward) on the host cores: bounded sample."""
+    from oracle import c3_train_oracle as CO
+    c = TRAIN_CFG
+    H, W = c['hw']
+    sd = CO.synthetic_state(c['cin'], c['cout'], c['n'])
+    g = torch.Generator().manual_seed(5)
+    x, G = torch.randn(B, c['cin'], H, W, generator=g), torch.randn(B, c['cout'], H, W, generator=g)
+    cores = pick_cpu_threads(lambda: CO.train_step(x[:1, :, :20, :20], G[:1, :, :20, :20], sd, c['n']))
+    torch.set_num_threads(cores)
+    CO.train_step(x, G, sd, c['n'])
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        CO.train_step(x, G, sd, c['n'])
+    dt = time.perf_counter() - t0
+    return B * steps / dt, cores, dt / steps, f'{steps} steps x bs{B} 80x80 forward+backward of the block, torch {torch.__version__} fp32 autograd, {cores} threads'
+
+
+def run_train_arm(args):
+    """--config c3train: the training step of one YOLOX C3 block on the B200 kernels (cvpytorch_b200/train.py)."""
+    from cvpytorch_b200 import _lib, train as T
+    from oracle import c3_train_oracle as CO  # (parameters only: the seeded state the CPU leg also uses)
+    c = TRAIN_CFG
+    dist, world, rank, local, dev, numa, barrier, max_over_ranks = _dist_setup()
+    B = args.batch or c['batch']
+    H, Wd = c['hw']
+    K, W = args.steps, max(3, args.warmup)
+    m = T.CSPLayer(c['cin'], c['cout'], n=c['n'])
+    m.load_state_dict({k: torch.as_tensor(v) for k, v in CO.synthetic_state(c['cin'], c['cout'], c['n']).items()})
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.eps, mod.momentum = 1e-3, 0.03
+    m.to(dev).train()
+    params = [p for p in m.parameters()]
+    opt = torch.optim.SGD(params, lr=1e-3, momentum=0.9)
+    NBUF = 4
+    gen = torch.Generator().manual_seed(1029 + rank)
+    xs = [torch.randn(B, H, Wd, c['cin'], generator=gen).to(dev).to(torch.bfloat16) for _ in range(NBUF)]   # NHWC bf16: the layout between blocks
+    Gs = [torch.randn(B, H, Wd, c['cout'], generator=gen).to(dev).to(torch.bfloat16) for _ in range(NBUF)]  # stand-in for d(loss)/d(out) of the rest of the net
+
+    def step(i):
+        x = xs[i % NBUF].requires_grad_(True)
+        y = m.forward_nhwc(x)
+        y.backward(Gs[i % NBUF])
+        if world > 1:  # data-parallel gradient all-reduce (one flat bucket: 0.3 M parameters)
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+            flat /= world
+            off = 0
+            for p in params:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+                off += p.numel()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        x.grad = None
+
+    # the whole step (forward, backward, optimiser) as ONE CUDA graph: 100+ launches per step make the eager step CPU-launch bound.
+    # (N > 1 keeps the eager step: the gradient all-reduce sits between backward and the update)
+    graphed = None
+    eager_step = step
+    if args.graph and world == 1:
+        try:
+            sx = xs[0].clone().requires_grad_(True)
+            sG = Gs[0].clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    m.forward_nhwc(sx).backward(sG)
+                    opt.step()
+                    opt.zero_grad(set_to_none=True)
+                    sx.grad = None
+            torch.cuda.current_stream().wait_stream(side)
+            graphed = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graphed):
+                m.forward_nhwc(sx).backward(sG)
+                opt.step()
+                opt.zero_grad(set_to_none=True)
+
+            def step(i):  # noqa: F811
+                sx.detach().copy_(xs[i % NBUF])
+                sG.copy_(Gs[i % NBUF])
+                graphed.replay()
+            for i in range(W):
+                step(i)
+        except Exception as ex:  # noqa: BLE001
+            print(f'[bench] CUDA graph capture of the training step failed ({ex}); timing the eager step', file=sys.stderr)
+            graphed = None
+            step = eager_step
+    if graphed is None:
+        for i in range(W):
+            step(i)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for i in range(K):
+        step(i)
+    t1.record()
+    barrier()
+    total_ms = max_over_ranks(t0.elapsed_time(t1))
+    n0 = _lib.launch_count()
+    eager_step(0)  # (counts the library launches of one step; graph replays do not pass through the C ABI)
+    torch.cuda.synchronize()
+    launches = (_lib.launch_count() - n0) * K
+    clocks = sampler.stop() if rank == 0 else None
+    value = world * B * K / (total_ms / 1e3)
+
+    # the tensor-core kernels alone (forward convs, backward-data, backward-weight of every layer), CUDA events around them
+    def conv_only():
+        x = xs[0]
+        hid = c['cout'] // 2
+        t = torch.randn(B, H, Wd, hid, generator=gen).to(dev).to(torch.bfloat16)  # (host RNG: the device generator is tied to the captured graph)
+        w1 = (torch.randn(hid, c['cin'], 1, 1, generator=gen) * 0.05).to(dev)
+        w3 = (torch.randn(hid, hid, 3, 3, generator=gen) * 0.05).to(dev)
+        wo = (torch.randn(c['cout'], c['cin'], 1, 1, generator=gen) * 0.05).to(dev)
+        wf1, wb1 = T.pack_weights(w1)
+        wf3, wb3 = T.pack_weights(w3)
+        wfo, wbo = T.pack_weights(wo)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(2):  # conv1, conv2: 128 -> 64, 1x1
+            y = T.conv(x, wf1, hid, 1); T.conv(y, wb1, c['cin'], 1); T.conv_wgrad(x, y, 1)
+        for _ in range(c['n']):
+            wf11, wb11 = wf3[:, 4:5, :].contiguous(), wb3[:, 4:5, :].contiguous()
+            y = T.conv(t, wf11, hid, 1); T.conv(y, wb11, hid, 1); T.conv_wgrad(t, y, 1)
+            y = T.conv(t, wf3, hid, 3); T.conv(y, wb3, hid, 3); T.conv_wgrad(t, y, 3)
+        y = T.conv(x, wfo, c['cout'], 1); T.conv(y, wbo, c['cin'], 1); T.conv_wgrad(x, y, 1)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+    conv_only()
+    conv_ms = min(conv_only() for _ in range(3))
+
+    # library baseline on the same GPU (context, not the reference arm): the oracle's block through cuDNN / ATen under bf16 autocast
+    lib_ms = None
+    try:
+        sdg = {k: torch.as_tensor(v).to(dev) for k, v in CO.synthetic_state(c['cin'], c['cout'], c['n']).items()}
+        for k, v in sdg.items():
+            if v.dtype.is_floating_point and 'running_' not in k:
+                v.requires_grad_(True)
+        xn = xs[0].float().permute(0, 3, 1, 2).contiguous().to(memory_format=torch.channels_last)
+        Gn = Gs[0].float().permute(0, 3, 1, 2).contiguous().to(memory_format=torch.channels_last)
+
+        def lib_step():
+            xg = xn.detach().requires_grad_(True)
+            with torch.autocast('cuda', dtype=torch.bfloat16):
+                y = CO.csp_layer(xg, sdg, c['n'])
+            y.backward(Gn.to(y.dtype))
+            for v in sdg.values():
+                v.grad = None
+        for _ in range(3):
+            lib_step()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(10):
+            lib_step()
+        e1.record()
+        torch.cuda.synchronize()
+        lib_ms = e0.elapsed_time(e1) / 10
+    except Exception as ex:  # noqa: BLE001  (context number only)
+        lib_ms = None
+        print(f'[bench] library baseline skipped: {ex}', file=sys.stderr)
+
+    # end to end through the reference-facing module call: pinned host NCHW fp32 block input in, fp32 NCHW output + loss value back to the host
+    hosts = [torch.randn(B, c['cin'], H, Wd, generator=gen).pin_memory() for _ in range(2)]
+    Gn32 = Gs[0].float().permute(0, 3, 1, 2).contiguous()
+    x_in = torch.empty(B, c['cin'], H, Wd, device=dev)
+    loss_h = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def e2e_step(i):
+        x_in.copy_(hosts[i % 2], non_blocking=True)
+        xg = x_in.detach().requires_grad_(True)
+        y = m(xg)
+        loss = (y * Gn32).sum()
+        loss.backward()
+        if world > 1:
+            flat = torch.cat([p.grad.reshape(-1) for p in params])
+            dist.all_reduce(flat)
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        loss_h.copy_(loss.detach(), non_blocking=True)
+    for i in range(W):
+        e2e_step(i)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    if rank == 0:
+        peaks = _peaks()
+        peak_tf = float(peaks.get('bf16_tflops_sustained', 1400.0))
+        hbm = float(peaks.get('hbm_gbs', 6500.0))
+        flops = _train_flops(B, H, Wd, c['cin'], c['cout'], c['n'])
+        ach = flops / conv_ms / 1e9
+        # HBM bound of the conv kernels: every conv reads its input + writes its output once in each of the three passes (bf16)
+        hid = c['cout'] // 2
+        npix = B * H * Wd
+        io = [(c['cin'], hid), (c['cin'], hid), (2 * hid, c['cout'])] + [(hid, hid), (hid, hid)] * c['n']
+        conv_bytes = sum(3 * 2.0 * npix * (ci + co) for ci, co in io)
+        cpu_v, cores, spt, sample = _train_cpu(args.cpu_steps) if (args.cpu_steps > 0 and world == 1) else (None, 0, 0, 'skipped (timed at N=1 only)' if world > 1 else 'skipped')
+        line = {'metric': c['metric'], 'value': round(value, 2), 'unit': 'images/sec', 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': round(total_ms / K, 4),
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16 (fp32 accumulate, fp32 master weights)', 'data': 'synthetic',
+                'config': {'workload': c['workload'], 'global_batch': world * B, 'per_gpu_batch': B, 'parallelism': f'dp{world}', 'cuda_graph': graphed is not None,
+                           'l2': '4 input / output-gradient buffer pairs used round robin (26 MB each: the block working set is L2 resident on B200, as it is inside the full net)',
+                           'collective': 'one NCCL all-reduce of the flat fp32 gradient bucket per step' if world > 1 else 'none (N=1)', 'numa_node': numa},
+                'gpu_launches': int(launches),
+                'e2e': {'value': round(world * B * K / (e2e_ms / 1e3), 2), 'unit': 'images/sec', 'h2d_bytes_per_step': B * c['cin'] * H * Wd * 4, 'd2h_bytes_per_step': 4,
+                        'ms_per_step': round(e2e_ms / K, 4), 'api': 'cvpytorch_b200.train.CSPLayer.__call__ (NCHW fp32 in / out like the reference block) + loss.backward() + optimizer.step(); pinned host input, loss value back'},
+                'clocks': clocks,
+                'roofline': {'bound': 'hbm', 'achieved': round(conv_bytes / conv_ms / 1e6, 1), 'peak': hbm, 'unit': 'GB/s', 'frac': round(conv_bytes / conv_ms / 1e6 / hbm, 4), 'traffic': None,
+                             'kernel': 'tconv_kernel / twgrad_kernel (the 27 conv forward / backward-data / backward-weight launches of one step, timed back to back)',
+                             'conv_ms_per_step': round(conv_ms, 4), 'tensor_tflops': round(ach, 1), 'tensor_frac_of_bf16_peak': round(ach / peak_tf, 4),
+                             'algorithmic_bytes_per_step': conv_bytes, 'algorithmic_gflop_per_step': round(flops / 1e9, 2), 'kernel_sources_sha1': csrc_sha1(),
+                             'note': 'bf16 128/64-channel convolutions at 80x80 are HBM / L2 bound (arithmetic intensity 32-64 flop/B per pass); the step also runs 42 '
+                                     'element-wise BatchNorm / SiLU kernels and the torch optimiser'},
+                'library_baseline': {'what': 'the same block through cuDNN / ATen (torch autocast bf16, channels_last) forward+backward on this GPU', 'ms_per_step': round(lib_ms, 4) if lib_ms else None},
+                'cpu_baseline': {'value': round(cpu_v, 4) if cpu_v else None, 'unit': 'images/sec', 'cores': cores, 'kind': 'port', 'sample': sample}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_train_reference_arm(args):
+    if env_int('RANK', 0) != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    v, cores, spt, sample = _train_cpu(steps)
+    line = {'impl': 'reference', 'metric': TRAIN_CFG['metric'], 'value': round(v, 4), 'unit': 'images/sec', 'n_gpus': args.gpus, 'steps': steps, 'warmup': 1,
+            'ms_per_step': round(spt * 1e3, 3), 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': TRAIN_CFG['workload'] + ', CPU sample bs2 per step', 'parallelism': 'cpu'},
+            'cpu_baseline': {'value': round(v, 4), 'unit': 'images/sec', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': round(v, 4), 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
 def run_secondary_reference_arm(args):
     if env_int('RANK', 0) != 0:
         return
@@ -698,14 +958,24 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--config', default='yolov5s', choices=['yolov5s'] + sorted(SECONDARY),
-                    help='yolov5s (default) = the headline, BASELINE.json configs[1]; fcos / deeplab / yolox = the secondary configurations')
+    ap.add_argument('--config', default='yolov5s', choices=['yolov5s', 'c3train'] + sorted(SECONDARY),
+                    help='yolov5s (default) = the headline, BASELINE.json configs[1]; fcos / deeplab / yolox = the secondary configurations; '
+                         'c3train = the training step of one YOLOX C3 block (the built part of configs[3])')
     ap.add_argument('--batch', type=int, default=0, help='images per GPU per step (default: the configuration\'s own, 64 for yolov5s)')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'], help='weak: --batch images per GPU (default); strong: --batch images in total')
     ap.add_argument('--graph', type=int, default=1, help='1 (default): the timed steps replay captured CUDA graphs (the conv-stack time for the roofline '
                     'comes from the conv launches replayed as their own graph); 0: eager launches with per-conv-segment events inside the timed region')
     ap.add_argument('--cpu-steps', type=int, default=3, help='CPU baseline steps timed on rank 0 (0 = skip)')
     args = ap.parse_args()
+    if args.config == 'c3train':
+        if args.impl == 'reference':
+            return run_train_reference_arm(args)
+        if not torch.cuda.is_available():
+            raise SystemExit('bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU arm)')
+        if args.steps == 100:
+            args.steps = 20
+        args.cpu_steps = min(args.cpu_steps, 3)
+        return run_train_arm(args)
     if args.config == 'yolov5s':
         args.batch = args.batch or 64
         if args.impl == 'reference':

@@ -365,19 +365,53 @@ __device__ __forceinline__ uint4 float_to_bf16x8(const float (&f)[8]) {
   return u;
 }
 
+// Per-channel reductions over pixels: a CTA owns a contiguous pixel range, thread (v, pl) = (8-channel vector, pixel lane) accumulates in
+// registers, the pixel lanes are combined through shared memory ([lane][2C] partials, no atomics) and 2C global atomicAdds leave the CTA.
+constexpr int kRedSmemFloats = kEwThreads * 16;  // np * 2C == 256 * 16 for every C
+
+__device__ __forceinline__ void red_finish(float (&a1)[8], float (&a2)[8], int v, int pl, int np, bool active, int C, float* s_part, float* __restrict__ sums) {
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      s_part[pl * 2 * C + v * 8 + i] = a1[i];
+      s_part[pl * 2 * C + C + v * 8 + i] = a2[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * C; c += kEwThreads) {
+    float t = 0.0f;
+    for (int l = 0; l < np; ++l) t += s_part[l * 2 * C + c];
+    atomicAdd(&sums[c], t);
+  }
+}
+
 // sums[c] += sum_p y[p][c], sums[C + c] += sum_p y[p][c]^2
 __global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(const __nv_bfloat16* __restrict__ y, long long npix, int C, float* __restrict__ sums) {
-  extern __shared__ float s_acc[];  // [2 * C]
-  for (int i = threadIdx.x; i < 2 * C; i += kEwThreads) s_acc[i] = 0.0f;
-  __syncthreads();
+  __shared__ float s_part[kRedSmemFloats];
   const int cv = C / 8;
   const int v = threadIdx.x % cv;
   const int pl = threadIdx.x / cv, np = kEwThreads / cv;
-  if (pl < np) {
-    float a1[8], a2[8];
+  const bool active = pl < np;
+  const long long chunk = (npix + gridDim.x - 1) / gridDim.x;
+  const long long p0 = (long long)blockIdx.x * chunk, p1 = min(npix, p0 + chunk);
+  float a1[8], a2[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) a1[i] = a2[i] = 0.0f;
-    for (long long p = (long long)blockIdx.x * np + pl; p < npix; p += (long long)gridDim.x * np) {
+  for (int i = 0; i < 8; ++i) a1[i] = a2[i] = 0.0f;
+  if (active) {
+    long long p = p0 + pl;
+    for (; p + np < p1; p += 2 * np) {  // two independent 16-byte loads in flight
+      float f[8], h[8];
+      const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(y + p * C) + v);
+      const uint4 u1 = __ldg(reinterpret_cast<const uint4*>(y + (p + np) * C) + v);
+      bf16x8_to_float(u0, f);
+      bf16x8_to_float(u1, h);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        a1[i] += f[i] + h[i];
+        a2[i] = fmaf(f[i], f[i], fmaf(h[i], h[i], a2[i]));
+      }
+    }
+    if (p < p1) {
       float f[8];
       bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(y + p * C) + v), f);
 #pragma unroll
@@ -386,14 +420,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_stats_kernel(const __nv_bfloat1
         a2[i] = fmaf(f[i], f[i], a2[i]);
       }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&s_acc[v * 8 + i], a1[i]);
-      atomicAdd(&s_acc[C + v * 8 + i], a2[i]);
-    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += kEwThreads) atomicAdd(&sums[i], s_acc[i]);
+  red_finish(a1, a2, v, pl, np, active, C, s_part, sums);
 }
 
 // batch statistics -> mean, rstd, folded scale / shift; running statistics updated like nn.BatchNorm2d (unbiased variance, momentum)
@@ -443,26 +471,31 @@ __device__ __forceinline__ float silu_grad(float z) {
 // sums[c] += sum_p dz, sums[C + c] += sum_p dz * xhat   (dz = g * silu'(z) when `g` is d(loss)/d(a); dz = g when g_is_dz)
 __global__ void __launch_bounds__(kEwThreads) bn_silu_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ g, const __nv_bfloat16* __restrict__ y, long long npix,
                                                                         int C, const float* __restrict__ stat, int g_is_dz, float* __restrict__ sums) {
-  extern __shared__ float s_acc[];
-  for (int i = threadIdx.x; i < 2 * C; i += kEwThreads) s_acc[i] = 0.0f;
-  __syncthreads();
+  __shared__ float s_part[kRedSmemFloats];
   const int cv = C / 8;
   const int v = threadIdx.x % cv;
   const int pl = threadIdx.x / cv, np = kEwThreads / cv;
-  if (pl < np) {
-    float mean[8], rstd[8], sc[8], sh[8], a1[8], a2[8];
+  const bool active = pl < np;
+  const long long chunk = (npix + gridDim.x - 1) / gridDim.x;
+  const long long p0 = (long long)blockIdx.x * chunk, p1 = min(npix, p0 + chunk);
+  float a1[8], a2[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a1[i] = a2[i] = 0.0f;
+  if (active) {
+    float mean[8], rstd[8], sc[8], sh[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       mean[i] = stat[v * 8 + i];
       rstd[i] = stat[C + v * 8 + i];
       sc[i] = stat[2 * C + v * 8 + i];
       sh[i] = stat[3 * C + v * 8 + i];
-      a1[i] = a2[i] = 0.0f;
     }
-    for (long long p = (long long)blockIdx.x * np + pl; p < npix; p += (long long)gridDim.x * np) {
+    for (long long p = p0 + pl; p < p1; p += np) {
       float fy[8], fg[8];
-      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(y + p * C) + v), fy);
-      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(g + p * C) + v), fg);
+      const uint4 uy = __ldg(reinterpret_cast<const uint4*>(y + p * C) + v);
+      const uint4 ug = __ldg(reinterpret_cast<const uint4*>(g + p * C) + v);
+      bf16x8_to_float(uy, fy);
+      bf16x8_to_float(ug, fg);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float dz = g_is_dz ? fg[i] : fg[i] * silu_grad(fmaf(fy[i], sc[i], sh[i]));
@@ -470,14 +503,8 @@ __global__ void __launch_bounds__(kEwThreads) bn_silu_bwd_reduce_kernel(const __
         a2[i] = fmaf(dz, (fy[i] - mean[i]) * rstd[i], a2[i]);
       }
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      atomicAdd(&s_acc[v * 8 + i], a1[i]);
-      atomicAdd(&s_acc[C + v * 8 + i], a2[i]);
-    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += kEwThreads) atomicAdd(&sums[i], s_acc[i]);
+  red_finish(a1, a2, v, pl, np, active, C, s_part, sums);
 }
 
 // dy = gamma * rstd * (dz - sum_dz / N - xhat * sum_dzx / N)
@@ -659,10 +686,10 @@ extern "C" int cvb_train_conv_wgrad(const void* x, const void* dy, int32_t B, in
   return CVB_OK;
 }
 
-// reduction kernels: `np` pixel lanes per CTA, at least ~8 pixels per thread
+// reduction kernels: `np` pixel lanes per CTA, at least ~4 pixels per thread, at most four CTAs per SM (2C global atomics per CTA)
 static int red_grid(long long npix, int np) {
-  long long g = (npix + (long long)np * 8 - 1) / ((long long)np * 8);
-  const long long cap = (long long)num_sms() * 8;
+  long long g = (npix + (long long)np * 4 - 1) / ((long long)np * 4);
+  const long long cap = (long long)num_sms() * 4;
   return (int)(g < 1 ? 1 : (g > cap ? cap : g));
 }
 
@@ -679,7 +706,7 @@ extern "C" int cvb_train_bn_stats(const void* y, int64_t npix, int32_t C, const 
   CVB_CHECK_CUDA(cudaMemsetAsync(sums_scratch, 0, 2 * (size_t)C * sizeof(float), st));
   const int np = kEwThreads / (C / 8) > 0 ? kEwThreads / (C / 8) : 1;
   CVB_REQUIRE(C / 8 <= kEwThreads, "train_bn_stats: C too large");
-  bn_stats_kernel<<<red_grid(npix, np), kEwThreads, 2 * C * sizeof(float), st>>>(static_cast<const __nv_bfloat16*>(y), npix, C, sums_scratch);
+  bn_stats_kernel<<<red_grid(npix, np), kEwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(y), npix, C, sums_scratch);
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums_scratch, npix, C, gamma, beta, eps, momentum, running_mean, running_var, stat);
   CVB_CHECK_CUDA(cudaGetLastError());
   count_launch(2);
@@ -701,7 +728,7 @@ extern "C" int cvb_train_bn_silu_bwd(const void* g, int32_t g_is_dz, const void*
   cudaStream_t st = as_stream(stream);
   CVB_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(float), st));
   const int np = kEwThreads / (C / 8);
-  bn_silu_bwd_reduce_kernel<<<red_grid(npix, np), kEwThreads, 2 * C * sizeof(float), st>>>(
+  bn_silu_bwd_reduce_kernel<<<red_grid(npix, np), kEwThreads, 0, st>>>(
       static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(y), npix, C, stat, g_is_dz, sums);
   const long long nvec = npix * (C / 8);
   bn_silu_bwd_apply_kernel<<<ew_grid(nvec), kEwThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(g), static_cast<const __nv_bfloat16*>(y), nvec, C, stat, gamma, sums,
