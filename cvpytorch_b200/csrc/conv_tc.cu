@@ -213,7 +213,8 @@ struct ConvCfg {
 
 // EPI selects a compile-time specialisation of the epilogue (the hot layers run a compact, branch-free instruction stream; the generic
 // stream with its run-time mode checks costs ~40 % more issue slots per tile, and the HBM-bound layers are issue bound in the epilogue):
-//   0 generic   1 act = SiLU, no residual, no up-partial   2 act = SiLU, residual tile by TMA added after the activation
+//   0 generic   1 act = SiLU, no residual, no up-partial   2 act = SiLU, residual tile by TMA added after the activation (Darknet bottleneck)
+//   3 act = ReLU, no residual, no up-partial   4 act = ReLU, residual tile by TMA added BEFORE the activation (ResNet bottleneck)
 template <int BLOCK_N, int BLOCK_K, bool OUT_F32, bool YOLO, int EPI = 0>
 __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK_N <= 64 ? 2 : 1)) conv_tc_kernel(const __grid_constant__ ConvKArgs a) {
   using Cfg = ConvCfg<BLOCK_N, BLOCK_K, OUT_F32>;
@@ -227,8 +228,8 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
   constexpr int EPI_THREADS = YOLO ? kYoloEpiThreads : kEpiThreads;
   static_assert(EPI == 0 || (!OUT_F32 && !YOLO), "epilogue specialisations exist for the split16 output only");
   // run-time mode flags, folded to constants in the specialised kernels
-  const bool resid_tma = EPI == 2 ? true : (EPI == 1 ? false : a.resid_tma != 0);
-  const int act_mode = EPI != 0 ? CVB_ACT_SILU : a.act;
+  const bool resid_tma = (EPI == 2 || EPI == 4) ? true : ((EPI == 1 || EPI == 3) ? false : a.resid_tma != 0);
+  const int act_mode = (EPI == 1 || EPI == 2) ? CVB_ACT_SILU : ((EPI == 3 || EPI == 4) ? CVB_ACT_RELU : a.act);
 
   // the kernel has no static shared memory, so the dynamic window starts at offset 0 of the CTA's (1024-byte aligned)
   // allocation; checked once instead of spending 1 KB of slack (which is what lets some two-CTA plans fit in 113 KB)
@@ -576,7 +577,7 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
     uint32_t res_phase = 0;
     grid_dep_wait();  // residual / up-partial reads and the output stores must not pass the previous kernel(s)
     const int n_main = a.n_main;
-    const float rscale = a.resid_scale;
+    const float rscale = (EPI == 2 || EPI == 4) ? 1.0f : a.resid_scale;  // (the specialised kernels are selected for unit shortcuts only)
     constexpr int kGroups = BLOCK_N / OUT_GROUP_CH;
     // residual tile of (tile, group): two TMA boxes (hi, lo) with the output tile's geometry; OOB parts are zero-filled
     auto issue_residual = [&](int tile_i, int g) {
@@ -788,7 +789,7 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
         const int col0 = g * OUT_GROUP_CH + half * CW;
         const bool ch_ok = (n0 + col0 + CW <= a.cout);
         const bool has_up = EPI != 0 ? false : ((up_row != nullptr) && ch_ok);
-        const bool has_res = EPI == 1 ? false : (resid_tma ? true : ((res_row != nullptr) && ch_ok));
+        const bool has_res = (EPI == 1 || EPI == 3) ? false : (resid_tma ? true : ((res_row != nullptr) && ch_ok));
         // the thread's CW columns are processed in sub-chunks of SUB columns (SUB < CW only for the small-N kernels that must
         // stay within the two-CTAs-per-SM register budget).  Epilogue operands that do not depend on the accumulator are
         // requested first, so their latency hides behind the accumulator wait / barrier / tcgen05.ld below
@@ -908,7 +909,7 @@ __global__ void __launch_bounds__(YOLO ? 64 + kYoloEpiThreads : kThreads, (BLOCK
               }
             }
           }
-          const bool rf = EPI != 0 ? false : (a.resid_first != 0);
+          const bool rf = EPI == 4 ? true : (EPI != 0 ? false : (a.resid_first != 0));
           if (act_mode == CVB_ACT_SILU) {
 #pragma unroll
             for (int j = 0; j < SUB; ++j) {
@@ -1036,7 +1037,8 @@ static bool lookup_kernel(int bn, int bk, bool f32, KernelEntry* e, bool yolo = 
 #define CVB_CASE(BN, BK)                                                                                          \
   if (bn == BN && bk == BK) {                                                                                     \
     *e = f32 ? entry<BN, BK, true>()                                                                              \
-             : (epi == 1 ? entry<BN, BK, false, false, 1>() : (epi == 2 ? entry<BN, BK, false, false, 2>() : entry<BN, BK, false>())); \
+             : (epi == 1 ? entry<BN, BK, false, false, 1>() : (epi == 2 ? entry<BN, BK, false, false, 2>() : (epi == 3 ? entry<BN, BK, false, false, 3>() \
+             : (epi == 4 ? entry<BN, BK, false, false, 4>() : entry<BN, BK, false>())))); \
     return true;                                                                                                  \
   }
   CVB_CASE(32, 16) CVB_CASE(32, 32) CVB_CASE(32, 64)
@@ -1779,9 +1781,14 @@ extern "C" int cvb_conv_plan_create(const CvbConvDesc* d, CvbConvPlan** out_plan
     // compile-time specialised epilogues for the two hot modes (same tile / smem geometry as the generic kernel picked above)
     static const bool spec_on = [] { const char* e = getenv("CVB_EPI_SPEC"); return !(e && atoi(e) == 0); }();  // A/B knob
     int epi = 0;
-    if (spec_on && !f32 && !yolo && d->act == CVB_ACT_SILU && !d->up_partial.base) {
-      if (!d->residual.base) epi = 1;
-      else if (a.resid_tma && !a.resid_first) epi = 2;
+    if (spec_on && !f32 && !yolo && !d->up_partial.base) {
+      if (d->act == CVB_ACT_SILU) {
+        if (!d->residual.base) epi = 1;
+        else if (a.resid_tma && !a.resid_first && a.resid_scale == 1.0f) epi = 2;
+      } else if (d->act == CVB_ACT_RELU) {
+        if (!d->residual.base) epi = 3;
+        else if (a.resid_tma && a.resid_first && a.resid_scale == 1.0f) epi = 4;
+      }
     }
     if (epi) {
       KernelEntry k2;

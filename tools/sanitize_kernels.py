@@ -89,3 +89,36 @@ m = synth.build_yolov5s(True)
 m.predict(torch.randn(1, 3, 64, 64, device='cuda'))
 torch.cuda.synchronize()
 print('model ok')
+
+# fused detect head: 1x1 conv with the YOLOv5 decode as its epilogue (CVB_OUT_YOLO; bulk-store and generic copy-out paths)
+for (Bh, ny, nx, cinh, na, nc, zo) in ((1, 12, 20, 64, 3, 80, 4), (1, 7, 13, 32, 3, 80, 3), (1, 9, 16, 96, 2, 3, 8)):
+    no = nc + 5
+    tin = ops.SplitTensor(Bh, ny, nx, cinh)
+    ops.nchw_to_split(torch.randn(Bh, cinh, ny, nx, device='cuda'), tin.view())
+    wh_ = (torch.randn(na * no, cinh, 1, 1) * (2.5 / cinh ** 0.5)).double()
+    bh_ = (torch.randn(na * no) * 0.5).double()
+    A = na * ny * nx + zo + 7
+    wsh = ops.NmsWorkspace(Bh, A, nc)
+    ops.nms_reset(wsh)
+    zh = torch.zeros(Bh, A, no, device='cuda')
+    wy, by = ops.pack_yolo_head_weights(wh_, bh_, na, no)
+    yd = ops.yolo_decode_desc(na, no, torch.tensor([[10., 13.], [16., 30.], [33., 23.]][:na]), 8.0, zh, A, zo, wsh, 0.05, True)
+    ops.ConvPlan(tin.view(), ops.CvbView(zh.data_ptr(), Bh, ny, nx, na * 128, na * 128, 0), wy, by, 1, 1, 0, 1, None, yolo=yd).run()
+    ops.yolo_nms(zh, wsh, 0.05, 0.6, True, hist_ready=True)
+torch.cuda.synchronize()
+print('fused head ok')
+
+# training kernels: conv forward / backward-data (+ SiLU' epilogue) / backward-weight, BatchNorm + SiLU passes, one C3 step
+from cvpytorch_b200 import train as TR  # noqa: E402
+for (Bt, Ht, Wt, ci, co, kk) in ((1, 8, 16, 64, 64, 1), (2, 9, 7, 128, 64, 3), (1, 8, 8, 64, 128, 3)):
+    xt = torch.randn(Bt, Ht, Wt, ci, device='cuda').to(torch.bfloat16)
+    dyt = torch.randn(Bt, Ht, Wt, co, device='cuda').to(torch.bfloat16)
+    wf_, wb_ = TR.pack_weights(torch.randn(co, ci, kk, kk, device='cuda') * 0.05)
+    TR.conv(xt, wf_, co, kk)
+    TR.conv(dyt, wb_, ci, kk)
+    TR.conv_wgrad(xt, dyt, kk)
+mt = TR.CSPLayer(128, 128, n=1).cuda().train()
+xt = torch.randn(1, 128, 8, 8, device='cuda', requires_grad=True)
+mt(xt).sum().backward()
+torch.cuda.synchronize()
+print('training kernels ok')
