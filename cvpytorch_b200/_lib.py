@@ -101,8 +101,9 @@ def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise CvbError(f'{LIB_PATH} not found: build it with `python -c "import __graft_entry__ as g; g.build()"` '
-                           '(cvpytorch_b200/csrc/build.sh). The B200 path has no CPU fallback.')
+            how = ('`bash cvpytorch_b200/csrc/build.sh diag` (the diagnostics build used by tools/*profile*.py)' if LIB_PATH.endswith('_diag.so')
+                   else '`python -c "import __graft_entry__ as g; g.build()"` (cvpytorch_b200/csrc/build.sh)')
+            raise CvbError(f'{LIB_PATH} not found: build it with {how}. The B200 path has no CPU fallback.')
         handle = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
             fn = getattr(handle, name)  # AttributeError if the symbol is missing
