@@ -732,18 +732,22 @@ def run_train_arm(args):
     xs = [torch.randn(B, H, Wd, c['cin'], generator=gen).to(dev).to(torch.bfloat16) for _ in range(NBUF)]   # NHWC bf16: the layout between blocks
     Gs = [torch.randn(B, H, Wd, c['cout'], generator=gen).to(dev).to(torch.bfloat16) for _ in range(NBUF)]  # stand-in for d(loss)/d(out) of the rest of the net
 
+    def allreduce_grads():  # data-parallel gradient all-reduce (one flat fp32 bucket: 0.3 M parameters)
+        if world == 1:
+            return
+        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        dist.all_reduce(flat)
+        flat /= world
+        off = 0
+        for p in params:
+            p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+            off += p.numel()
+
     def step(i):
         x = xs[i % NBUF].requires_grad_(True)
         y = m.forward_nhwc(x)
         y.backward(Gs[i % NBUF])
-        if world > 1:  # data-parallel gradient all-reduce (one flat bucket: 0.3 M parameters)
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
-            flat /= world
-            off = 0
-            for p in params:
-                p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
-                off += p.numel()
+        allreduce_grads()
         opt.step()
         opt.zero_grad(set_to_none=True)
         x.grad = None
@@ -873,9 +877,7 @@ def run_train_arm(args):
         y = m(xg)
         loss = (y * Gn32).sum()
         loss.backward()
-        if world > 1:
-            flat = torch.cat([p.grad.reshape(-1) for p in params])
-            dist.all_reduce(flat)
+        allreduce_grads()
         opt.step()
         opt.zero_grad(set_to_none=True)
         loss_h.copy_(loss.detach(), non_blocking=True)
