@@ -48,7 +48,7 @@ def csrc_sha1():
     """Hash of the CUDA sources: stamps profile-derived numbers (roofline.traffic) with the kernel version they were captured on."""
     h = hashlib.sha1()
     for f in sorted(glob.glob(os.path.join(ROOT, 'cvpytorch_b200', 'csrc', '*'))):
-        if f.endswith(('.cu', '.cuh', '.h')):
+        if f.endswith(('.cu', '.cuh', '.h')) and not os.path.basename(f).startswith('train_'):  # (the training kernels are not on the measured inference path)
             h.update(open(f, 'rb').read())
     return h.hexdigest()[:12]
 

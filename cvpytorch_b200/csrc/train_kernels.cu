@@ -61,6 +61,7 @@ struct alignas(64) TConvArgs {
   int tiles_w, tiles_h, tiles_b;
   int TW, TH, NB, H, W, B;
   int cin, cout, taps, kw, pad;
+  int stages;  // ring depth = min(4, K iterations): short-K 1x1 layers take less shared memory, so more CTAs share an SM
   __nv_bfloat16* out;
   const __nv_bfloat16* y_prev;  // SiLU' epilogue: conv output of the layer that produced this conv's input, and its BN scale / shift
   const float* s_prev;
@@ -77,7 +78,8 @@ __global__ void __launch_bounds__(kTThreads, 1) tconv_kernel(const __grid_consta
   constexpr int STAGE = A_BYTES + B_BYTES;
   constexpr uint32_t IDESC = make_idesc_bf16(128, BN, 0, 0);
   extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTStagesFwd * STAGE);
+  const int STAGES = a.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE);
   uint64_t* full = bars;
   uint64_t* empty = bars + kTStagesFwd;
   uint64_t* tfull = empty + kTStagesFwd;
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(kTThreads, 1) tconv_kernel(const __grid_consta
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < kTStagesFwd; ++s) {
+      for (int s = 0; s < STAGES; ++s) {
         mbar_init(&full[s], 1);
         mbar_init(&empty[s], 1);
       }
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(kTThreads, 1) tconv_kernel(const __grid_consta
           uint8_t* sb = smem + stage * STAGE;
           tma_load_4d(&a.tmA, &full[stage], sb, ck * 64, w0 + dw, h0 + dh, b0);
           tma_load_2d(&a.tmB, &full[stage], sb + A_BYTES, tap * a.cin + ck * 64, n0);
-          if (++stage == kTStagesFwd) {
+          if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
@@ -153,7 +155,7 @@ __global__ void __launch_bounds__(kTThreads, 1) tconv_kernel(const __grid_consta
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_f16(tmem_base, da + 2 * k, db + 2 * k, IDESC, (i | k) ? 1u : 0u);
         umma_commit(&empty[stage]);
-        if (++stage == kTStagesFwd) {
+        if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
         }
@@ -450,16 +452,34 @@ __global__ void bn_finalize_kernel(const float* __restrict__ sums, long long npi
 __global__ void __launch_bounds__(kEwThreads) bn_silu_fwd_kernel(const __nv_bfloat16* __restrict__ y, long long nvec, int C, const float* __restrict__ stat,
                                                                  __nv_bfloat16* __restrict__ out) {
   const int cv = C / 8;
-  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < nvec; i += (long long)gridDim.x * kEwThreads) {
-    const int c0 = (int)(i % cv) * 8;
-    float f[8];
-    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(y) + i), f);
+  const long long stride = (long long)gridDim.x * kEwThreads;
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < nvec; i += 2 * stride) {
+    const long long i2 = i + stride;
+    const bool two = i2 < nvec;
+    const uint4 u0 = __ldg(reinterpret_cast<const uint4*>(y) + i);
+    const uint4 u1 = two ? __ldg(reinterpret_cast<const uint4*>(y) + i2) : u0;  // two independent 16-byte loads in flight
+    {
+      const int c0 = (int)(i % cv) * 8;
+      float f[8];
+      bf16x8_to_float(u0, f);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float z = fmaf(f[k], __ldg(stat + 2 * C + c0 + k), __ldg(stat + 3 * C + c0 + k));
-      f[k] = z / (1.0f + __expf(-z));
+      for (int k = 0; k < 8; ++k) {
+        const float z = fmaf(f[k], __ldg(stat + 2 * C + c0 + k), __ldg(stat + 3 * C + c0 + k));
+        f[k] = z / (1.0f + __expf(-z));
+      }
+      reinterpret_cast<uint4*>(out)[i] = float_to_bf16x8(f);
     }
-    reinterpret_cast<uint4*>(out)[i] = float_to_bf16x8(f);
+    if (two) {
+      const int c0 = (int)(i2 % cv) * 8;
+      float f[8];
+      bf16x8_to_float(u1, f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float z = fmaf(f[k], __ldg(stat + 2 * C + c0 + k), __ldg(stat + 3 * C + c0 + k));
+        f[k] = z / (1.0f + __expf(-z));
+      }
+      reinterpret_cast<uint4*>(out)[i2] = float_to_bf16x8(f);
+    }
   }
 }
 
@@ -512,20 +532,31 @@ __global__ void __launch_bounds__(kEwThreads) bn_silu_bwd_apply_kernel(const __n
                                                                        const float* __restrict__ stat, const float* __restrict__ gamma, const float* __restrict__ sums,
                                                                        float inv_n, int g_is_dz, __nv_bfloat16* __restrict__ dy) {
   const int cv = C / 8;
-  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < nvec; i += (long long)gridDim.x * kEwThreads) {
-    const int c0 = (int)(i % cv) * 8;
-    float fy[8], fg[8];
-    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(y) + i), fy);
-    bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(g) + i), fg);
+  const long long stride = (long long)gridDim.x * kEwThreads;
+  for (long long i = (long long)blockIdx.x * kEwThreads + threadIdx.x; i < nvec; i += 2 * stride) {
+    const long long i2 = i + stride;
+    const bool two = i2 < nvec;
+    // four independent 16-byte loads in flight
+    const uint4 uy0 = __ldg(reinterpret_cast<const uint4*>(y) + i), ug0 = __ldg(reinterpret_cast<const uint4*>(g) + i);
+    const uint4 uy1 = two ? __ldg(reinterpret_cast<const uint4*>(y) + i2) : uy0, ug1 = two ? __ldg(reinterpret_cast<const uint4*>(g) + i2) : ug0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = c0 + k;
-      const float mean = __ldg(stat + c), rstd = __ldg(stat + C + c);
-      const float dz = g_is_dz ? fg[k] : fg[k] * silu_grad(fmaf(fy[k], __ldg(stat + 2 * C + c), __ldg(stat + 3 * C + c)));
-      const float xhat = (fy[k] - mean) * rstd;
-      fg[k] = __ldg(gamma + c) * rstd * (dz - __ldg(sums + c) * inv_n - xhat * __ldg(sums + C + c) * inv_n);
+    for (int h = 0; h < 2; ++h) {
+      if (h == 1 && !two) break;
+      const long long ii = h ? i2 : i;
+      const int c0 = (int)(ii % cv) * 8;
+      float fy[8], fg[8];
+      bf16x8_to_float(h ? uy1 : uy0, fy);
+      bf16x8_to_float(h ? ug1 : ug0, fg);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = c0 + k;
+        const float mean = __ldg(stat + c), rstd = __ldg(stat + C + c);
+        const float dz = g_is_dz ? fg[k] : fg[k] * silu_grad(fmaf(fy[k], __ldg(stat + 2 * C + c), __ldg(stat + 3 * C + c)));
+        const float xhat = (fy[k] - mean) * rstd;
+        fg[k] = __ldg(gamma + c) * rstd * (dz - __ldg(sums + c) * inv_n - xhat * __ldg(sums + C + c) * inv_n);
+      }
+      reinterpret_cast<uint4*>(dy)[ii] = float_to_bf16x8(fg);
     }
-    reinterpret_cast<uint4*>(dy)[i] = float_to_bf16x8(fg);
   }
 }
 
@@ -639,7 +670,11 @@ extern "C" int cvb_train_conv(const void* x, int32_t B, int32_t H, int32_t W, in
   const void* fn;
   if (bn == 128) fn = y_prev ? reinterpret_cast<const void*>(&tconv_kernel<128, true>) : reinterpret_cast<const void*>(&tconv_kernel<128, false>);
   else fn = y_prev ? reinterpret_cast<const void*>(&tconv_kernel<64, true>) : reinterpret_cast<const void*>(&tconv_kernel<64, false>);
-  const int smem = kTStagesFwd * (128 * 128 + bn * 128) + 256 + 2 * bn * 4;
+  {
+    const int k_iters = a.taps * (cin / 64);
+    a.stages = k_iters < kTStagesFwd ? k_iters : kTStagesFwd;
+  }
+  const int smem = a.stages * (128 * 128 + bn * 128) + 256 + 2 * bn * 4;
   CVB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   void* kargs[1] = {&a};
   const dim3 grid((unsigned)(a.tiles_w * a.tiles_h * a.tiles_b), (unsigned)(cout / bn));
