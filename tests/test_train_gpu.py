@@ -123,3 +123,35 @@ def test_c3_training_step_vs_reference_fixture(cuda, case):
     opt.zero_grad(set_to_none=True)
     y2 = m(x.detach())
     assert torch.isfinite(y2).all()
+
+
+def test_c3_dropin_through_the_reference_trainer_train_step(cuda):
+    """The drop-in block inside a copy of the reference's training-step logic (trainer.py:177-207: amp.autocast(enabled=cfg.AMP) ->
+    scaler.scale(losses['loss']).backward() -> clip_grad -> scaler.step(optimizer) -> scaler.update() -> optimizer.zero_grad(set_to_none=True)),
+    with unchanged torch modules before and after it: the loss goes down and every parameter of the block receives finite gradients."""
+    from cvpytorch_b200 import train as T
+    torch.manual_seed(3)
+    stem = torch.nn.Conv2d(3, 128, 3, 2, 1).cuda()          # reference-side layer in front of the block
+    block = T.CSPLayer(128, 128, n=2).cuda().train()
+    head = torch.nn.Conv2d(128, 8, 1).cuda()                # reference-side layer behind it
+    params = list(stem.parameters()) + list(block.parameters()) + list(head.parameters())
+    optimizer = torch.optim.SGD(params, lr=0.02, momentum=0.9)
+    scaler = torch.amp.GradScaler('cuda', enabled=True)
+    imgs = torch.randn(4, 3, 64, 64, device='cuda')
+    target = torch.randn(4, 8, 32, 32, device='cuda') * 0.1
+    hist = []
+    for it in range(8):
+        with torch.autocast('cuda', enabled=True):           # cfg.AMP
+            out = head(block(stem(imgs)))
+            losses = {'loss': (out.float() - target).pow(2).mean()}
+        scaler.scale(losses['loss']).backward()
+        scaler.unscale_(optimizer)
+        torch.nn.utils.clip_grad_norm_(params, 10.0)          # cfg.GRAD_CLIP
+        if it == 0:
+            for k, p in block.named_parameters():
+                assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().max()) > 0, k
+        scaler.step(optimizer)
+        scaler.update()
+        optimizer.zero_grad(set_to_none=True)
+        hist.append(float(losses['loss']))
+    assert all(np.isfinite(hist)) and hist[-1] < 0.7 * hist[0], hist
