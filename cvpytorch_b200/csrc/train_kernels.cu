@@ -56,11 +56,15 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
 }
 
 struct alignas(64) TConvArgs {
-  CUtensorMap tmA;  // activations {C, W, H, B}, box {64, TW, TH, NB}
-  CUtensorMap tmB;  // weights {K = taps * cin, cout}, box {64, BN}
+  CUtensorMap tmA[4];  // activations {C, W, H, B}, box {64, TW, TH, NB}; stride 2: one map per (row parity, column parity) of the input
+  CUtensorMap tmB;     // weights {K = taps * cin, cout}, box {64, BN}
   int tiles_w, tiles_h, tiles_b;
-  int TW, TH, NB, H, W, B;
-  int cin, cout, taps, kw, pad;
+  int TW, TH, NB, H, W, B;   // H, W: the tile grid (output pixels of this launch)
+  int cin, cout, taps;
+  // tap t reads input map tap_map[t] at (w + tap_dw[t], h + tap_dh[t]) and the weight K block tap_wblk[t]
+  int8_t tap_dh[9], tap_dw[9], tap_map[9], tap_wblk[9];
+  // output pixel of grid point (h, w): (h * os + ooh, w * os + oow) of an out_H x out_W tensor (stride-2 backward-data writes one parity class per launch)
+  int out_H, out_W, os, ooh, oow;
   int stages;  // ring depth = min(4, K iterations): short-K 1x1 layers take less shared memory, so more CTAs share an SM
   __nv_bfloat16* out;
   const __nv_bfloat16* y_prev;  // SiLU' epilogue: conv output of the layer that produced this conv's input, and its BN scale / shift
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(kTThreads, 1) tconv_kernel(const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&a.tmA);
+    tma_prefetch_desc(&a.tmA[0]);
     tma_prefetch_desc(&a.tmB);
   }
   if (warp == 1) {
@@ -128,13 +132,15 @@ __global__ void __launch_bounds__(kTThreads, 1) tconv_kernel(const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int tap = 0; tap < a.taps; ++tap) {
-        const int dh = tap / a.kw - a.pad, dw = tap % a.kw - a.pad;
+        const int dh = a.tap_dh[tap], dw = a.tap_dw[tap];
+        const CUtensorMap* mapA = &a.tmA[a.tap_map[tap]];
+        const int kb = a.tap_wblk[tap] * a.cin;
         for (int ck = 0; ck < chunks; ++ck) {
           mbar_wait(&empty[stage], phase ^ 1, 100 + stage);
           mbar_expect_tx(&full[stage], A_BYTES + B_BYTES);
           uint8_t* sb = smem + stage * STAGE;
-          tma_load_4d(&a.tmA, &full[stage], sb, ck * 64, w0 + dw, h0 + dh, b0);
-          tma_load_2d(&a.tmB, &full[stage], sb + A_BYTES, tap * a.cin + ck * 64, n0);
+          tma_load_4d(mapA, &full[stage], sb, ck * 64, w0 + dw, h0 + dh, b0);
+          tma_load_2d(&a.tmB, &full[stage], sb + A_BYTES, kb + ck * 64, n0);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -169,7 +175,7 @@ __global__ void __launch_bounds__(kTThreads, 1) tconv_kernel(const __grid_consta
     const int th = r2 % a.TH, nb = r2 / a.TH;
     const int ow = w0 + tw, oh = h0 + th, ob = b0 + nb;
     const bool valid = ow < a.W && oh < a.H && ob < a.B;
-    const size_t pix = ((size_t)ob * a.H + oh) * a.W + ow;
+    const size_t pix = ((size_t)ob * a.out_H + (oh * a.os + a.ooh)) * a.out_W + (ow * a.os + a.oow);
     mbar_wait(tfull, 0, 400);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
@@ -218,11 +224,12 @@ __global__ void __launch_bounds__(kTThreads, 1) tconv_kernel(const __grid_consta
 }
 
 struct alignas(64) TWgradArgs {
-  CUtensorMap tmX;  // x  {cin, W, H, B},  box {64, TW, TH, NB}
-  CUtensorMap tmD;  // dy {cout, W, H, B}, box {64, TW, TH, NB}
-  int tiles_w, tiles_h, tiles_b;
+  CUtensorMap tmX[4];  // x  {cin, W, H, B},  box {64, TW, TH, NB}; stride 2: one map per input parity class
+  CUtensorMap tmD;     // dy {cout, Wo, Ho, B}, box {64, TW, TH, NB}
+  int tiles_w, tiles_h, tiles_b;  // over the OUTPUT pixels (dy)
   int TW, TH, NB;
-  int cin, cout, taps, kw, pad;
+  int cin, cout, taps;
+  int8_t tap_dh[9], tap_dw[9], tap_map[9];
   int splits;
   float* dw;  // [cout][taps][cin] fp32, accumulated with atomics (zeroed by the caller)
 };
@@ -246,7 +253,7 @@ __global__ void __launch_bounds__(kTThreads, 1) twgrad_kernel(const __grid_const
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&a.tmX);
+    tma_prefetch_desc(&a.tmX[0]);
     tma_prefetch_desc(&a.tmD);
   }
   if (warp == 1) {
@@ -269,7 +276,8 @@ __global__ void __launch_bounds__(kTThreads, 1) twgrad_kernel(const __grid_const
 
   const int split = blockIdx.x, tap = blockIdx.y, c0 = blockIdx.z * 128;
   const int m_pan = (a.cin - c0) >= 128 ? 2 : 1;  // valid 64-channel panels of this cin block
-  const int dh = tap / a.kw - a.pad, dw_ = tap % a.kw - a.pad;
+  const int dh = a.tap_dh[tap], dw_ = a.tap_dw[tap];
+  const CUtensorMap* mapX = &a.tmX[a.tap_map[tap]];
   const int m_tiles = a.tiles_w * a.tiles_h * a.tiles_b;
   const int per = (m_tiles + a.splits - 1) / a.splits;
   const int t_begin = split * per, t_end = min(m_tiles, t_begin + per);
@@ -285,7 +293,7 @@ __global__ void __launch_bounds__(kTThreads, 1) twgrad_kernel(const __grid_const
         mbar_wait(&empty[stage], phase ^ 1, 100 + stage);
         mbar_expect_tx(&full[stage], (uint32_t)(m_pan * PANEL + D_BYTES));
         uint8_t* sb = smem + stage * STAGE;
-        for (int p = 0; p < m_pan; ++p) tma_load_4d(&a.tmX, &full[stage], sb + p * PANEL, c0 + p * 64, w0 + dw_, h0 + dh, b0);
+        for (int p = 0; p < m_pan; ++p) tma_load_4d(mapX, &full[stage], sb + p * PANEL, c0 + p * 64, w0 + dw_, h0 + dh, b0);
         for (int p = 0; p < NPAN; ++p) tma_load_4d(&a.tmD, &full[stage], sb + X_BYTES + p * PANEL, p * 64, w0, h0, b0);
         if (++stage == STAGES) {
           stage = 0;
@@ -632,72 +640,162 @@ extern "C" int cvb_train_pack_weights(const float* w, int32_t cout, int32_t cin,
   return CVB_OK;
 }
 
-extern "C" int cvb_train_conv(const void* x, int32_t B, int32_t H, int32_t W, int32_t cin, const void* w_packed, int32_t cout, int32_t k, void* out,
-                              const void* y_prev, const float* bn_stat_prev, void* stream) {
-  CVB_REQUIRE(x && w_packed && out, "train_conv: null tensor");
-  CVB_REQUIRE((k == 1 || k == 3) && cin % 64 == 0 && cout % 64 == 0 && B > 0 && H > 0 && W > 0, "train_conv: k in {1,3}, channels multiples of 64 (cin=%d cout=%d k=%d)", cin, cout, k);
-  CVB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_packed) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "train_conv: pointers must be 16-byte aligned");
-  CVB_REQUIRE((y_prev == nullptr) == (bn_stat_prev == nullptr), "train_conv: the SiLU' epilogue needs both y_prev and its BN statistics");
-  TConvArgs a;
-  memset(&a, 0, sizeof(a));
-  choose_box128(B, H, W, &a.TW, &a.TH, &a.NB);
-  a.tiles_w = ceil_div(W, a.TW);
-  a.tiles_h = ceil_div(H, a.TH);
-  a.tiles_b = ceil_div(B, a.NB);
-  a.H = H;
-  a.W = W;
-  a.B = B;
-  a.cin = cin;
-  a.cout = cout;
-  a.taps = k * k;
-  a.kw = k;
-  a.pad = k / 2;
-  a.out = static_cast<__nv_bfloat16*>(out);
+// tensor map of one parity class (py, px) of an NHWC tensor: pixels (2i + py, 2j + px); (0, 0) with step 1 is the plain map
+static int act_map_strided(CUtensorMap* m, const void* base, int B, int H, int W, int C, int step, int py, int px, int TW, int TH, int NB) {
+  const int Wp = (W - px + step - 1) / step, Hp = (H - py + step - 1) / step;
+  if (Wp <= 0 || Hp <= 0) return act_map(m, base, B, H, W, C, TW, TH, NB);  // never addressed (no pixel of this parity): any valid map
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)B};
+  const cuuint64_t str[3] = {(cuuint64_t)C * 2 * step, (cuuint64_t)C * 2 * W * step, (cuuint64_t)C * 2 * W * H};
+  const cuuint32_t box[4] = {64, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)NB};
+  return encode_tiled(m, 4, static_cast<const uint8_t*>(base) + ((size_t)py * W + px) * C * 2, dims, str, box);
+}
+
+// stride-2 3x3 / pad 1: tap (ky, kx) reads input pixel (2h + ky - 1, 2w + kx - 1) = parity class ((ky + 1) & 1, (kx + 1) & 1) at index
+// (h + (ky == 0 ? -1 : 0), w + (kx == 0 ? -1 : 0)) of that class
+static void s2_taps(int8_t* dh, int8_t* dw, int8_t* map) {
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      const int t = ky * 3 + kx;
+      dh[t] = (int8_t)(ky == 0 ? -1 : 0);
+      dw[t] = (int8_t)(kx == 0 ? -1 : 0);
+      map[t] = (int8_t)((((ky + 1) & 1) << 1) | ((kx + 1) & 1));
+    }
+}
+
+static int launch_tconv(TConvArgs& a, const void* w_packed, int wblocks, const void* y_prev, const float* bn_stat_prev, void* stream) {
+  choose_box128(a.B, a.H, a.W, &a.TW, &a.TH, &a.NB);
+  a.tiles_w = ceil_div(a.W, a.TW);
+  a.tiles_h = ceil_div(a.H, a.TH);
+  a.tiles_b = ceil_div(a.B, a.NB);
   a.y_prev = static_cast<const __nv_bfloat16*>(y_prev);
-  a.s_prev = bn_stat_prev ? bn_stat_prev + 2 * (size_t)cout : nullptr;
-  a.t_prev = bn_stat_prev ? bn_stat_prev + 3 * (size_t)cout : nullptr;
-  const int bn = cout % 128 == 0 ? 128 : 64;
-  int rc = act_map(&a.tmA, x, B, H, W, cin, a.TW, a.TH, a.NB);
-  if (rc != CVB_OK) return rc;
+  a.s_prev = bn_stat_prev ? bn_stat_prev + 2 * (size_t)a.cout : nullptr;
+  a.t_prev = bn_stat_prev ? bn_stat_prev + 3 * (size_t)a.cout : nullptr;
+  const int bn = a.cout % 128 == 0 ? 128 : 64;
   {
-    const long long K = (long long)a.taps * cin;
-    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)cout};
+    const long long K = (long long)wblocks * a.cin;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)a.cout};
     const cuuint64_t str[1] = {(cuuint64_t)K * 2};
     const cuuint32_t box[2] = {64, (cuuint32_t)bn};
-    rc = encode_tiled(&a.tmB, 2, w_packed, dims, str, box);
+    const int rc = encode_tiled(&a.tmB, 2, w_packed, dims, str, box);
     if (rc != CVB_OK) return rc;
   }
   const void* fn;
   if (bn == 128) fn = y_prev ? reinterpret_cast<const void*>(&tconv_kernel<128, true>) : reinterpret_cast<const void*>(&tconv_kernel<128, false>);
   else fn = y_prev ? reinterpret_cast<const void*>(&tconv_kernel<64, true>) : reinterpret_cast<const void*>(&tconv_kernel<64, false>);
-  {
-    const int k_iters = a.taps * (cin / 64);
-    a.stages = k_iters < kTStagesFwd ? k_iters : kTStagesFwd;
-  }
+  const int k_iters = a.taps * (a.cin / 64);
+  a.stages = k_iters < kTStagesFwd ? k_iters : kTStagesFwd;
   const int smem = a.stages * (128 * 128 + bn * 128) + 256 + 2 * bn * 4;
   CVB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   void* kargs[1] = {&a};
-  const dim3 grid((unsigned)(a.tiles_w * a.tiles_h * a.tiles_b), (unsigned)(cout / bn));
+  const dim3 grid((unsigned)(a.tiles_w * a.tiles_h * a.tiles_b), (unsigned)(a.cout / bn));
   CVB_CHECK_CUDA(cudaLaunchKernel(fn, grid, dim3(kTThreads), kargs, (size_t)smem, as_stream(stream)));
   count_launch();
   return CVB_OK;
 }
 
-extern "C" int cvb_train_conv_wgrad(const void* x, const void* dy, int32_t B, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t k, float* dw, void* stream) {
+extern "C" int cvb_train_conv(const void* x, int32_t B, int32_t H, int32_t W, int32_t cin, const void* w_packed, int32_t cout, int32_t k, int32_t stride, void* out,
+                              const void* y_prev, const float* bn_stat_prev, void* stream) {
+  CVB_REQUIRE(x && w_packed && out, "train_conv: null tensor");
+  CVB_REQUIRE((k == 1 || k == 3) && cin % 64 == 0 && cout % 64 == 0 && B > 0 && H > 0 && W > 0, "train_conv: k in {1,3}, channels multiples of 64 (cin=%d cout=%d k=%d)", cin, cout, k);
+  CVB_REQUIRE(stride == 1 || (stride == 2 && k == 3), "train_conv: stride 1, or stride 2 with k = 3");
+  CVB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_packed) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "train_conv: pointers must be 16-byte aligned");
+  CVB_REQUIRE((y_prev == nullptr) == (bn_stat_prev == nullptr), "train_conv: the SiLU' epilogue needs both y_prev and its BN statistics");
+  TConvArgs a;
+  memset(&a, 0, sizeof(a));
+  const int Ho = (H + 2 * (k / 2) - k) / stride + 1, Wo = (W + 2 * (k / 2) - k) / stride + 1;
+  a.H = Ho;
+  a.W = Wo;
+  a.B = B;
+  a.cin = cin;
+  a.cout = cout;
+  a.taps = k * k;
+  a.out = static_cast<__nv_bfloat16*>(out);
+  a.out_H = Ho;
+  a.out_W = Wo;
+  a.os = 1;
+  choose_box128(B, Ho, Wo, &a.TW, &a.TH, &a.NB);
+  int rc = CVB_OK;
+  if (stride == 1) {
+    for (int t = 0; t < k * k; ++t) {
+      a.tap_dh[t] = (int8_t)(t / k - k / 2);
+      a.tap_dw[t] = (int8_t)(t % k - k / 2);
+      a.tap_map[t] = 0;
+      a.tap_wblk[t] = (int8_t)t;
+    }
+    rc = act_map(&a.tmA[0], x, B, H, W, cin, a.TW, a.TH, a.NB);
+  } else {
+    s2_taps(a.tap_dh, a.tap_dw, a.tap_map);
+    for (int t = 0; t < 9; ++t) a.tap_wblk[t] = (int8_t)t;
+    for (int py = 0; py < 2 && rc == CVB_OK; ++py)
+      for (int px = 0; px < 2 && rc == CVB_OK; ++px) rc = act_map_strided(&a.tmA[py * 2 + px], x, B, H, W, cin, 2, py, px, a.TW, a.TH, a.NB);
+  }
+  if (rc != CVB_OK) return rc;
+  return launch_tconv(a, w_packed, k * k, y_prev, bn_stat_prev, stream);
+}
+
+// Backward-data of the 3x3 / stride 2 / pad 1 convolution: dx[2a + pi, 2b + pj] gets dy[a + dh, b + dw] through the taps whose parity matches
+// (pi = 0: ky = 1; pi = 1: ky = 0 (dh = +1) and ky = 2 (dh = 0); same for columns) -- four dense stride-1 sub-convolutions over dy, one per
+// parity class of dx, each writing its class with a strided store.  w_bwd = the [cin][9][cout] operand of cvb_train_pack_weights (taps rotated).
+extern "C" int cvb_train_conv_dgrad_s2(const void* dy, int32_t B, int32_t Ho, int32_t Wo, int32_t cout, const void* w_bwd, int32_t cin, int32_t H, int32_t W, void* dx,
+                                       const void* y_prev, const float* bn_stat_prev, void* stream) {
+  CVB_REQUIRE(dy && w_bwd && dx, "train_conv_dgrad_s2: null tensor");
+  CVB_REQUIRE(cin % 64 == 0 && cout % 64 == 0 && B > 0 && Ho == (H - 1) / 2 + 1 && Wo == (W - 1) / 2 + 1, "train_conv_dgrad_s2: bad geometry");
+  CVB_REQUIRE((y_prev == nullptr) == (bn_stat_prev == nullptr), "train_conv_dgrad_s2: the SiLU' epilogue needs both y_prev and its BN statistics");
+  for (int pi = 0; pi < 2; ++pi)
+    for (int pj = 0; pj < 2; ++pj) {
+      const int Hs = (H - pi + 1) / 2, Ws = (W - pj + 1) / 2;  // pixels of this parity class
+      if (Hs <= 0 || Ws <= 0) continue;
+      TConvArgs a;
+      memset(&a, 0, sizeof(a));
+      a.H = Hs;
+      a.W = Ws;
+      a.B = B;
+      a.cin = cout;  // the GEMM's K: dy channels
+      a.cout = cin;  // the GEMM's N: dx channels
+      a.out = static_cast<__nv_bfloat16*>(dx);
+      a.out_H = H;
+      a.out_W = W;
+      a.os = 2;
+      a.ooh = pi;
+      a.oow = pj;
+      int nt = 0;
+      for (int ky = 0; ky < 3; ++ky) {
+        if (((ky + 1) & 1) != pi) continue;  // rows of parity pi are reached by ky with 2*oh + ky - 1 = ih
+        for (int kx = 0; kx < 3; ++kx) {
+          if (((kx + 1) & 1) != pj) continue;
+          a.tap_dh[nt] = (int8_t)(ky == 0 ? 1 : 0);
+          a.tap_dw[nt] = (int8_t)(kx == 0 ? 1 : 0);
+          a.tap_map[nt] = 0;
+          a.tap_wblk[nt] = (int8_t)(8 - (ky * 3 + kx));  // w_bwd stores tap t of the forward filter at block 8 - t
+          ++nt;
+        }
+      }
+      a.taps = nt;
+      choose_box128(B, Hs, Ws, &a.TW, &a.TH, &a.NB);
+      int rc = act_map(&a.tmA[0], dy, B, Ho, Wo, cout, a.TW, a.TH, a.NB);
+      if (rc != CVB_OK) return rc;
+      rc = launch_tconv(a, w_bwd, 9, y_prev, bn_stat_prev, stream);
+      if (rc != CVB_OK) return rc;
+    }
+  return CVB_OK;
+}
+
+extern "C" int cvb_train_conv_wgrad(const void* x, const void* dy, int32_t B, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t k, int32_t stride, float* dw,
+                                    void* stream) {
   CVB_REQUIRE(x && dy && dw, "train_conv_wgrad: null tensor");
   CVB_REQUIRE((k == 1 || k == 3) && cin % 64 == 0 && (cout == 64 || cout == 128 || cout == 256), "train_conv_wgrad: k in {1,3}, cin %% 64 == 0, cout in {64,128,256}");
+  CVB_REQUIRE(stride == 1 || (stride == 2 && k == 3), "train_conv_wgrad: stride 1, or stride 2 with k = 3");
   CVB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0, "train_conv_wgrad: pointers must be 16-byte aligned");
   TWgradArgs a;
   memset(&a, 0, sizeof(a));
-  choose_box128(B, H, W, &a.TW, &a.TH, &a.NB);
-  a.tiles_w = ceil_div(W, a.TW);
-  a.tiles_h = ceil_div(H, a.TH);
+  const int Ho = (H + 2 * (k / 2) - k) / stride + 1, Wo = (W + 2 * (k / 2) - k) / stride + 1;
+  choose_box128(B, Ho, Wo, &a.TW, &a.TH, &a.NB);
+  a.tiles_w = ceil_div(Wo, a.TW);
+  a.tiles_h = ceil_div(Ho, a.TH);
   a.tiles_b = ceil_div(B, a.NB);
   a.cin = cin;
   a.cout = cout;
   a.taps = k * k;
-  a.kw = k;
-  a.pad = k / 2;
   a.dw = dw;
   const int m_tiles = a.tiles_w * a.tiles_h * a.tiles_b;
   const int cblocks = ceil_div(cin, 128);
@@ -705,8 +803,20 @@ extern "C" int cvb_train_conv_wgrad(const void* x, const void* dy, int32_t B, in
   if (splits < 1) splits = 1;
   if (splits > m_tiles) splits = m_tiles;
   a.splits = splits;
-  int rc = act_map(&a.tmX, x, B, H, W, cin, a.TW, a.TH, a.NB);
-  if (rc == CVB_OK) rc = act_map(&a.tmD, dy, B, H, W, cout, a.TW, a.TH, a.NB);
+  int rc = CVB_OK;
+  if (stride == 1) {
+    for (int t = 0; t < k * k; ++t) {
+      a.tap_dh[t] = (int8_t)(t / k - k / 2);
+      a.tap_dw[t] = (int8_t)(t % k - k / 2);
+      a.tap_map[t] = 0;
+    }
+    rc = act_map(&a.tmX[0], x, B, H, W, cin, a.TW, a.TH, a.NB);
+  } else {
+    s2_taps(a.tap_dh, a.tap_dw, a.tap_map);
+    for (int py = 0; py < 2 && rc == CVB_OK; ++py)
+      for (int px = 0; px < 2 && rc == CVB_OK; ++px) rc = act_map_strided(&a.tmX[py * 2 + px], x, B, H, W, cin, 2, py, px, a.TW, a.TH, a.NB);
+  }
+  if (rc == CVB_OK) rc = act_map(&a.tmD, dy, B, Ho, Wo, cout, a.TW, a.TH, a.NB);
   if (rc != CVB_OK) return rc;
   const int npan = cout / 64;
   const void* fn = npan == 1 ? reinterpret_cast<const void*>(&twgrad_kernel<1>) : (npan == 2 ? reinterpret_cast<const void*>(&twgrad_kernel<2>) : reinterpret_cast<const void*>(&twgrad_kernel<4>));

@@ -43,20 +43,30 @@ def pack_weights(w):
     return wf, wb
 
 
-def conv(x, w_packed, cout, k, y_prev=None, stat_prev=None):
-    """x NHWC bf16 [B,H,W,cin] -> [B,H,W,cout].  (y_prev, stat_prev): SiLU' epilogue of the producing layer (backward-data only)."""
+def conv(x, w_packed, cout, k, y_prev=None, stat_prev=None, stride=1):
+    """x NHWC bf16 [B,H,W,cin] -> [B,Ho,Wo,cout] (pad k//2).  (y_prev, stat_prev): SiLU' epilogue of the producing layer (backward-data only)."""
     B, H, W, cin = x.shape
-    out = torch.empty((B, H, W, cout), dtype=torch.bfloat16, device=x.device)
-    _lib.check(_lib.lib().cvb_train_conv(_p(x), B, H, W, cin, _p(w_packed), cout, k, _p(out), _p(y_prev), _p(stat_prev), _stream()), 'cvb_train_conv')
+    Ho, Wo = (H + 2 * (k // 2) - k) // stride + 1, (W + 2 * (k // 2) - k) // stride + 1
+    out = torch.empty((B, Ho, Wo, cout), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().cvb_train_conv(_p(x), B, H, W, cin, _p(w_packed), cout, k, stride, _p(out), _p(y_prev), _p(stat_prev), _stream()), 'cvb_train_conv')
     return out
 
 
-def conv_wgrad(x, dy, k):
+def conv_dgrad_s2(dy, w_bwd, cin, H, W, y_prev=None, stat_prev=None):
+    """Backward-data of the 3x3 / stride 2 / pad 1 convolution: dy [B,Ho,Wo,cout] -> dx [B,H,W,cin] (four parity sub-convolutions)."""
+    B, Ho, Wo, cout = dy.shape
+    dx = torch.empty((B, H, W, cin), dtype=torch.bfloat16, device=dy.device)
+    _lib.check(_lib.lib().cvb_train_conv_dgrad_s2(_p(dy), B, Ho, Wo, cout, _p(w_bwd), cin, H, W, _p(dx), _p(y_prev), _p(stat_prev), _stream()),
+               'cvb_train_conv_dgrad_s2')
+    return dx
+
+
+def conv_wgrad(x, dy, k, stride=1):
     """-> fp32 [cout, cin, k, k] (the nn.Conv2d layout)."""
     B, H, W, cin = x.shape
     cout = dy.shape[3]
     dw = torch.zeros((cout, k * k, cin), dtype=torch.float32, device=x.device)
-    _lib.check(_lib.lib().cvb_train_conv_wgrad(_p(x), _p(dy), B, H, W, cin, cout, k, _p(dw), _stream()), 'cvb_train_conv_wgrad')
+    _lib.check(_lib.lib().cvb_train_conv_wgrad(_p(x), _p(dy), B, H, W, cin, cout, k, stride, _p(dw), _stream()), 'cvb_train_conv_wgrad')
     return dw.view(cout, k, k, cin).permute(0, 3, 1, 2)
 
 
@@ -64,14 +74,14 @@ class _ConvBnSiLU(torch.autograd.Function):
     """a = silu(bn_train(conv(x, W))) with the backward the reference obtains from torch.autograd, on the B200 kernels."""
 
     @staticmethod
-    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, eps, momentum, k):
+    def forward(ctx, x, weight, gamma, beta, running_mean, running_var, eps, momentum, k, stride=1):
         _check_cuda(x, 'BaseConv (B200 training)')
         B, H, W, cin = x.shape
         cout = weight.shape[0]
         L = _lib.lib()
         wf, wb = pack_weights(weight)
-        y = conv(x, wf, cout, k)
-        npix = B * H * W
+        y = conv(x, wf, cout, k, stride=stride)
+        npix = B * y.shape[1] * y.shape[2]
         stat = torch.empty((4, cout), dtype=torch.float32, device=x.device)
         scratch = torch.empty((2, cout), dtype=torch.float32, device=x.device)
         g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
@@ -81,6 +91,7 @@ class _ConvBnSiLU(torch.autograd.Function):
         _lib.check(L.cvb_train_bn_silu_fwd(_p(y), npix, cout, _p(stat), _p(a), _stream()), 'cvb_train_bn_silu_fwd')
         ctx.save_for_backward(x, y, stat, g32, wb)
         ctx.k = k
+        ctx.stride = stride
         ctx.need_dx = x.requires_grad
         return a
 
@@ -94,10 +105,13 @@ class _ConvBnSiLU(torch.autograd.Function):
         da = da.contiguous()
         sums = torch.empty((2, cout), dtype=torch.float32, device=x.device)
         dy = torch.empty_like(y)
-        _lib.check(L.cvb_train_bn_silu_bwd(_p(da), 0, _p(y), B * H * W, cout, _p(stat), _p(g32), _p(sums), _p(dy), _stream()), 'cvb_train_bn_silu_bwd')
-        dw = conv_wgrad(x, dy, k)
-        dx = conv(dy, wb, cin, k) if ctx.need_dx else None
-        return dx, dw, sums[1].clone(), sums[0].clone(), None, None, None, None, None
+        _lib.check(L.cvb_train_bn_silu_bwd(_p(da), 0, _p(y), B * y.shape[1] * y.shape[2], cout, _p(stat), _p(g32), _p(sums), _p(dy), _stream()),
+                   'cvb_train_bn_silu_bwd')
+        dw = conv_wgrad(x, dy, k, ctx.stride)
+        dx = None
+        if ctx.need_dx:
+            dx = conv(dy, wb, cin, k) if ctx.stride == 1 else conv_dgrad_s2(dy, wb, cin, H, W)
+        return dx, dw, sums[1].clone(), sums[0].clone(), None, None, None, None, None, None
 
 
 class _BottleneckChain(torch.autograd.Function):
@@ -152,18 +166,20 @@ class _BottleneckChain(torch.autograd.Function):
 
 
 class BaseConv(nn.Module):
-    """src/models/modules/yolox_modules.py:35-55 (act='silu', groups=1, stride 1).  forward: NHWC bf16 in -> NHWC bf16 out."""
+    """src/models/modules/yolox_modules.py:35-55 (act='silu', groups=1; stride 1, or stride 2 with ksize 3 = the downsampling conv in front of
+    every CSPLayer of the YOLOX backbone).  forward: NHWC bf16 in -> NHWC bf16 out."""
 
     def __init__(self, in_channels, out_channels, ksize, stride, groups=1, bias=False, act='silu'):
         super().__init__()
-        if stride != 1 or groups != 1 or bias or act != 'silu' or ksize not in (1, 3):
-            raise NotImplementedError('B200 training BaseConv: ksize in {1,3}, stride 1, groups 1, no bias, SiLU (the C3 block)')
+        if not (stride == 1 or (stride == 2 and ksize == 3)) or groups != 1 or bias or act != 'silu' or ksize not in (1, 3):
+            raise NotImplementedError('B200 training BaseConv: ksize in {1,3}, stride 1 (or 2 with ksize 3), groups 1, no bias, SiLU')
         if in_channels % 64 or out_channels % 64:
             raise NotImplementedError('B200 training BaseConv: channel counts must be multiples of 64')
         self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=ksize, stride=stride, padding=(ksize - 1) // 2, groups=groups, bias=bias)
         self.bn = nn.BatchNorm2d(out_channels)
         self.act = nn.SiLU(inplace=True)  # (parameter-free; kept for module-tree parity with the reference)
         self.ksize = ksize
+        self.stride = stride
 
     def forward(self, x):
         if not self.training:
@@ -171,7 +187,12 @@ class BaseConv(nn.Module):
         bn = self.bn
         bn.num_batches_tracked += 1
         mom = bn.momentum if bn.momentum is not None else 1.0 / float(bn.num_batches_tracked)
-        return _ConvBnSiLU.apply(x, self.conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, mom, self.ksize)
+        return _ConvBnSiLU.apply(x, self.conv.weight, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, mom, self.ksize, self.stride)
+
+    def forward_nchw(self, x):
+        """Reference interface (NCHW in / out) for a stand-alone BaseConv, e.g. the stride-2 conv of a `dark` stage."""
+        _check_cuda(x, 'BaseConv (B200 training)')
+        return self.forward(x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)).permute(0, 3, 1, 2).to(x.dtype)
 
 
 class Bottleneck(nn.Module):

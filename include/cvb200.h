@@ -335,7 +335,12 @@ int cvb_coco_pack(const float* rows, int32_t B, int32_t M, int32_t row_stride, c
  * cvb_train_conv: out[B,H,W,cout] = conv(x[B,H,W,cin], w_packed [cout][k*k][cin]).  Forward: (x, w_fwd).  Backward-data: (dy, w_bwd) with
  *   cin/cout swapped.  y_prev / bn_stat_prev != NULL: SiLU' epilogue -- the result is multiplied by silu'(y_prev * scale + shift) of the
  *   layer that produced this conv's input (bn_stat layout below), giving dz of that layer directly.
- * cvb_train_conv_wgrad: dw[cout][k*k][cin] (fp32, ZEROED BY THE CALLER, accumulated with atomics) += sum over pixels of dy x (shifted x).
+ *   stride = 2 (k = 3, pad 1; the downsampling BaseConv in front of every CSPLayer, src/models/backbones/det/csp_darknet.py): the forward
+ *   reads the input through four parity tensor maps, out is [B,(H-1)/2+1,(W-1)/2+1,cout].
+ * cvb_train_conv_dgrad_s2: backward-data of that stride-2 convolution, dx[B,H,W,cin] from dy[B,Ho,Wo,cout] and w_bwd: four dense
+ *   sub-convolutions, one per parity class of dx (1 + 2 + 2 + 4 taps), same optional SiLU' epilogue.
+ * cvb_train_conv_wgrad: dw[cout][k*k][cin] (fp32, ZEROED BY THE CALLER, accumulated with atomics) += sum over pixels of dy x (shifted x);
+ *   x is [B,H,W,cin], dy the conv output's gradient (stride 1: same H, W; stride 2: (H-1)/2+1 etc.).
  * cvb_train_bn_stats: batch mean / biased variance of y over npix = B*H*W -> stat [4][C] fp32 = (mean, rstd, scale = gamma*rstd,
  *   shift = beta - mean*scale); running_mean / running_var (may be NULL) updated like nn.BatchNorm2d (momentum, unbiased variance).
  *   sums_scratch: [2][C] fp32.
@@ -344,9 +349,12 @@ int cvb_coco_pack(const float* rows, int32_t B, int32_t M, int32_t row_stride, c
  *   dy = gamma * rstd * (dz - dbeta / N - xhat * dgamma / N)   (the batch-norm backward of torch.autograd).
  */
 int cvb_train_pack_weights(const float* w, int32_t cout, int32_t cin, int32_t k, void* w_fwd, void* w_bwd, void* stream);
-int cvb_train_conv(const void* x, int32_t B, int32_t H, int32_t W, int32_t cin, const void* w_packed, int32_t cout, int32_t k, void* out,
+int cvb_train_conv(const void* x, int32_t B, int32_t H, int32_t W, int32_t cin, const void* w_packed, int32_t cout, int32_t k, int32_t stride, void* out,
                    const void* y_prev, const float* bn_stat_prev, void* stream);
-int cvb_train_conv_wgrad(const void* x, const void* dy, int32_t B, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t k, float* dw, void* stream);
+int cvb_train_conv_dgrad_s2(const void* dy, int32_t B, int32_t Ho, int32_t Wo, int32_t cout, const void* w_bwd, int32_t cin, int32_t H, int32_t W, void* dx,
+                            const void* y_prev, const float* bn_stat_prev, void* stream);
+int cvb_train_conv_wgrad(const void* x, const void* dy, int32_t B, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t k, int32_t stride, float* dw,
+                         void* stream);
 int cvb_train_bn_stats(const void* y, int64_t npix, int32_t C, const float* gamma, const float* beta, float eps, float momentum, float* running_mean,
                        float* running_var, float* sums_scratch, float* stat, void* stream);
 int cvb_train_bn_silu_fwd(const void* y, int64_t npix, int32_t C, const float* stat, void* out, void* stream);

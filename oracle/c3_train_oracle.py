@@ -16,9 +16,9 @@ BN_EPS = 1e-3        # src/models/yolox.py init: every BatchNorm2d gets eps = 1e
 BN_MOMENTUM = 0.03
 
 
-def base_conv(x, sd, prefix, ksize):
+def base_conv(x, sd, prefix, ksize, stride=1):
     """sd: name -> tensor (weights with requires_grad for the backward; running statistics are updated in place)."""
-    y = F.conv2d(x, sd[prefix + '.conv.weight'], None, 1, (ksize - 1) // 2)
+    y = F.conv2d(x, sd[prefix + '.conv.weight'], None, stride, (ksize - 1) // 2)
     y = F.batch_norm(y, sd[prefix + '.bn.running_mean'], sd[prefix + '.bn.running_var'], sd[prefix + '.bn.weight'], sd[prefix + '.bn.bias'], True,
                      BN_MOMENTUM, BN_EPS)
     return F.silu(y)
@@ -74,3 +74,9 @@ def synthetic_state(cin, cout, n, seed=0):
         conv(f'm.{i}.conv1', hid, hid, 1)
         conv(f'm.{i}.conv2', hid, hid, 3)
     return sd
+
+
+def dark_stage(x, sd, n):
+    """One `dark` stage of the YOLOX CSPDarknet (src/models/backbones/det/csp_darknet.py: nn.Sequential(BaseConv(c, 2c, 3, 2), CSPLayer(2c, 2c, n))):
+    keys '0.*' = the stride-2 BaseConv, '1.*' = the CSPLayer."""
+    return csp_layer(base_conv(x, sd, '0', 3, 2), sd, n, prefix='1')

@@ -324,3 +324,5 @@ def test_training_dropin_mirrors_reference_block_and_fails_loudly_on_cpu():
         m.conv1(torch.zeros(1, 8, 8, 128, dtype=torch.bfloat16))
     with pytest.raises(NotImplementedError):
         T.BaseConv(48, 64, 1, 1)
+    with pytest.raises(NotImplementedError):
+        T.BaseConv(64, 64, 1, 2)  # stride 2 only with ksize 3

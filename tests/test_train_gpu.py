@@ -155,3 +155,64 @@ def test_c3_dropin_through_the_reference_trainer_train_step(cuda):
         optimizer.zero_grad(set_to_none=True)
         hist.append(float(losses['loss']))
     assert all(np.isfinite(hist)) and hist[-1] < 0.7 * hist[0], hist
+
+
+@pytest.mark.parametrize('B,H,W,cin,cout', [(2, 16, 16, 64, 64), (2, 13, 9, 64, 128), (3, 26, 18, 128, 64), (1, 7, 30, 64, 128)])
+def test_stride2_conv_forward_backward_data_backward_weight(cuda, B, H, W, cin, cout):
+    """3x3 / stride 2 / pad 1 (the downsampling BaseConv of every dark stage): forward through four parity tensor maps, backward-data as four
+    parity sub-convolutions (with and without the SiLU' epilogue), backward-weight -- vs torch on bf16-representable inputs, odd sizes included."""
+    from cvpytorch_b200 import train as T
+    g = torch.Generator().manual_seed(B * 31 + H + W + cin)
+    x = _bf(torch.randn(B, cin, H, W, generator=g)).cuda().requires_grad_(True)
+    w = _bf(torch.randn(cout, cin, 3, 3, generator=g) / (cin * 9) ** 0.5).cuda().requires_grad_(True)
+    y_ref = F.conv2d(x, w, None, 2, 1)
+    dy = _bf(torch.randn(y_ref.shape, generator=g)).cuda()
+    y_ref.backward(dy)
+    xh = x.detach().permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    dyh = dy.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16)
+    wf, wb = T.pack_weights(w.detach())
+    y = T.conv(xh, wf, cout, 3, stride=2)
+    assert tuple(y.shape) == (B, y_ref.shape[2], y_ref.shape[3], cout)
+    dx = T.conv_dgrad_s2(dyh, wb, cin, H, W)
+    dw = T.conv_wgrad(xh, dyh, 3, stride=2)
+    torch.cuda.synchronize()
+    e = dict(y=_rel(y.float().permute(0, 3, 1, 2), y_ref), dx=_rel(dx.float().permute(0, 3, 1, 2), x.grad), dw=_rel(dw, w.grad))
+    print(e)
+    assert e['y'] < 6e-3 and e['dx'] < 6e-3 and e['dw'] < 2e-3, e
+    # SiLU' epilogue on the strided stores
+    yp = _bf(torch.randn(B, H, W, cin, generator=g)).cuda().to(torch.bfloat16)
+    stat = torch.stack([torch.zeros(cin), torch.ones(cin), torch.rand(cin, generator=g) + 0.5, torch.randn(cin, generator=g) * 0.2]).cuda().contiguous()
+    fused = T.conv_dgrad_s2(dyh, wb, cin, H, W, y_prev=yp, stat_prev=stat).float()
+    z = yp.float() * stat[2] + stat[3]
+    sg = torch.sigmoid(z)
+    torch.cuda.synchronize()
+    assert _rel(fused, dx.float() * (sg * (1 + z * (1 - sg)))) < 8e-3
+
+
+def test_dark_stage_training_step_vs_reference_fixture(cuda):
+    """stride-2 BaseConv + CSPLayer (one `dark` stage) forward + backward vs the reference modules + torch.autograd (fixture case 'dark')."""
+    from cvpytorch_b200 import train as T
+    g = np.load(os.path.join(GOLD, 'c3_train.npz'))
+    down, csp = T.BaseConv(64, 128, 3, 2), T.CSPLayer(128, 128, n=1)
+    m = torch.nn.Sequential(down, csp)
+    keys = [str(k) for k in g['dark_keys']]
+    assert list(m.state_dict().keys()) == keys
+    m.load_state_dict({k: torch.from_numpy(g[f'dark_sd_{k}']) for k in keys})
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.eps, mod.momentum = 1e-3, 0.03
+    m.cuda().train()
+    x = torch.from_numpy(g['dark_x']).cuda().requires_grad_(True)
+    G = torch.from_numpy(g['dark_G']).cuda()
+    y = csp.forward_nhwc(down(x.permute(0, 2, 3, 1).contiguous().to(torch.bfloat16))).permute(0, 3, 1, 2).float()
+    (y * G).sum().backward()
+    torch.cuda.synchronize()
+    errs = {'y': _rel(y, torch.from_numpy(g['dark_y'])), 'dx': _rel(x.grad, torch.from_numpy(g['dark_dx']))}
+    for k, p in m.named_parameters():
+        errs['grad ' + k] = _rel(p.grad, torch.from_numpy(g[f'dark_grad_{k}']))
+    for k, v in m.state_dict().items():
+        if 'running_' in k:
+            errs['after ' + k] = _rel(v, torch.from_numpy(g[f'dark_after_{k}']))
+    print({k: round(v, 4) for k, v in errs.items()})
+    assert errs['y'] < 3e-2 and errs['dx'] < 6e-2 and max(v for k, v in errs.items() if k.startswith('grad ')) < 6e-2, errs
+    assert max(v for k, v in errs.items() if k.startswith('after ')) < 1e-2, errs

@@ -58,6 +58,33 @@ def main():
             if 'running_' in k:
                 out[f'{name}_after_{k}'] = v.numpy()
         print(name, 'x', tuple(x.shape), 'y std', float(y.std()), 'dx std', float(x.grad.std()), 'params', sum(1 for _ in m.parameters()))
+    # one `dark` stage: stride-2 BaseConv in front of a CSPLayer (the structure of every stage of src/models/backbones/det/csp_darknet.py:57-91),
+    # odd map sizes (26x18 -> 13x9) so that the stride-2 parity classes are ragged
+    from src.models.modules.yolox_modules import BaseConv
+    torch.manual_seed(77)
+    m = torch.nn.Sequential(BaseConv(64, 128, 3, 2), CSPLayer(128, 128, n=1))
+    randomize(m, 78)
+    m.train()
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    x = torch.randn(2, 64, 26, 18, generator=torch.Generator().manual_seed(79), requires_grad=True)
+    y = m(x)
+    G = torch.randn(y.shape, generator=torch.Generator().manual_seed(80))
+    (y * G).sum().backward()
+    name = 'dark'
+    out[f'{name}_cfg'] = np.array([64, 128, 1, 2, 26, 18])
+    out[f'{name}_keys'] = np.array(list(sd0.keys()))
+    for k, v in sd0.items():
+        out[f'{name}_sd_{k}'] = v.numpy()
+    out[f'{name}_x'] = x.detach().numpy()
+    out[f'{name}_G'] = G.numpy()
+    out[f'{name}_y'] = y.detach().numpy()
+    out[f'{name}_dx'] = x.grad.numpy()
+    for k, p in m.named_parameters():
+        out[f'{name}_grad_{k}'] = p.grad.numpy()
+    for k, v in m.state_dict().items():
+        if 'running_' in k:
+            out[f'{name}_after_{k}'] = v.numpy()
+    print(name, 'x', tuple(x.shape), 'y', tuple(y.shape), 'y std', float(y.std()), 'dx std', float(x.grad.std()))
     np.savez_compressed(os.path.join(ROOT, 'tests/golden/c3_train.npz'), **out)
 
 

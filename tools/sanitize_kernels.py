@@ -117,6 +117,12 @@ for (Bt, Ht, Wt, ci, co, kk) in ((1, 8, 16, 64, 64, 1), (2, 9, 7, 128, 64, 3), (
     TR.conv(xt, wf_, co, kk)
     TR.conv(dyt, wb_, ci, kk)
     TR.conv_wgrad(xt, dyt, kk)
+for (Bt, Ht, Wt, ci, co) in ((1, 9, 14, 64, 64), (2, 8, 8, 64, 128)):  # stride 2: parity maps, four backward-data sub-convolutions
+    xt = torch.randn(Bt, Ht, Wt, ci, device='cuda').to(torch.bfloat16)
+    wf_, wb_ = TR.pack_weights(torch.randn(co, ci, 3, 3, device='cuda') * 0.05)
+    yt = TR.conv(xt, wf_, co, 3, stride=2)
+    TR.conv_dgrad_s2(yt, wb_, ci, Ht, Wt)
+    TR.conv_wgrad(xt, yt, 3, stride=2)
 mt = TR.CSPLayer(128, 128, n=1).cuda().train()
 xt = torch.randn(1, 128, 8, 8, device='cuda', requires_grad=True)
 mt(xt).sum().backward()
