@@ -229,6 +229,7 @@ struct alignas(64) TWgradArgs {
   int tiles_w, tiles_h, tiles_b;  // over the OUTPUT pixels (dy)
   int TW, TH, NB;
   int cin, cout, taps;
+  int nblocks;  // cout / (64 * NPAN): output-channel blocks of one launch (cout = 512 runs as two 256-wide blocks), folded into blockIdx.z
   int8_t tap_dh[9], tap_dw[9], tap_map[9];
   int splits;
   float* dw;  // [cout][taps][cin] fp32, accumulated with atomics (zeroed by the caller)
@@ -274,7 +275,7 @@ __global__ void __launch_bounds__(kTThreads, 1) twgrad_kernel(const __grid_const
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int split = blockIdx.x, tap = blockIdx.y, c0 = blockIdx.z * 128;
+  const int split = blockIdx.x, tap = blockIdx.y, c0 = ((int)blockIdx.z / a.nblocks) * 128, n0 = ((int)blockIdx.z % a.nblocks) * N;
   const int m_pan = (a.cin - c0) >= 128 ? 2 : 1;  // valid 64-channel panels of this cin block
   const int dh = a.tap_dh[tap], dw_ = a.tap_dw[tap];
   const CUtensorMap* mapX = &a.tmX[a.tap_map[tap]];
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(kTThreads, 1) twgrad_kernel(const __grid_const
         mbar_expect_tx(&full[stage], (uint32_t)(m_pan * PANEL + D_BYTES));
         uint8_t* sb = smem + stage * STAGE;
         for (int p = 0; p < m_pan; ++p) tma_load_4d(mapX, &full[stage], sb + p * PANEL, c0 + p * 64, w0 + dw_, h0 + dh, b0);
-        for (int p = 0; p < NPAN; ++p) tma_load_4d(&a.tmD, &full[stage], sb + X_BYTES + p * PANEL, p * 64, w0, h0, b0);
+        for (int p = 0; p < NPAN; ++p) tma_load_4d(&a.tmD, &full[stage], sb + X_BYTES + p * PANEL, n0 + p * 64, w0, h0, b0);
         if (++stage == STAGES) {
           stage = 0;
           phase ^= 1;
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__(kTThreads, 1) twgrad_kernel(const __grid_const
       if (valid) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)  // lanes = consecutive cin: one coalesced 128-byte reduction per (cout, tap)
-          atomicAdd(a.dw + ((size_t)(c + j) * a.taps + tap) * a.cin + c0 + row, __uint_as_float(v[j]));
+          atomicAdd(a.dw + ((size_t)(n0 + c + j) * a.taps + tap) * a.cin + c0 + row, __uint_as_float(v[j]));
       }
     }
   }
@@ -783,7 +784,7 @@ extern "C" int cvb_train_conv_dgrad_s2(const void* dy, int32_t B, int32_t Ho, in
 extern "C" int cvb_train_conv_wgrad(const void* x, const void* dy, int32_t B, int32_t H, int32_t W, int32_t cin, int32_t cout, int32_t k, int32_t stride, float* dw,
                                     void* stream) {
   CVB_REQUIRE(x && dy && dw, "train_conv_wgrad: null tensor");
-  CVB_REQUIRE((k == 1 || k == 3) && cin % 64 == 0 && (cout == 64 || cout == 128 || cout == 256), "train_conv_wgrad: k in {1,3}, cin %% 64 == 0, cout in {64,128,256}");
+  CVB_REQUIRE((k == 1 || k == 3) && cin % 64 == 0 && (cout == 64 || cout == 128 || cout % 256 == 0), "train_conv_wgrad: k in {1,3}, cin %% 64 == 0, cout in {64, 128, multiples of 256}");
   CVB_REQUIRE(stride == 1 || (stride == 2 && k == 3), "train_conv_wgrad: stride 1, or stride 2 with k = 3");
   CVB_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy)) & 15) == 0, "train_conv_wgrad: pointers must be 16-byte aligned");
   TWgradArgs a;
@@ -799,7 +800,9 @@ extern "C" int cvb_train_conv_wgrad(const void* x, const void* dy, int32_t B, in
   a.dw = dw;
   const int m_tiles = a.tiles_w * a.tiles_h * a.tiles_b;
   const int cblocks = ceil_div(cin, 128);
-  int splits = (2 * num_sms()) / (a.taps * cblocks);  // ~two waves of CTAs: (split, tap, cin block)
+  const int npan = cout >= 256 ? 4 : cout / 64;
+  a.nblocks = cout / (64 * npan);
+  int splits = (2 * num_sms()) / (a.taps * cblocks * a.nblocks);  // ~two waves of CTAs: (split, tap, cin block x cout block)
   if (splits < 1) splits = 1;
   if (splits > m_tiles) splits = m_tiles;
   a.splits = splits;
@@ -818,14 +821,13 @@ extern "C" int cvb_train_conv_wgrad(const void* x, const void* dy, int32_t B, in
   }
   if (rc == CVB_OK) rc = act_map(&a.tmD, dy, B, Ho, Wo, cout, a.TW, a.TH, a.NB);
   if (rc != CVB_OK) return rc;
-  const int npan = cout / 64;
   const void* fn = npan == 1 ? reinterpret_cast<const void*>(&twgrad_kernel<1>) : (npan == 2 ? reinterpret_cast<const void*>(&twgrad_kernel<2>) : reinterpret_cast<const void*>(&twgrad_kernel<4>));
   const int stages = npan == 4 ? 2 : kTStagesWg;
   const int smem = stages * ((2 + npan) * 128 * 128) + 256;
   CVB_REQUIRE(smem <= 232448, "train_conv_wgrad: cout=%d needs %d bytes of shared memory", cout, smem);
   CVB_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   void* kargs[1] = {&a};
-  const dim3 grid((unsigned)splits, (unsigned)a.taps, (unsigned)cblocks);
+  const dim3 grid((unsigned)splits, (unsigned)a.taps, (unsigned)(cblocks * a.nblocks));
   CVB_CHECK_CUDA(cudaLaunchKernel(fn, grid, dim3(kTThreads), kargs, (size_t)smem, as_stream(stream)));
   count_launch();
   return CVB_OK;

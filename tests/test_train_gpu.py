@@ -25,7 +25,7 @@ def _bf(t):
     return t.to(torch.bfloat16).float()
 
 
-@pytest.mark.parametrize('B,H,W,cin,cout,k', [(2, 16, 16, 64, 64, 1), (3, 20, 20, 128, 64, 3), (2, 13, 9, 64, 128, 3), (1, 40, 40, 128, 128, 1), (5, 8, 8, 256, 64, 1)])
+@pytest.mark.parametrize('B,H,W,cin,cout,k', [(2, 16, 16, 64, 64, 1), (3, 20, 20, 128, 64, 3), (2, 13, 9, 64, 128, 3), (1, 40, 40, 128, 128, 1), (5, 8, 8, 256, 64, 1), (2, 10, 10, 256, 512, 1), (1, 12, 12, 512, 256, 3)])  # (incl. the 256 / 512-channel layers of dark4 / dark5)
 def test_conv_forward_backward_data_backward_weight(cuda, B, H, W, cin, cout, k):
     from cvpytorch_b200 import train as T
     g = torch.Generator().manual_seed(B * 100 + H + cin + k)
@@ -216,3 +216,35 @@ def test_dark_stage_training_step_vs_reference_fixture(cuda):
     print({k: round(v, 4) for k, v in errs.items()})
     assert errs['y'] < 3e-2 and errs['dx'] < 6e-2 and max(v for k, v in errs.items() if k.startswith('grad ')) < 6e-2, errs
     assert max(v for k, v in errs.items() if k.startswith('after ')) < 1e-2, errs
+
+
+@pytest.mark.parametrize('c,n,shortcut', [(256, 1, True), (512, 1, False)])
+def test_wider_c3_blocks_vs_oracle(cuda, c, n, shortcut):
+    """dark4 / dark5 widths (256 / 512 channels; dark5 has shortcut=False): the drop-in vs the oracle's training step (reference block restated,
+    torch.autograd, fp32 on the host) on seeded parameters -- same tolerances as the fixture test."""
+    from cvpytorch_b200 import train as T
+    from oracle import c3_train_oracle as CO
+    sd = CO.synthetic_state(c, c, n, seed=c)
+    g = torch.Generator().manual_seed(c + 1)
+    x = torch.randn(2, c, 10, 12, generator=g)
+    G = torch.randn(2, c, 10, 12, generator=g)
+    sdt = {k: torch.as_tensor(v).clone().requires_grad_(True) if (torch.as_tensor(v).dtype.is_floating_point and 'running_' not in k) else torch.as_tensor(v).clone()
+           for k, v in sd.items()}
+    xr = x.clone().requires_grad_(True)
+    yr = CO.csp_layer(xr, sdt, n, shortcut=shortcut)
+    (yr * G).sum().backward()
+    m = T.CSPLayer(c, c, n=n, shortcut=shortcut)
+    m.load_state_dict({k: torch.as_tensor(v) for k, v in sd.items()})
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.BatchNorm2d):
+            mod.eps, mod.momentum = CO.BN_EPS, CO.BN_MOMENTUM
+    m.cuda().train()
+    xg = x.cuda().requires_grad_(True)
+    y = m(xg)
+    (y * G.cuda()).sum().backward()
+    torch.cuda.synchronize()
+    errs = {'y': _rel(y, yr), 'dx': _rel(xg.grad, xr.grad)}
+    for k, p in m.named_parameters():
+        errs['grad ' + k] = _rel(p.grad, sdt[k].grad)
+    print({k: round(v, 4) for k, v in errs.items()})
+    assert errs['y'] < 3e-2 and errs['dx'] < 6e-2 and max(v for k, v in errs.items() if k.startswith('grad ')) < 6e-2, errs
