@@ -326,3 +326,20 @@ def test_training_dropin_mirrors_reference_block_and_fails_loudly_on_cpu():
         T.BaseConv(48, 64, 1, 1)
     with pytest.raises(NotImplementedError):
         T.BaseConv(64, 64, 1, 2)  # stride 2 only with ksize 3
+
+
+def test_training_c_abi_rejects_bad_arguments_before_touching_the_device():
+    """cvb_train_* entry points validate their arguments on the host (no GPU needed) and report through cvb_last_error_string()."""
+    import ctypes
+    from cvpytorch_b200 import _lib
+    L = _lib.lib()
+    one = ctypes.c_void_p(16)  # any non-null, 16-byte aligned value: the checks below fail before it is dereferenced
+    assert L.cvb_train_conv(one, 1, 8, 8, 48, one, 64, 1, 1, one, None, None, None) != 0      # cin not a multiple of 64
+    assert b'multiples of 64' in L.cvb_last_error_string()
+    assert L.cvb_train_conv(one, 1, 8, 8, 64, one, 64, 1, 2, one, None, None, None) != 0      # stride 2 needs k = 3
+    assert b'stride' in L.cvb_last_error_string()
+    assert L.cvb_train_conv(one, 1, 8, 8, 64, one, 64, 3, 1, one, one, None, None) != 0       # SiLU' epilogue needs both operands
+    assert L.cvb_train_conv_wgrad(one, one, 1, 8, 8, 64, 192, 3, 1, one, None) != 0          # unsupported cout
+    assert L.cvb_train_conv_dgrad_s2(one, 1, 5, 5, 64, one, 64, 8, 8, one, None, None, None) != 0  # Ho != (H - 1) / 2 + 1
+    assert b'geometry' in L.cvb_last_error_string()
+    assert L.cvb_train_pack_weights(one, 64, 64, 5, one, one, None) != 0                      # k in {1, 3}
